@@ -1,0 +1,140 @@
+"""Oracle vs the fixtures produced by the reference's own code (oracle/make_golden.py)."""
+import math
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import docking_oracle as O
+from deeplocalproteindocking_b200 import rotations as rot
+
+
+def _load(golden_dir, name):
+    return torch.load(os.path.join(golden_dir, name), weights_only=False)
+
+
+def test_rotation_matrices_match_reference(golden_dir):
+    g = _load(golden_dir, "rotations.pt")
+    for inc, rec in g.items():
+        R = rot.Rotations(angle_inc=inc).R
+        assert R.shape == (rec["n"], 3, 3) and R.dtype == torch.float64
+        assert torch.equal(R[rec["idx"]], rec["R"]) or torch.allclose(R[rec["idx"]], rec["R"], rtol=0, atol=1e-15)
+        ang = rot.soi_euler_angles(inc)
+        for i in rec["idx"][:5].tolist():
+            assert torch.allclose(O.euler_to_matrix(*ang[i]), rec["R"][rec["idx"].tolist().index(i)], atol=1e-15)
+
+
+def test_rotation_sets_sizes_and_orthonormality():
+    for inc, n in rot.SOI_SIZES.items():
+        if inc == 4:
+            continue
+        R = rot.Rotations(inc).R
+        assert R.shape[0] == n
+        eye = torch.eye(3, dtype=torch.float64)
+        assert (R @ R.transpose(1, 2) - eye).abs().max() < 1e-14
+        assert (torch.linalg.det(R) - 1).abs().max() < 1e-14
+
+
+def test_surrogate_oim04_is_deterministic_and_well_formed(tmp_path):
+    a = rot.soi_euler_angles(4)
+    assert a.shape == (232020, 3)
+    assert np.array_equal(a, rot.soi_euler_angles(4))
+    assert np.all(a[:90, 1] == a[0, 1]) and np.all(a[:90, 2] == a[0, 2])
+    assert abs(a[1, 0] - a[0, 0] - math.radians(4)) < 2e-6
+    p = tmp_path / "oim04.eul"
+    rot.write_eul(str(p), a[:180])
+    assert np.array_equal(rot.read_eul(str(p)), a[:180])
+    r = rot.Rotations(str(p))
+    assert r.R.shape == (180, 3, 3)
+
+
+def test_eul_text_roundtrip_is_exact(tmp_path):
+    a = rot.soi_euler_angles(20)
+    p = tmp_path / "oim20.eul"
+    rot.write_eul(str(p), a)
+    lines = open(p).read().splitlines()
+    assert lines[0] == "-3.141593\t 2.396246\t -0.706115"
+    assert len(lines) == 1854
+
+
+def test_unknown_set_raises():
+    with pytest.raises(Exception):
+        rot.Rotations(7)
+    with pytest.raises(Exception):
+        rot.Rotations("/nonexistent/oim99.eul")
+
+
+def test_correlation_matches_multiply_volumes(golden_dir):
+    g = _load(golden_dir, "correlation.pt")
+    v1, v2 = g["v1"], g["v2"]
+    L = v1.shape[-1]
+    N = 2 * L
+    corr = O.correlate(v1[None], v2[None])[0]
+    for d, val in zip(g["d"].tolist(), g["values"]):
+        t = [a % N for a in d]
+        assert torch.allclose(corr[:, t[0], t[1], t[2]], val, rtol=0, atol=1e-11)
+        assert torch.allclose(O.correlate_direct(v1, v2, d), val, rtol=0, atol=1e-12)
+    # the plane d = -L (index L) has no overlap
+    assert corr[:, L].abs().max() < 1e-11 and corr[:, :, L].abs().max() < 1e-11 and corr[:, :, :, L].abs().max() < 1e-11
+
+
+def test_global_model_matches_reference(golden_dir):
+    g = _load(golden_dir, "global_model.pt")
+    filt = O.FilterWeights(g["W1"], g["b1"], g["W2"], g["b2"])
+    V = O.global_score(g["rec"], g["lig"], filt)[0]
+    assert torch.allclose(V, g["V_global"], rtol=0, atol=1e-10)
+    # LocalDockingModel pins the same filter on direct sums: equal for even translations and positive odd ones
+    N = V.shape[0]
+    for T, y in zip(g["T"].tolist(), g["y_local"]):
+        d = [int(t) for t in T]
+        if all(a % 2 == 0 or a > 0 for a in d):
+            assert abs(V[d[0] % N, d[1] % N, d[2] % N] - y) < 1e-9, (d,)
+
+
+def test_update_top_matches_reference(golden_dir):
+    cases = _load(golden_dir, "update_top.pt")
+    for c in cases:
+        K = c["K"]
+        for fn in (O.update_top_literal, O.update_top_fast):
+            items = [(3, x, y, z, s) for x, y, z, s in fn(c["V"], K)]
+            top = O.merge_top([], items, K)
+            assert top == c["after_first"], (c["kind"], fn.__name__)
+            items = [(5, x, y, z, s) for x, y, z, s in fn(c["V2"], K)]
+            top = O.merge_top(top, items, K)
+            assert top == c["after_second"], (c["kind"], fn.__name__)
+        s, x, y, z = O.best_pose(c["V"])
+        assert (x, y, z) == tuple(O.update_top_literal(c["V"], 1)[0][:3])
+
+
+def test_update_top_fast_equals_literal_randomised():
+    g = torch.Generator().manual_seed(11)
+    for trial in range(30):
+        V = torch.randn(5, 6, 7, generator=g)
+        mode = trial % 5
+        if mode == 0:
+            V = V * (torch.rand(5, 6, 7, generator=g) < 0.5).float()
+        elif mode == 1:
+            V = V.abs() + 0.01
+        elif mode == 2:
+            V = torch.round(V)
+        elif mode == 3:
+            V = V.abs(); V[2, 3, 4] = -0.0
+        for K in (1, 7, 40, 250):
+            assert O.update_top_fast(V, K) == O.update_top_literal(V, K), (trial, K)
+
+
+def test_conformation_text_matches_reference(golden_dir):
+    g = _load(golden_dir, "conformations.pt")
+    R20 = rot.Rotations(20).R
+    for key in ("plain", "rand"):
+        rec = g[key]
+        lines = []
+        for i, x, y, z, s in rec["top_list"]:
+            t = torch.tensor(O.index_to_translation((x, y, z), 80, 1.25), dtype=torch.float64)
+            r = R20[i]
+            if rec["randR"] is not None:
+                rt = rec["randR"][0].t()
+                t, r = rt @ t, rt @ r
+            lines.append(O.format_conformation(r, t.tolist(), s))
+        assert "".join(lines) == rec["text"]
