@@ -1,0 +1,67 @@
+"""ctypes binding of the C ABI in `include/dlpd.h` (libdlpd.so, hand-written sm_100a CUDA).
+
+There is no CPU fallback: `get_lib()` raises if the in-tree shared library is missing or cannot be
+loaded, and every operator in this package goes through it.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_void_p
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libdlpd.so")
+
+# name -> (restype, argtypes); mirrors include/dlpd.h one to one
+SIGNATURES = {
+    "dlpd_version": (c_int, []),
+    "dlpd_last_error": (c_char_p, []),
+    "dlpd_search_supported": (c_int, [c_int, c_int, c_int, c_int]),
+    "dlpd_op_supported": (c_int, [c_int]),
+    "dlpd_plan_create": (c_int, [POINTER(c_void_p), c_int, c_int, c_int, c_int, c_int, c_int, c_int]),
+    "dlpd_plan_destroy": (c_int, [c_void_p]),
+    "dlpd_plan_bytes": (c_longlong, [c_void_p]),
+    "dlpd_set_receptor": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dlpd_set_ligand": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "dlpd_set_filter": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_float), POINTER(c_float)]),
+    "dlpd_search": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "dlpd_search_host": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
+    "dlpd_volume_rotate": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
+    "dlpd_volume_correlate": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
+}
+
+CENTER_MODES = {"box": 0, "grid": 1}
+
+
+class DlpdError(RuntimeError):
+    pass
+
+
+def bind_signatures(cdll: ctypes.CDLL) -> ctypes.CDLL:
+    """Attach restype/argtypes for every symbol of include/dlpd.h; raises AttributeError if one is missing."""
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(cdll, name)
+        fn.restype = res
+        fn.argtypes = args
+    return cdll
+
+
+def check(cdll: ctypes.CDLL, rc: int) -> None:
+    """Error convention of the reference is a bare `raise Exception(...)` (Rotations.py:41); we raise DlpdError."""
+    if rc != 0:
+        msg = cdll.dlpd_last_error()
+        raise DlpdError("libdlpd error %d: %s" % (rc, msg.decode() if msg else "?"))
+
+
+_lib = None
+
+
+def get_lib() -> ctypes.CDLL:
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise DlpdError(
+                "libdlpd.so not found at %s -- build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+        _lib = bind_signatures(ctypes.CDLL(LIB_PATH))
+    return _lib

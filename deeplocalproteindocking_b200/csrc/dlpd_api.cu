@@ -1,0 +1,459 @@
+// Host side of libdlpd.so: the C ABI declared in include/dlpd.h, kernel launchers and workspace management.
+// Built by nvcc for sm_100a (product).  The same file compiles with `g++ -x c++ -DDLPD_EMU` into the
+// host emulation used by tests/emu (TEST INFRASTRUCTURE: never loaded by the package).
+#include "dlpd_kernels.h"
+#include "../../include/dlpd.h"
+
+#include <stdio.h>
+#include <stdlib.h>
+#include <map>
+#include <string>
+#include <vector>
+
+// ------------------------------------------------------------------------------------------------------
+// runtime shim
+// ------------------------------------------------------------------------------------------------------
+static thread_local std::string g_err;
+static int fail(int code, const std::string& msg) {
+    g_err = msg;
+    return code;
+}
+
+#if defined(DLPD_EMU)
+struct dim3 {
+    unsigned x, y, z;
+    dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
+};
+static int rt_set_device(int) { return 0; }
+static int rt_malloc(void** p, size_t n) { *p = calloc(n ? n : 1, 1); return *p ? 0 : fail(DLPD_ECUDA, "emu: out of memory"); }
+static int rt_malloc_host(void** p, size_t n) { return rt_malloc(p, n); }
+static void rt_free(void* p) { free(p); }
+static void rt_free_host(void* p) { free(p); }
+static int rt_copy(void* d, const void* s, size_t n, int, dlpd_stream_t) { memcpy(d, s, n); return 0; }
+static int rt_memset(void* d, int v, size_t n, dlpd_stream_t) { memset(d, v, n); return 0; }
+static int rt_sync(dlpd_stream_t) { return 0; }
+enum { H2D = 0, D2H = 1, D2D = 2 };
+template <class K> static int launch(dim3 g, const typename K::Params& p, dlpd_stream_t) {
+    std::vector<char> smem((size_t)K::SMEM + 16);
+    for (unsigned z = 0; z < g.z; ++z)
+        for (unsigned y = 0; y < g.y; ++y)
+            for (unsigned x = 0; x < g.x; ++x) K::body(p, (int)x, (int)y, (int)z, smem.data());
+    return 0;
+}
+#else
+#define CU(call)                                                                                     \
+    do {                                                                                             \
+        cudaError_t e_ = (call);                                                                     \
+        if (e_ != cudaSuccess)                                                                       \
+            return fail(DLPD_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
+    } while (0)
+static int rt_set_device(int d) { CU(cudaSetDevice(d)); return 0; }
+static int rt_malloc(void** p, size_t n) { CU(cudaMalloc(p, n ? n : 1)); return 0; }
+static int rt_malloc_host(void** p, size_t n) { CU(cudaMallocHost(p, n ? n : 1)); return 0; }
+static void rt_free(void* p) { if (p) cudaFree(p); }
+static void rt_free_host(void* p) { if (p) cudaFreeHost(p); }
+enum { H2D = 0, D2H = 1, D2D = 2 };
+static int rt_copy(void* d, const void* s, size_t n, int kind, dlpd_stream_t st) {
+    cudaMemcpyKind k = kind == H2D ? cudaMemcpyHostToDevice : kind == D2H ? cudaMemcpyDeviceToHost : cudaMemcpyDeviceToDevice;
+    CU(cudaMemcpyAsync(d, s, n, k, st));
+    return 0;
+}
+static int rt_memset(void* d, int v, size_t n, dlpd_stream_t st) { CU(cudaMemsetAsync(d, v, n, st)); return 0; }
+static int rt_sync(dlpd_stream_t st) { CU(cudaStreamSynchronize(st)); return 0; }
+
+template <class K>
+__global__ void __launch_bounds__(K::NT) dlpd_kernel(const __grid_constant__ typename K::Params p) {
+    extern __shared__ __align__(16) char smem[];
+    K::body(p, blockIdx.x, blockIdx.y, blockIdx.z, smem);
+}
+template <class K> static int launch(dim3 g, const typename K::Params& p, dlpd_stream_t st) {
+    static bool configured[64] = {};
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (dev < 64 && !configured[dev]) {
+        if (K::SMEM > 48 * 1024)
+            CU(cudaFuncSetAttribute(dlpd_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+        configured[dev] = true;
+    }
+    dlpd_kernel<K><<<g, K::NT, K::SMEM, st>>>(p);
+    CU(cudaGetLastError());
+    return 0;
+}
+#endif
+
+#define TRY(call)                  \
+    do {                           \
+        int rc_ = (call);          \
+        if (rc_ != 0) return rc_;  \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------------------
+// compiled sizes
+// ------------------------------------------------------------------------------------------------------
+template <int L> struct Tile {
+    static constexpr int FWD_YT = (L > 40) ? 40 : L;      // y lines per FwdZ CTA
+    static constexpr int INV_YT = ((2 * L) % 8 == 0) ? 8 : (((2 * L) % 4 == 0) ? 4 : 2);
+};
+
+// box sizes the single-level kernels are compiled for
+#define DLPD_OP_SIZES(X) X(4) X(8) X(10) X(16) X(20) X(40) X(80)
+// (L, C0, C1, H) the fused search is compiled for
+#define DLPD_SEARCH_CONFIGS(X) \
+    X(8, 4, 6, 5) X(16, 4, 6, 5) X(20, 4, 6, 5) X(8, 16, 32, 24) X(16, 16, 32, 24) X(20, 16, 32, 24) X(80, 16, 32, 24)
+
+static bool op_size_ok(int L) {
+    switch (L) {
+#define X(L_) case L_:
+        DLPD_OP_SIZES(X)
+#undef X
+        return true;
+    }
+    return false;
+}
+
+// twiddle table e^{+2 pi i k / n}, computed in double
+static int make_twiddles(cpx** dev, int n, dlpd_stream_t st) {
+    std::vector<cpx> h(n);
+    for (int k = 0; k < n; ++k) {
+        const double a = 2.0 * M_PI * (double)k / (double)n;
+        h[k] = make_float2((float)cos(a), (float)sin(a));
+    }
+    TRY(rt_malloc((void**)dev, sizeof(cpx) * n));
+    TRY(rt_copy(*dev, h.data(), sizeof(cpx) * n, H2D, st));
+    TRY(rt_sync(st));
+    return 0;
+}
+
+static float center_of(int L, int mode) { return mode == DLPD_CENTER_GRID ? 0.5f * (float)(L - 1) : 0.5f * (float)L; }
+
+// ---- single-level launch helpers (dispatch on L) -----------------------------------------------------------
+template <int L> static int launch_fwdz_t(const FwdZParams& p, int P, dlpd_stream_t st) {
+    typedef FwdZ<L, Tile<L>::FWD_YT> K;
+    return launch<K>(dim3(L * K::YTILES, p.C, P), p, st);
+}
+template <int L> static int launch_plane_t(const PlaneParams& p, dlpd_stream_t st) {
+    return launch<Plane<L> >(dim3((unsigned)(p.P * 2 * L * p.C)), p, st);
+}
+template <int L> static int launch_invz_t(const InvZParams& p, int Q, dlpd_stream_t st) {
+    typedef InvZStore<L, Tile<L>::INV_YT> K;
+    return launch<K>(dim3(2 * L * K::YTILES, Q), p, st);
+}
+static int launch_fwdz(int L, const FwdZParams& p, int P, dlpd_stream_t st) {
+    switch (L) {
+#define X(L_) case L_: return launch_fwdz_t<L_>(p, P, st);
+        DLPD_OP_SIZES(X)
+#undef X
+    }
+    return fail(DLPD_EINVAL, "unsupported box size");
+}
+static int launch_plane(int L, const PlaneParams& p, dlpd_stream_t st) {
+    switch (L) {
+#define X(L_) case L_: return launch_plane_t<L_>(p, st);
+        DLPD_OP_SIZES(X)
+#undef X
+    }
+    return fail(DLPD_EINVAL, "unsupported box size");
+}
+static int launch_invz(int L, const InvZParams& p, int Q, dlpd_stream_t st) {
+    switch (L) {
+#define X(L_) case L_: return launch_invz_t<L_>(p, Q, st);
+        DLPD_OP_SIZES(X)
+#undef X
+    }
+    return fail(DLPD_EINVAL, "unsupported box size");
+}
+
+// ------------------------------------------------------------------------------------------------------
+// plan
+// ------------------------------------------------------------------------------------------------------
+struct dlpd_plan {
+    int L, C0, C1, H, max_rot, center_mode, device;
+    int P;                       // pairs per chunk
+    cpx *tw0, *tw1, *tw2;        // tables of size 2L, L, L/2... (tw2 unused by kernels; kept for symmetry)
+    float *lig0, *lig1;          // [(C0+1)][L^3], [C1][(L/2)^3]
+    cpx *rspec0, *rspec1;        // receptor spectra [(C0+1)][N^3], [C1][L^3]
+    cpx *s1_0, *s1_1, *s2_0, *s2_1;
+    unsigned long long* best;    // [max_rot]
+    float *pin_R, *pin_best;     // pinned staging for dlpd_search_host
+    float *dev_R, *dev_best;
+    int host_cap;
+    std::vector<float> W1, b1, W2;
+    float b2;
+    bool has_receptor, has_ligand, lig_has_clash, has_filter;
+    long long bytes;
+};
+
+static size_t n3(int n) { return (size_t)n * n * n; }
+
+extern "C" int dlpd_version(void) { return 100; }
+extern "C" const char* dlpd_last_error(void) { return g_err.c_str(); }
+extern "C" int dlpd_op_supported(int L) { return op_size_ok(L) ? 1 : 0; }
+extern "C" int dlpd_search_supported(int L, int C0, int C1, int H) {
+#define X(L_, A, B, C) if (L == L_ && C0 == A && C1 == B && H == C) return 1;
+    DLPD_SEARCH_CONFIGS(X)
+#undef X
+    return 0;
+}
+
+extern "C" long long dlpd_plan_bytes(const dlpd_plan* p) { return p ? p->bytes : 0; }
+
+extern "C" int dlpd_plan_destroy(dlpd_plan* p) {
+    if (!p) return 0;
+    rt_set_device(p->device);
+    rt_free(p->tw0); rt_free(p->tw1); rt_free(p->tw2);
+    rt_free(p->lig0); rt_free(p->lig1); rt_free(p->rspec0); rt_free(p->rspec1);
+    rt_free(p->s1_0); rt_free(p->s1_1); rt_free(p->s2_0); rt_free(p->s2_1);
+    rt_free(p->best); rt_free(p->dev_R); rt_free(p->dev_best);
+    rt_free_host(p->pin_R); rt_free_host(p->pin_best);
+    delete p;
+    return 0;
+}
+
+extern "C" int dlpd_plan_create(dlpd_plan** out, int L, int C0, int C1, int H, int max_rot, int center_mode, int device) {
+    if (!out) return fail(DLPD_EINVAL, "plan pointer is NULL");
+    *out = nullptr;
+    if (!dlpd_search_supported(L, C0, C1, H)) {
+        char b[160];
+        snprintf(b, sizeof b, "search configuration L=%d C0=%d C1=%d H=%d is not compiled", L, C0, C1, H);
+        return fail(DLPD_EINVAL, b);
+    }
+    if (max_rot < 1) return fail(DLPD_EINVAL, "max_rot must be >= 1");
+    if (center_mode != DLPD_CENTER_BOX && center_mode != DLPD_CENTER_GRID) return fail(DLPD_EINVAL, "bad center_mode");
+    TRY(rt_set_device(device));
+    dlpd_plan* p = new dlpd_plan();
+    p->L = L; p->C0 = C0; p->C1 = C1; p->H = H; p->max_rot = max_rot; p->center_mode = center_mode; p->device = device;
+    p->P = (max_rot + 1) / 2;
+    p->tw0 = p->tw1 = p->tw2 = nullptr; p->lig0 = p->lig1 = nullptr; p->rspec0 = p->rspec1 = nullptr;
+    p->s1_0 = p->s1_1 = p->s2_0 = p->s2_1 = nullptr; p->best = nullptr;
+    p->pin_R = p->pin_best = p->dev_R = p->dev_best = nullptr; p->host_cap = 0;
+    p->has_receptor = p->has_ligand = p->lig_has_clash = p->has_filter = false;
+    p->b2 = 0.f;
+    const int N = 2 * L, L1 = L / 2, N1 = L;
+    const size_t P = (size_t)p->P;
+    struct { void** ptr; size_t bytes; } allocs[] = {
+        {(void**)&p->lig0, sizeof(float) * (C0 + 1) * n3(L)},
+        {(void**)&p->lig1, sizeof(float) * C1 * n3(L1)},
+        {(void**)&p->rspec0, sizeof(cpx) * (C0 + 1) * n3(N)},
+        {(void**)&p->rspec1, sizeof(cpx) * C1 * n3(N1)},
+        {(void**)&p->s1_0, sizeof(cpx) * P * (C0 + 1) * N * L * L},
+        {(void**)&p->s1_1, sizeof(cpx) * P * C1 * N1 * L1 * L1},
+        {(void**)&p->s2_0, sizeof(cpx) * P * (C0 + 1) * n3(N)},
+        {(void**)&p->s2_1, sizeof(cpx) * P * C1 * n3(N1)},
+        {(void**)&p->best, sizeof(unsigned long long) * (size_t)max_rot},
+    };
+    p->bytes = 0;
+    for (auto& a : allocs) {
+        int rc = rt_malloc(a.ptr, a.bytes);
+        if (rc) { dlpd_plan_destroy(p); return rc; }
+        p->bytes += (long long)a.bytes;
+    }
+    int rc = make_twiddles(&p->tw0, N, 0);
+    if (!rc) rc = make_twiddles(&p->tw1, N1, 0);
+    if (!rc) rc = make_twiddles(&p->tw2, L1 > 1 ? L1 : 2, 0);
+    if (rc) { dlpd_plan_destroy(p); return rc; }
+    *out = p;
+    return 0;
+}
+
+// forward transform of `C` real volumes (R = nullptr) into spectra: FwdZ (identity) + Plane (spectrum mode)
+static int real_spectra(int L, const float* vols, int C, cpx* s1, cpx* spec, const cpx* tw, dlpd_stream_t st) {
+    const int N = 2 * L;
+    FwdZParams f;
+    f.src = vols; f.src_pair_stride = 0; f.src_rot = nullptr; f.R = nullptr; f.out = s1; f.tw = tw;
+    f.C = C; f.c_ext = -1; f.n_rot = 1; f.center = 0.f;
+    TRY(launch_fwdz(L, f, 1, st));
+    PlaneParams q;
+    q.in = s1; q.out = spec; q.spec = nullptr; q.spec_pair_stride = 0; q.tw = tw; q.C = C; q.P = 1;
+    q.scale = (float)(1.0 / ((double)N * N * N));
+    TRY(launch_plane(L, q, st));
+    return 0;
+}
+
+extern "C" int dlpd_set_receptor(dlpd_plan* p, const float* vol0, const float* vol1, const float* clash, void* stream) {
+    if (!p || !vol0 || !vol1 || !clash) return fail(DLPD_EINVAL, "dlpd_set_receptor: NULL argument");
+    dlpd_stream_t st = (dlpd_stream_t)stream;
+    TRY(rt_set_device(p->device));
+    const int L = p->L, L1 = L / 2;
+    // stage [C0 feature volumes | clash] contiguously in the (not yet needed) ligand buffer
+    TRY(rt_copy(p->lig0, vol0, sizeof(float) * p->C0 * n3(L), D2D, st));
+    TRY(rt_copy(p->lig0 + p->C0 * n3(L), clash, sizeof(float) * n3(L), D2D, st));
+    TRY(real_spectra(L, p->lig0, p->C0 + 1, p->s1_0, p->rspec0, p->tw0, st));
+    TRY(real_spectra(L1, vol1, p->C1, p->s1_1, p->rspec1, p->tw1, st));
+    p->has_receptor = true;
+    p->has_ligand = false;      // lig0 was used as staging
+    return 0;
+}
+
+extern "C" int dlpd_set_ligand(dlpd_plan* p, const float* vol0, const float* vol1, const float* clash, void* stream) {
+    if (!p || !vol0 || !vol1) return fail(DLPD_EINVAL, "dlpd_set_ligand: NULL argument");
+    dlpd_stream_t st = (dlpd_stream_t)stream;
+    TRY(rt_set_device(p->device));
+    const int L = p->L, L1 = L / 2;
+    TRY(rt_copy(p->lig0, vol0, sizeof(float) * p->C0 * n3(L), D2D, st));
+    if (clash) TRY(rt_copy(p->lig0 + p->C0 * n3(L), clash, sizeof(float) * n3(L), D2D, st));
+    else TRY(rt_memset(p->lig0 + p->C0 * n3(L), 0, sizeof(float) * n3(L), st));
+    TRY(rt_copy(p->lig1, vol1, sizeof(float) * p->C1 * n3(L1), D2D, st));
+    p->has_ligand = true;
+    p->lig_has_clash = clash != nullptr;
+    return 0;
+}
+
+extern "C" int dlpd_set_filter(dlpd_plan* p, const float* W1, const float* b1, const float* W2, const float* b2) {
+    if (!p || !W1 || !b1 || !W2 || !b2) return fail(DLPD_EINVAL, "dlpd_set_filter: NULL argument");
+    const int CT = p->C0 + p->C1;
+    p->W1.assign(W1, W1 + (size_t)p->H * CT);
+    p->b1.assign(b1, b1 + p->H);
+    p->W2.assign(W2, W2 + p->H);
+    p->b2 = b2[0];
+    p->has_filter = true;
+    return 0;
+}
+
+template <int L, int C0, int C1, int H>
+static int launch_epilogue(dlpd_plan* p, int n, int P, float tau, float* out_scores, dlpd_stream_t st) {
+    typedef Epilogue<L, C0, C1, H> K;
+    typename K::Params e;
+    e.s2_0 = p->s2_0; e.s2_1 = p->s2_1; e.best = p->best; e.score_out = out_scores;
+    e.tw0 = p->tw0; e.tw1 = p->tw1; e.n_rot = n; e.tau = tau;
+    memcpy(e.filt.W1, p->W1.data(), sizeof(float) * H * (C0 + C1));
+    memcpy(e.filt.b1, p->b1.data(), sizeof(float) * H);
+    memcpy(e.filt.W2, p->W2.data(), sizeof(float) * H);
+    e.filt.b2 = p->b2;
+    return launch<K>(dim3(L, L, P), e, st);
+}
+
+// one chunk of n <= max_rot rotations
+static int search_chunk(dlpd_plan* p, const float* R, const float* clash_rot, int n, float tau, float* out_best,
+                        float* out_scores, dlpd_stream_t st) {
+    const int L = p->L, L1 = L / 2, N = 2 * L;
+    const int P = (n + 1) / 2;
+    TRY(rt_memset(p->best, 0xff, sizeof(unsigned long long) * n, st));
+    FwdZParams f;
+    f.src = p->lig0; f.src_pair_stride = 0; f.src_rot = clash_rot; f.R = R; f.out = p->s1_0; f.tw = p->tw0;
+    f.C = p->C0 + 1; f.c_ext = p->C0; f.n_rot = n; f.center = center_of(L, p->center_mode);
+    TRY(launch_fwdz(L, f, P, st));
+    f.src = p->lig1; f.src_rot = nullptr; f.out = p->s1_1; f.tw = p->tw1; f.C = p->C1; f.c_ext = -1;
+    f.center = center_of(L1, p->center_mode);
+    TRY(launch_fwdz(L1, f, P, st));
+    PlaneParams q;
+    q.in = p->s1_0; q.out = p->s2_0; q.spec = p->rspec0; q.spec_pair_stride = 0; q.tw = p->tw0; q.C = p->C0 + 1; q.P = P;
+    q.scale = 1.f;
+    TRY(launch_plane(L, q, st));
+    q.in = p->s1_1; q.out = p->s2_1; q.spec = p->rspec1; q.tw = p->tw1; q.C = p->C1;
+    TRY(launch_plane(L1, q, st));
+    int rc = DLPD_EINVAL;
+#define X(L_, A, B, C) if (p->L == L_ && p->C0 == A && p->C1 == B && p->H == C) rc = launch_epilogue<L_, A, B, C>(p, n, P, tau, out_scores, st);
+    DLPD_SEARCH_CONFIGS(X)
+#undef X
+    TRY(rc);
+    DecodeParams d;
+    d.best = p->best; d.out = out_best; d.n_rot = n; d.N = N;
+    TRY(launch<DecodeBest>(dim3((n + DecodeBest::NT - 1) / DecodeBest::NT), d, st));
+    return 0;
+}
+
+extern "C" int dlpd_search(dlpd_plan* p, const float* R, const float* lig_clash_rot, int n, float tau, float* out_best,
+                           float* out_scores, void* stream) {
+    if (!p || !R || !out_best || n < 1) return fail(DLPD_EINVAL, "dlpd_search: bad argument");
+    if (!p->has_receptor || !p->has_ligand || !p->has_filter)
+        return fail(DLPD_ESTATE, "dlpd_search: set_receptor, set_ligand and set_filter must be called first");
+    if (!lig_clash_rot && !p->lig_has_clash)
+        return fail(DLPD_ESTATE, "dlpd_search: no ligand clash volume (pass one to set_ligand or per rotation)");
+    dlpd_stream_t st = (dlpd_stream_t)stream;
+    TRY(rt_set_device(p->device));
+    const size_t L3 = n3(p->L), N3 = n3(2 * p->L);
+    for (int i0 = 0; i0 < n; i0 += p->max_rot) {
+        const int m = n - i0 < p->max_rot ? n - i0 : p->max_rot;
+        TRY(search_chunk(p, R + 9 * (size_t)i0, lig_clash_rot ? lig_clash_rot + L3 * i0 : nullptr, m, tau,
+                         out_best + 4 * (size_t)i0, out_scores ? out_scores + N3 * i0 : nullptr, st));
+    }
+    return 0;
+}
+
+extern "C" int dlpd_search_host(dlpd_plan* p, const float* R_host, int n, float tau, float* best_host, void* stream) {
+    if (!p || !R_host || !best_host || n < 1) return fail(DLPD_EINVAL, "dlpd_search_host: bad argument");
+    dlpd_stream_t st = (dlpd_stream_t)stream;
+    TRY(rt_set_device(p->device));
+    if (n > p->host_cap) {
+        rt_free_host(p->pin_R); rt_free_host(p->pin_best); rt_free(p->dev_R); rt_free(p->dev_best);
+        p->pin_R = p->pin_best = p->dev_R = p->dev_best = nullptr;
+        p->host_cap = 0;
+        TRY(rt_malloc_host((void**)&p->pin_R, sizeof(float) * 9 * n));
+        TRY(rt_malloc_host((void**)&p->pin_best, sizeof(float) * 4 * n));
+        TRY(rt_malloc((void**)&p->dev_R, sizeof(float) * 9 * n));
+        TRY(rt_malloc((void**)&p->dev_best, sizeof(float) * 4 * n));
+        p->host_cap = n;
+    }
+    memcpy(p->pin_R, R_host, sizeof(float) * 9 * n);
+    TRY(rt_copy(p->dev_R, p->pin_R, sizeof(float) * 9 * n, H2D, st));
+    TRY(dlpd_search(p, p->dev_R, nullptr, n, tau, p->dev_best, nullptr, stream));
+    TRY(rt_copy(p->pin_best, p->dev_best, sizeof(float) * 4 * n, D2H, st));
+    TRY(rt_sync(st));
+    memcpy(best_host, p->pin_best, sizeof(float) * 4 * n);
+    return 0;
+}
+
+// ------------------------------------------------------------------------------------------------------
+// standalone operators
+// ------------------------------------------------------------------------------------------------------
+extern "C" int dlpd_volume_rotate(const float* vol, const float* R, float* out, int B, int C, int L, int center_mode,
+                                  void* stream) {
+    if (!vol || !R || !out || B < 1 || C < 1 || L < 2) return fail(DLPD_EINVAL, "dlpd_volume_rotate: bad argument");
+    if (vol == out) return fail(DLPD_EINVAL, "dlpd_volume_rotate: in-place rotation is not supported");
+    RotateParams p;
+    p.vol = vol; p.R = R; p.out = out; p.B = B; p.C = C; p.L = L; p.center = center_of(L, center_mode);
+    const unsigned gx = (unsigned)((n3(L) + RotateVolume::VOX_PER_CTA - 1) / RotateVolume::VOX_PER_CTA);
+    return launch<RotateVolume>(dim3(gx, C, B), p, (dlpd_stream_t)stream);
+}
+
+struct OpWorkspace {
+    cpx *tw = nullptr, *s1 = nullptr, *spec = nullptr, *s2 = nullptr;
+    int L = 0, Q = 0;
+};
+static std::map<int, OpWorkspace> g_ws;     // per device
+
+extern "C" int dlpd_volume_correlate(const float* v1, const float* v2, float* out, int B, int C, int L, void* stream) {
+    if (!v1 || !v2 || !out || B < 1 || C < 1) return fail(DLPD_EINVAL, "dlpd_volume_correlate: bad argument");
+    if (!op_size_ok(L)) return fail(DLPD_EINVAL, "dlpd_volume_correlate: box size not compiled");
+    dlpd_stream_t st = (dlpd_stream_t)stream;
+    int dev = 0;
+#if !defined(DLPD_EMU)
+    CU(cudaGetDevice(&dev));
+#endif
+    const int N = 2 * L, items = B * C;
+    // workspace: ~2 * 8 * N^3 + 8 * N L^2 bytes per item; keep chunks under ~1.5 GB
+    const size_t per_item = sizeof(cpx) * (2 * n3(N) + (size_t)N * L * L);
+    int Q = (int)((size_t)1536 * 1024 * 1024 / per_item);
+    if (Q < 1) Q = 1;
+    if (Q > items) Q = items;
+    OpWorkspace& w = g_ws[dev];
+    if (w.L != L || w.Q < Q) {
+        TRY(rt_sync(st));
+        rt_free(w.tw); rt_free(w.s1); rt_free(w.spec); rt_free(w.s2);
+        w = OpWorkspace();
+        TRY(make_twiddles(&w.tw, N, st));
+        TRY(rt_malloc((void**)&w.s1, sizeof(cpx) * Q * N * L * L));
+        TRY(rt_malloc((void**)&w.spec, sizeof(cpx) * Q * n3(N)));
+        TRY(rt_malloc((void**)&w.s2, sizeof(cpx) * Q * n3(N)));
+        w.L = L; w.Q = Q;
+    }
+    for (int i0 = 0; i0 < items; i0 += w.Q) {
+        const int q = items - i0 < w.Q ? items - i0 : w.Q;
+        FwdZParams f;
+        f.src = v1 + n3(L) * i0; f.src_pair_stride = (long)n3(L); f.src_rot = nullptr; f.R = nullptr; f.out = w.s1; f.tw = w.tw;
+        f.C = 1; f.c_ext = -1; f.n_rot = 1; f.center = 0.f;
+        TRY(launch_fwdz(L, f, q, st));
+        PlaneParams pl;
+        pl.in = w.s1; pl.out = w.spec; pl.spec = nullptr; pl.spec_pair_stride = 0; pl.tw = w.tw; pl.C = 1; pl.P = q;
+        pl.scale = (float)(1.0 / ((double)N * N * N));
+        TRY(launch_plane(L, pl, st));
+        f.src = v2 + n3(L) * i0;
+        TRY(launch_fwdz(L, f, q, st));
+        pl.out = w.s2; pl.spec = w.spec; pl.spec_pair_stride = (long)n3(N); pl.scale = 1.f;
+        TRY(launch_plane(L, pl, st));
+        InvZParams iz;
+        iz.in = w.s2; iz.out = out + n3(N) * i0; iz.tw = w.tw;
+        TRY(launch_invz(L, iz, q, st));
+    }
+    return 0;
+}

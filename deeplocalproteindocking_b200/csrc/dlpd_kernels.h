@@ -1,0 +1,459 @@
+// Kernel bodies of the docking search (reference path: Docker.dockSE3, /root/reference/src/Docker/Docker.py:211-236).
+//
+// Two rotations are processed per complex volume ("pair packing"): u = B^{rotA} + i B^{rotB}.  The receptor A is
+// real, so corr(A, u) = corr(A, B^{rotA}) + i corr(A, B^{rotB}) and one complex N^3 transform chain serves two
+// rotations with no Hermitian bookkeeping.  With G[k] = sum_r u[r] e^{+2 pi i k r/N} (sign + forward) and
+// Ahat[k] = sum_r A[r] e^{-2 pi i k r/N} = conj(sign+ transform of A):
+//     sum_r A[r+d] u[r] = (1/N^3) sum_k Ahat[k] G[k] e^{+2 pi i k d/N}        (sign + inverse)
+// which is the reference's VolumeConvolution output at circular index d mod N (DockingModels.py:71).
+//
+// Data flow per pair (L = box, N = 2L, ' = digit-reversed frequency order of dlpd_fft.h):
+//   FwdZ    : ligand volume --trilinear gather (Docker.py:218)--> z-lines --pruned fwd FFT--> S1[c][kz'][x<L][y<L]
+//   Plane   : per (c,kz'): pruned fwd FFT along y, x; multiply by receptor spectrum [c][kz'][kx'][ky'];
+//             inverse FFT along x, y                                            --> S2[c][kz'][x][y]
+//   Epilogue: per 2x2 (x,y) tile, all channels: inverse FFT along z, nearest-upsampled level 1 (DockingModels.py:74-76),
+//             48->24->1 filter (DockingModels.py:28-32,79-82), clash mask (Docker.py:226,232), argmin (Docker.py:91-97)
+//             -- the correlation and score volumes are never written to HBM.
+#pragma once
+#include "dlpd_fft.h"
+
+template <int S> struct LineMul {
+    DLPD_DEV int operator()(int l) const { return l * S; }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// trilinear sample with zero padding:  value of v (L^3, z fastest) at (sx,sy,sz)
+// ------------------------------------------------------------------------------------------------------
+DLPD_DEV float trilinear_zero(const float* DLPD_RESTRICT v, int L, float sx, float sy, float sz) {
+    const float fx = floorf(sx), fy = floorf(sy), fz = floorf(sz);
+    const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    if (ix < -1 || iy < -1 || iz < -1 || ix >= L || iy >= L || iz >= L) return 0.0f;
+    const float wx1 = sx - fx, wy1 = sy - fy, wz1 = sz - fz;
+    const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1, wz0 = 1.0f - wz1;
+    const bool x0 = ix >= 0, x1 = ix + 1 < L;
+    const bool y0 = iy >= 0, y1 = iy + 1 < L;
+    const bool z0 = iz >= 0, z1 = iz + 1 < L;
+    const float* p = v + ((long)ix * L + iy) * L + iz;
+    const int sxs = L * L, sys = L;
+    float acc = 0.0f;
+    if (x0) {
+        if (y0) {
+            if (z0) acc = fmaf_(__ldg(p), wx0 * wy0 * wz0, acc);
+            if (z1) acc = fmaf_(__ldg(p + 1), wx0 * wy0 * wz1, acc);
+        }
+        if (y1) {
+            if (z0) acc = fmaf_(__ldg(p + sys), wx0 * wy1 * wz0, acc);
+            if (z1) acc = fmaf_(__ldg(p + sys + 1), wx0 * wy1 * wz1, acc);
+        }
+    }
+    if (x1) {
+        if (y0) {
+            if (z0) acc = fmaf_(__ldg(p + sxs), wx1 * wy0 * wz0, acc);
+            if (z1) acc = fmaf_(__ldg(p + sxs + 1), wx1 * wy0 * wz1, acc);
+        }
+        if (y1) {
+            if (z0) acc = fmaf_(__ldg(p + sxs + sys), wx1 * wy1 * wz0, acc);
+            if (z1) acc = fmaf_(__ldg(p + sxs + sys + 1), wx1 * wy1 * wz1, acc);
+        }
+    }
+    return acc;
+}
+
+// source position of output voxel (x,y,z):  s = ctr + R^T (p - ctr)   (R row-major 3x3)
+DLPD_DEV void rotate_point(const float* R, float ctr, int x, int y, int z, float& sx, float& sy, float& sz) {
+    const float dx = (float)x - ctr, dy = (float)y - ctr, dz = (float)z - ctr;
+    sx = fmaf_(R[6], dz, fmaf_(R[3], dy, fmaf_(R[0], dx, ctr)));
+    sy = fmaf_(R[7], dz, fmaf_(R[4], dy, fmaf_(R[1], dx, ctr)));
+    sz = fmaf_(R[8], dz, fmaf_(R[5], dy, fmaf_(R[2], dx, ctr)));
+}
+
+// ------------------------------------------------------------------------------------------------------
+// VolumeRotation as a standalone operator (Docker.py:40,218): out[b,c,p] = trilinear(vol[b,c], ctr + R_b^T (p-ctr))
+// ------------------------------------------------------------------------------------------------------
+struct RotateParams {
+    const float* vol;   // [B][C][L^3]
+    const float* R;     // [B][9]
+    float* out;         // [B][C][L^3]
+    int B, C, L;
+    float center;
+};
+
+struct RotateVolume {
+    typedef RotateParams Params;
+    static constexpr int NT = 256;
+    static constexpr int SMEM = 0;
+    static constexpr int VOX_PER_CTA = 1024;
+    // grid: x = ceil(L^3 / VOX_PER_CTA), y = C, z = B
+    static DLPD_DEV void body(const Params& p, int bx, int by, int bz, char*) {
+        const int L = p.L, L3 = L * L * L;
+        const float* R = p.R + 9 * bz;
+        float r[9];
+        for (int i = 0; i < 9; ++i) r[i] = R[i];
+        const float* src = p.vol + ((long)bz * p.C + by) * L3;
+        float* dst = p.out + ((long)bz * p.C + by) * L3;
+        DLPD_FOR_TASKS(t, VOX_PER_CTA, NT) {
+            const int i = bx * VOX_PER_CTA + t;
+            if (i < L3) {
+                const int z = i % L, y = (i / L) % L, x = i / (L * L);
+                float sx, sy, sz;
+                rotate_point(r, p.center, x, y, z, sx, sy, sz);
+                dst[i] = trilinear_zero(src, L, sx, sy, sz);
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// FwdZ: gather (rotate) + pruned forward FFT along z.
+// ------------------------------------------------------------------------------------------------------
+struct FwdZParams {
+    const float* src;        // [.. pair_stride ..][C][L^3] source volumes
+    long src_pair_stride;    // 0: every pair reads the same volumes (search); C*L^3: one real volume per "pair"
+    const float* src_rot;    // optional [n_rot][L^3]: volumes that are ALREADY rotated, used for channel c_ext
+    const float* R;          // [n_rot][9] rotation matrices, or nullptr: identity, imaginary part = 0
+    cpx* out;                // S1 [P][C][N][L][L]
+    const cpx* tw;           // [N] e^{+2 pi i k/N}
+    int C, c_ext, n_rot;
+    float center;
+};
+
+template <int L_, int YT_> struct FwdZ {
+    typedef FwdZParams Params;
+    static constexpr int L = L_, N = 2 * L_, YT = YT_, YTILES = L_ / YT_;
+    static constexpr int NT = 256;
+    static constexpr int SMEM = (N * YT + N) * (int)sizeof(cpx);
+    static_assert(L_ % YT_ == 0, "y tile must divide L");
+    // grid: x = L * YTILES, y = C, z = P
+    static DLPD_DEV void body(const Params& p, int bx, int by, int bz, char* smem) {
+        cpx* buf = reinterpret_cast<cpx*>(smem);       // [N][YT]  (kz, y)
+        cpx* tw = buf + N * YT;
+        const int x = bx / YTILES, y0 = (bx % YTILES) * YT, c = by, pair = bz;
+        const int rotA = 2 * pair, rotB = 2 * pair + 1;
+        const bool hasB = rotB < p.n_rot;
+        const bool ext = (p.src_rot != nullptr) && (c == p.c_ext);
+        const bool rotate = (p.R != nullptr) && !ext;
+        constexpr int L3 = L * L * L;
+        float ra[9], rb[9];
+        for (int i = 0; i < 9; ++i) {
+            ra[i] = rotate ? p.R[9 * rotA + i] : 0.0f;
+            rb[i] = (rotate && hasB) ? p.R[9 * rotB + i] : 0.0f;
+        }
+        const float* src = p.src + (long)pair * p.src_pair_stride + (long)c * L3;
+        DLPD_FOR_TASKS(t, N, NT) tw[t] = p.tw[t];
+        DLPD_SYNC();
+        DLPD_FOR_TASKS(t, YT * L, NT) {
+            const int yl = t % YT, z = t / YT, y = y0 + yl;
+            const int idx = (x * L + y) * L + z;
+            float a, b = 0.0f;
+            if (rotate) {
+                float sx, sy, sz;
+                rotate_point(ra, p.center, x, y, z, sx, sy, sz);
+                a = trilinear_zero(src, L, sx, sy, sz);
+                if (hasB) {
+                    rotate_point(rb, p.center, x, y, z, sx, sy, sz);
+                    b = trilinear_zero(src, L, sx, sy, sz);
+                }
+            } else if (ext) {
+                a = __ldg(p.src_rot + (long)rotA * L3 + idx);
+                if (hasB) b = __ldg(p.src_rot + (long)rotB * L3 + idx);
+            } else {
+                a = __ldg(src + idx);                          // plain real volume (receptor / standalone operator)
+            }
+            const cpx v = make_float2(a, b);
+            buf[z * YT + yl] = v;
+            buf[(z + L) * YT + yl] = cmul(v, tw[z]);          // pruned radix-2 step: upper half input is zero
+        }
+        DLPD_SYNC();
+        fft_forward_halves<L, YT, YT, NT>(buf, tw, LineMul<1>());
+        cpx* out = p.out + ((((long)pair * p.C + c) * N) * L + x) * L + y0;
+        DLPD_FOR_TASKS(t, N * YT, NT) {
+            const int kz = t / YT, yl = t % YT;
+            out[(long)kz * L * L + yl] = buf[t];
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// Plane: for one (pair, channel, kz') the whole (x,y) plane lives in shared memory.
+// ------------------------------------------------------------------------------------------------------
+struct PlaneParams {
+    const cpx* in;           // S1 [P][C][N][L][L]
+    cpx* out;                // S2 [P][C][N][N][N]   (or, in spectrum mode, [P][C][N][N][N] spectra)
+    const cpx* spec;         // receptor spectrum [..][C][N][N][N]; nullptr = spectrum mode (write conj(fwd) * scale)
+    long spec_pair_stride;   // 0: all pairs share the receptor (search); C*N^3: one spectrum per "pair"
+    const cpx* tw;           // [N]
+    int C, P;
+    float scale;
+};
+
+template <int L_> struct Plane {
+    typedef PlaneParams Params;
+    static constexpr int L = L_, N = 2 * L_, NP = N + 1;     // odd pitch: conflict-free along both axes
+    static constexpr int NT = (N >= 128) ? 512 : 256;
+    static constexpr int SMEM = (N * NP + N) * (int)sizeof(cpx);
+    // grid: x = P * N * C  with the pair index fastest (CTAs that share a receptor plane run together -> L2 reuse)
+    static DLPD_DEV void body(const Params& p, int bx, int, int, char* smem) {
+        cpx* pl = reinterpret_cast<cpx*>(smem);        // [x][y], pitch NP
+        cpx* tw = pl + N * NP;
+        const int pair = bx % p.P, kz = (bx / p.P) % N, c = bx / (p.P * N);
+        DLPD_FOR_TASKS(t, N, NT) tw[t] = p.tw[t];
+        DLPD_SYNC();
+        const cpx* in = p.in + (((long)pair * p.C + c) * N + kz) * L * L;
+        DLPD_FOR_TASKS(t, L * L, NT) {
+            const int x = t / L, y = t % L;
+            const cpx v = in[t];
+            pl[x * NP + y] = v;
+            pl[x * NP + y + L] = cmul(v, tw[y]);
+        }
+        DLPD_SYNC();
+        fft_forward_halves<L, L, 1, NT>(pl, tw, LineMul<NP>());                 // along y, rows x < L
+        DLPD_FOR_TASKS(t, L * N, NT) {
+            const int x = t / N, ky = t % N;
+            pl[(x + L) * NP + ky] = cmul(pl[x * NP + ky], tw[x]);
+        }
+        DLPD_SYNC();
+        fft_forward_halves<L, N, NP, NT>(pl, tw, LineMul<1>());                 // along x, all ky
+        if (p.spec == nullptr) {
+            cpx* out = p.out + (((long)pair * p.C + c) * N + kz) * N * N;
+            DLPD_FOR_TASKS(t, N * N, NT) {
+                const int kx = t / N, ky = t % N;
+                const cpx v = pl[kx * NP + ky];
+                out[t] = make_float2(v.x * p.scale, -v.y * p.scale);
+            }
+            return;
+        }
+        const cpx* spec = p.spec + (long)pair * p.spec_pair_stride + ((long)c * N + kz) * N * N;
+        DLPD_FOR_TASKS(t, N * N, NT) {
+            const int kx = t / N, ky = t % N;
+            pl[kx * NP + ky] = cmul(pl[kx * NP + ky], __ldg(spec + t));
+        }
+        DLPD_SYNC();
+        fft_inverse_full<L, N, NP, NT>(pl, tw, LineMul<1>());                   // along x
+        fft_inverse_full<L, N, 1, NT>(pl, tw, LineMul<NP>());                   // along y
+        cpx* out = p.out + (((long)pair * p.C + c) * N + kz) * N * N;
+        DLPD_FOR_TASKS(t, N * N, NT) {
+            const int x = t / N, y = t % N;
+            out[t] = pl[x * NP + y];
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// InvZStore: inverse FFT along z, real part -> real volume (standalone VolumeConvolution operator only).
+// ------------------------------------------------------------------------------------------------------
+struct InvZParams {
+    const cpx* in;     // S2 [Q][N][N][N]  (kz', x, y)
+    float* out;        // [Q][N][N][N]     (x, y, z)
+    const cpx* tw;
+};
+
+template <int L_, int YT_> struct InvZStore {
+    typedef InvZParams Params;
+    static constexpr int L = L_, N = 2 * L_, YT = YT_, YP = YT_ + 1, YTILES = N / YT_;
+    static constexpr int NT = 256;
+    static constexpr int SMEM = (N * YP + N) * (int)sizeof(cpx);
+    static_assert(N % YT_ == 0, "y tile must divide N");
+    // grid: x = N * YTILES, y = Q
+    static DLPD_DEV void body(const Params& p, int bx, int by, int, char* smem) {
+        cpx* buf = reinterpret_cast<cpx*>(smem);       // [kz][YP]
+        cpx* tw = buf + N * YP;
+        const int x = bx / YTILES, y0 = (bx % YTILES) * YT;
+        DLPD_FOR_TASKS(t, N, NT) tw[t] = p.tw[t];
+        const cpx* in = p.in + (long)by * N * N * N + (long)x * N + y0;
+        DLPD_FOR_TASKS(t, N * YT, NT) {
+            const int kz = t / YT, yl = t % YT;
+            buf[kz * YP + yl] = in[(long)kz * N * N + yl];
+        }
+        DLPD_SYNC();
+        fft_inverse_full<L, YT, YP, NT>(buf, tw, LineMul<1>());
+        float* out = p.out + (long)by * N * N * N + ((long)x * N + y0) * N;
+        DLPD_FOR_TASKS(t, N * YT, NT) {
+            const int z = t % N, yl = t / N;
+            out[yl * N + z] = buf[z * YP + yl].x;
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// Epilogue
+// ------------------------------------------------------------------------------------------------------
+template <int C0, int C1, int H> struct FilterW {
+    float W1[H * (C0 + C1)];   // row-major [H][C0+C1]  (nn.Linear weight, DockingModels.py:29)
+    float b1[H];
+    float W2[H];               // [1][H]                (DockingModels.py:31)
+    float b2;
+};
+
+// order-preserving map float -> uint32 (a < b  <=>  key(a) < key(b)); +-0 collapse to +0 like torch.min
+DLPD_HD unsigned int score_key(float s) {
+    if (s == 0.0f) s = 0.0f;
+    unsigned int u;
+    memcpy(&u, &s, 4);
+    return (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+}
+DLPD_HD float key_score(unsigned int k) {
+    unsigned int u = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    float s;
+    memcpy(&s, &u, 4);
+    return s;
+}
+
+#if !defined(DLPD_EMU)
+template <int NT>
+DLPD_DEV unsigned long long block_min_u64(unsigned long long v, unsigned long long* red) {
+    DLPD_UNROLL
+    for (int o = 16; o > 0; o >>= 1) {
+        unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+        v = w < v ? w : v;
+    }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0) red[warp] = v;
+    __syncthreads();
+    if (warp == 0) {
+        v = lane < NT / 32 ? red[lane] : ~0ull;
+        DLPD_UNROLL
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+            v = w < v ? w : v;
+        }
+    }
+    __syncthreads();
+    return v;      // valid in thread 0
+}
+#endif
+
+template <int C0, int C1, int H> struct EpiParams {
+    const cpx* s2_0;              // [P][C0+1][N][N][N]   (kz', x, y); channel C0 = clash
+    const cpx* s2_1;              // [P][C1][L][L][L]     level 1 (N1 = L)
+    unsigned long long* best;     // [n_rot] packed (score_key << 32 | linear index), pre-set to ~0
+    float* score_out;             // optional [n_rot][N^3] masked score volume (module-level drop-in / tests)
+    const cpx* tw0;               // [N]
+    const cpx* tw1;               // [L]
+    int n_rot;
+    float tau;
+    FilterW<C0, C1, H> filt;
+};
+
+template <int L_, int C0, int C1, int H> struct Epilogue {
+    typedef EpiParams<C0, C1, H> Params;
+    static constexpr int L = L_, N = 2 * L_, N1 = L_, M1 = L_ / 2;
+    static constexpr int NL0 = 4 * (C0 + 1), NL1 = C1;
+    static constexpr int NT = 256;
+    static constexpr int SMEM = (N * NL0 + N1 * NL1 + N + N1) * (int)sizeof(cpx) + 64 * 8;
+    // grid: x = N/2 (y tiles), y = N/2 (x tiles), z = P
+    static DLPD_DEV void body(const Params& p, int bx, int by, int bz, char* smem) {
+        cpx* b0 = reinterpret_cast<cpx*>(smem);        // [kz][NL0]   line = c*4 + xl*2 + yl
+        cpx* b1 = b0 + N * NL0;                        // [kz1][NL1]
+        cpx* tw0 = b1 + N1 * NL1;
+        cpx* tw1 = tw0 + N;
+        const int y0 = 2 * bx, x0 = 2 * by, pair = bz;
+        const int rotA = 2 * pair, rotB = 2 * pair + 1;
+        const bool hasB = rotB < p.n_rot;
+        DLPD_FOR_TASKS(t, N, NT) tw0[t] = p.tw0[t];
+        DLPD_FOR_TASKS(t, N1, NT) tw1[t] = p.tw1[t];
+        {   // level-0 lines: two complex (y0, y0+1) = 16 bytes per (channel, kz, xl)
+            const cpx* s = p.s2_0 + (long)pair * (C0 + 1) * N * N * N + (long)x0 * N + y0;
+            DLPD_FOR_TASKS(t, (C0 + 1) * N * 2, NT) {
+                const int xl = t & 1, kz = (t >> 1) % N, c = t / (2 * N);
+                const float4 v = __ldg(reinterpret_cast<const float4*>(s + (((long)c * N + kz) * N + xl) * N));
+                cpx* d = b0 + kz * NL0 + c * 4 + xl * 2;
+                d[0] = make_float2(v.x, v.y);
+                d[1] = make_float2(v.z, v.w);
+            }
+        }
+        {   // level-1 lines at (x0/2, y0/2)
+            const cpx* s = p.s2_1 + (long)pair * C1 * N1 * N1 * N1 + (long)(x0 >> 1) * N1 + (y0 >> 1);
+            DLPD_FOR_TASKS(t, C1 * N1, NT) {
+                const int kz = t % N1, c = t / N1;
+                b1[kz * NL1 + c] = __ldg(s + ((long)c * N1 + kz) * N1 * N1);
+            }
+        }
+        DLPD_SYNC();
+        fft_inverse_full<L, NL0, NL0, NT>(b0, tw0, LineMul<1>());
+        fft_inverse_full<M1, NL1, NL1, NT>(b1, tw1, LineMul<1>());
+
+        unsigned long long bestA = ~0ull, bestB = ~0ull;
+        constexpr int CT = C0 + C1;
+        DLPD_FOR_TASKS(t, 4 * N, NT) {
+            const int xy = t & 3, z = t >> 2;
+            float ha[H], hb[H];
+            DLPD_UNROLL
+            for (int j = 0; j < H; ++j) { ha[j] = p.filt.b1[j]; hb[j] = p.filt.b1[j]; }
+            const cpx* v0 = b0 + z * NL0 + xy;
+            DLPD_UNROLL
+            for (int c = 0; c < C0; ++c) {
+                const cpx v = v0[c * 4];
+                DLPD_UNROLL
+                for (int j = 0; j < H; ++j) {
+                    ha[j] = fmaf_(p.filt.W1[j * CT + c], v.x, ha[j]);
+                    hb[j] = fmaf_(p.filt.W1[j * CT + c], v.y, hb[j]);
+                }
+            }
+            const cpx* v1 = b1 + (z >> 1) * NL1;
+            DLPD_UNROLL
+            for (int c = 0; c < C1; ++c) {
+                const cpx v = v1[c];
+                DLPD_UNROLL
+                for (int j = 0; j < H; ++j) {
+                    ha[j] = fmaf_(p.filt.W1[j * CT + C0 + c], v.x, ha[j]);
+                    hb[j] = fmaf_(p.filt.W1[j * CT + C0 + c], v.y, hb[j]);
+                }
+            }
+            float sa = p.filt.b2, sb = p.filt.b2;
+            DLPD_UNROLL
+            for (int j = 0; j < H; ++j) {
+                sa = fmaf_(p.filt.W2[j], fmaxf(ha[j], 0.0f), sa);
+                sb = fmaf_(p.filt.W2[j], fmaxf(hb[j], 0.0f), sb);
+            }
+            const cpx clash = v0[C0 * 4];
+            const float Va = clash.x < p.tau ? sa : 0.0f;      // (clash < tau).float() * score   (Docker.py:226,232)
+            const float Vb = clash.y < p.tau ? sb : 0.0f;
+            const unsigned int lin = (unsigned int)(((x0 + (xy >> 1)) * N + (y0 + (xy & 1))) * N + z);
+            const unsigned long long ka = ((unsigned long long)score_key(Va) << 32) | lin;
+            const unsigned long long kb = ((unsigned long long)score_key(Vb) << 32) | lin;
+            bestA = ka < bestA ? ka : bestA;
+            bestB = kb < bestB ? kb : bestB;
+            if (p.score_out != nullptr) {
+                p.score_out[(long)rotA * N * N * N + lin] = Va;
+                if (hasB) p.score_out[(long)rotB * N * N * N + lin] = Vb;
+            }
+        }
+#if defined(DLPD_EMU)
+        if (bestA < p.best[rotA]) p.best[rotA] = bestA;
+        if (hasB && bestB < p.best[rotB]) p.best[rotB] = bestB;
+#else
+        unsigned long long* red = reinterpret_cast<unsigned long long*>(tw1 + N1);
+        bestA = block_min_u64<NT>(bestA, red);
+        bestB = block_min_u64<NT>(bestB, red + 32);
+        if (threadIdx.x == 0) {
+            atomicMin(p.best + rotA, bestA);
+            if (hasB) atomicMin(p.best + rotB, bestB);
+        }
+#endif
+    }
+};
+
+// packed best -> [n_rot][4] floats (score, x, y, z)
+struct DecodeParams {
+    const unsigned long long* best;
+    float* out;
+    int n_rot, N;
+};
+struct DecodeBest {
+    typedef DecodeParams Params;
+    static constexpr int NT = 256;
+    static constexpr int SMEM = 0;
+    static DLPD_DEV void body(const Params& p, int bx, int, int, char*) {
+        DLPD_FOR_TASKS(t, NT, NT) {
+            const int i = bx * NT + t;
+            if (i < p.n_rot) {
+                const unsigned long long k = p.best[i];
+                const unsigned int lin = (unsigned int)(k & 0xffffffffu);
+                p.out[4 * i + 0] = key_score((unsigned int)(k >> 32));
+                p.out[4 * i + 1] = (float)(lin / (unsigned int)(p.N * p.N));
+                p.out[4 * i + 2] = (float)((lin / (unsigned int)p.N) % (unsigned int)p.N);
+                p.out[4 * i + 3] = (float)(lin % (unsigned int)p.N);
+            }
+        }
+    }
+};

@@ -1,0 +1,42 @@
+// Platform glue: the kernel BODIES in dlpd_kernels.h are written once against the small set of
+// macros below.  The product build (nvcc, sm_100a) maps them to CUDA; the emulation build
+// (g++ -DDLPD_EMU, tests/emu only -- TEST INFRASTRUCTURE, never loaded by the package) runs every
+// "parallel for over tasks" sequentially on the host so that index math, twiddles and layouts can
+// be checked against the oracle without a GPU.
+#pragma once
+#include <stdint.h>
+#include <math.h>
+#include <string.h>
+
+#if defined(DLPD_EMU)
+  #define DLPD_HD inline
+  #define DLPD_DEV inline
+  #define DLPD_CE constexpr
+  struct float2 { float x, y; };
+  struct float4 { float x, y, z, w; };
+  static inline float2 make_float2(float x, float y) { float2 r; r.x = x; r.y = y; return r; }
+  static inline float4 make_float4(float x, float y, float z, float w) { float4 r; r.x = x; r.y = y; r.z = z; r.w = w; return r; }
+  static inline float __ldg(const float* p) { return *p; }
+  static inline float2 __ldg(const float2* p) { return *p; }
+  static inline float4 __ldg(const float4* p) { return *p; }
+  static inline float fmaf_(float a, float b, float c) { return fmaf(a, b, c); }
+  // one emulated "thread": tasks run in order
+  #define DLPD_FOR_TASKS(t, n, NT) for (int t = 0; t < (n); ++t)
+  #define DLPD_SYNC() do {} while (0)
+  #define DLPD_UNROLL
+  #define DLPD_RESTRICT
+  typedef void* dlpd_stream_t;
+#else
+  #include <cuda_runtime.h>
+  #define DLPD_HD __host__ __device__ __forceinline__
+  #define DLPD_DEV __device__ __forceinline__
+  #define DLPD_CE __host__ __device__ constexpr
+  #define DLPD_FOR_TASKS(t, n, NT) for (int t = threadIdx.x; t < (n); t += (NT))
+  #define DLPD_SYNC() __syncthreads()
+  #define DLPD_UNROLL _Pragma("unroll")
+  #define DLPD_RESTRICT __restrict__
+  DLPD_DEV float fmaf_(float a, float b, float c) { return fmaf(a, b, c); }
+  typedef cudaStream_t dlpd_stream_t;
+#endif
+
+typedef float2 cpx;

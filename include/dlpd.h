@@ -1,0 +1,94 @@
+/* dlpd.h -- C ABI of the B200 docking-search library (libdlpd.so).
+ *
+ * This is the drop-in boundary for the hot path of lupoglaz/DeepLocalProteinDocking: the rotation loop of
+ * `Docker.dockSE3` (reference: src/Docker/Docker.py:211-236) and the three TorchProteinLibrary operators it
+ * calls.  The reference has no FFI table of its own -- its boundary is the Python module surface of
+ * TorchProteinLibrary (`_Volume` pybind module) -- so each entry point below names the reference call it
+ * replaces.  INTEGRATION.md shows the Python-side binding (ctypes) a maintainer would add.
+ *
+ * Conventions
+ *   - plain C types only; every `const float*` / `float*` volume pointer is a DEVICE pointer owned by the caller
+ *     (a torch tensor's data_ptr()), fp32, contiguous, layout [..][x][y][z] with z fastest (NCDHW);
+ *   - `stream` is a cudaStream_t passed as void* (NULL = default stream); calls are asynchronous on it unless
+ *     stated otherwise;
+ *   - return value 0 = success, otherwise a DLPD_E* code; dlpd_last_error() returns the message of the last
+ *     failure on the calling thread;
+ *   - a plan is not thread-safe; distinct plans are independent;
+ *   - there is no CPU fallback: every entry point fails with DLPD_ECUDA if no device is usable.
+ */
+#ifndef DLPD_H
+#define DLPD_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DLPD_OK 0
+#define DLPD_EINVAL 1      /* bad argument / unsupported size                       */
+#define DLPD_ECUDA 2       /* CUDA runtime error (message in dlpd_last_error)       */
+#define DLPD_ESTATE 3      /* call order violated (e.g. search before set_receptor) */
+
+#define DLPD_CENTER_BOX 0  /* rotation centre L/2     (default; SURVEY 8c choice 2) */
+#define DLPD_CENTER_GRID 1 /* rotation centre (L-1)/2 (literal torch-1.1 affine_grid) */
+
+typedef struct dlpd_plan dlpd_plan;
+
+int dlpd_version(void);
+const char* dlpd_last_error(void);
+
+/* Non-zero if (L, C0, C1, H) is a compiled search configuration. */
+int dlpd_search_supported(int L, int C0, int C1, int H);
+/* Non-zero if the standalone operators accept box size L. */
+int dlpd_op_supported(int L);
+
+/* ---- search engine: replaces the body of the loop Docker.py:211-236 -------------------------------------
+ * L            box size (Docker.__init__ box_size, Docker.py:18; 80 in local_test.py:55)
+ * C0, C1       channels of the two resolution levels (16 @ L, 32 @ L/2: ProteinRepresentationModels.py:35-36)
+ * H            hidden width of SimpleFilter (DockingModels.py:29: (C0+C1)/2)
+ * max_rot      rotations processed per internal batch (workspace is sized for it)
+ */
+int dlpd_plan_create(dlpd_plan** plan, int L, int C0, int C1, int H, int max_rot, int center_mode, int device);
+int dlpd_plan_destroy(dlpd_plan* plan);
+/* bytes of device memory the plan owns */
+long long dlpd_plan_bytes(const dlpd_plan* plan);
+
+/* Receptor side, once per pair (Docker.py:204-206): feature volumes vol0 [C0][L^3], vol1 [C1][(L/2)^3] and the
+ * clash volume `receptor.sum(dim=1)` [L^3].  Computes and keeps the receptor spectra (the reference re-transforms
+ * the receptor inside every VolumeConvolution call, DockingModels.py:71). */
+int dlpd_set_receptor(dlpd_plan* plan, const float* vol0, const float* vol1, const float* clash, void* stream);
+
+/* Ligand side, once per pair (Docker.py:208-209): un-rotated feature volumes; `clash` [L^3] may be NULL when
+ * per-rotation clash volumes are supplied to dlpd_search (re-projected rotated atoms, Docker.py:221-224). */
+int dlpd_set_ligand(dlpd_plan* plan, const float* vol0, const float* vol1, const float* clash, void* stream);
+
+/* SimpleFilter weights (DockingModels.py:28-32), HOST pointers: W1 [H][C0+C1], b1 [H], W2 [H], b2 [1]. */
+int dlpd_set_filter(dlpd_plan* plan, const float* W1, const float* b1, const float* W2, const float* b2);
+
+/* One batch of rotations (any n >= 1; processed in chunks of max_rot).
+ *   R              device [n][9] row-major rotation matrices (r_batch_gpu, Docker.py:215)
+ *   lig_clash_rot  device [n][L^3] already-rotated ligand clash volumes (Docker.py:221-224) or NULL to rotate the
+ *                  clash volume given to dlpd_set_ligand with the same operator as the feature volumes
+ *   tau            clash threshold (docking_model.threshold_clash, Docker.py:226)
+ *   out_best       device [n][4]: score, x, y, z of argmin_t V[t] (first extraction of update_top, Docker.py:91-97;
+ *                  ties -> first voxel in row-major order)
+ *   out_scores     optional device [n][(2L)^3]: the masked score volume V (Docker.py:232); NULL in production */
+int dlpd_search(dlpd_plan* plan, const float* R, const float* lig_clash_rot, int n, float tau, float* out_best,
+                float* out_scores, void* stream);
+
+/* Same with HOST buffers (R_host [n][9] in, best_host [n][4] out): stages through pinned memory, copies inside,
+ * and synchronises the stream before returning.  This is the end-to-end call bench.py times. */
+int dlpd_search_host(dlpd_plan* plan, const float* R_host, int n, float tau, float* best_host, void* stream);
+
+/* ---- standalone operators (module-level drop-ins) --------------------------------------------------------
+ * TorchProteinLibrary.Volume.VolumeRotation.forward(volume, R)   (Docker.py:40,218)
+ *   out[b,c,p] = trilinear(vol[b,c], ctr + R_b^T (p - ctr)), zero outside;  vol/out [B][C][L^3], R [B][9] */
+int dlpd_volume_rotate(const float* vol, const float* R, float* out, int B, int C, int L, int center_mode,
+                       void* stream);
+/* TorchProteinLibrary.Volume.VolumeConvolution.forward(v1, v2)   (DockingModels.py:71, Docker.py:225)
+ *   out[b,c,d mod 2L] = sum_r v1[b,c,r+d] * v2[b,c,r];  v1,v2 [B][C][L^3] -> out [B][C][(2L)^3] */
+int dlpd_volume_correlate(const float* v1, const float* v2, float* out, int B, int C, int L, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DLPD_H */

@@ -1,0 +1,101 @@
+"""Host EMULATION of the CUDA kernel bodies -- TEST INFRASTRUCTURE ONLY.
+
+`libdlpd_emu.so` is `csrc/dlpd_api.cu` compiled by g++ with -DDLPD_EMU: every "parallel for over tasks" of a
+kernel body runs sequentially on the CPU, "device" pointers are host pointers.  It lets the `-m "not gpu"`
+suite check index math, twiddles, layouts and the pair-packing algebra against the oracle without a GPU.
+The package never loads it; GPU parity tests (`-m gpu`) go through the real libdlpd.so.
+"""
+import ctypes
+import os
+import subprocess
+
+import torch
+
+from deeplocalproteindocking_b200 import _lib
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+SRC = os.path.join(ROOT, "deeplocalproteindocking_b200", "csrc")
+SO = os.path.join(HERE, "libdlpd_emu.so")
+
+
+def build(force=False):
+    srcs = [os.path.join(SRC, f) for f in os.listdir(SRC)] + [os.path.join(ROOT, "include", "dlpd.h")]
+    if force or not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-DDLPD_EMU", "-x", "c++", "-fPIC", "-shared",
+                               "-o", SO, os.path.join(SRC, "dlpd_api.cu")])
+    return SO
+
+
+_emu = None
+
+
+def lib():
+    global _emu
+    if _emu is None:
+        _emu = _lib.bind_signatures(ctypes.CDLL(build()))
+    return _emu
+
+
+def ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t is not None else None
+
+
+def fptr(t):
+    return ctypes.cast(t.data_ptr(), ctypes.POINTER(ctypes.c_float))
+
+
+class EmuPlan:
+    def __init__(self, L, C0, C1, H, max_rot=4, center="box"):
+        self.L, self.C0, self.C1, self.H = L, C0, C1, H
+        self.h = ctypes.c_void_p()
+        _lib.check(lib(), lib().dlpd_plan_create(ctypes.byref(self.h), L, C0, C1, H, max_rot, _lib.CENTER_MODES[center], 0))
+
+    def close(self):
+        if self.h:
+            lib().dlpd_plan_destroy(self.h)
+            self.h = ctypes.c_void_p()
+
+    def set_receptor(self, v0, v1, clash):
+        v0, v1, clash = (t.contiguous().float() for t in (v0, v1, clash))
+        _lib.check(lib(), lib().dlpd_set_receptor(self.h, ptr(v0), ptr(v1), ptr(clash), None))
+
+    def set_ligand(self, v0, v1, clash=None):
+        v0, v1 = v0.contiguous().float(), v1.contiguous().float()
+        clash = clash.contiguous().float() if clash is not None else None
+        _lib.check(lib(), lib().dlpd_set_ligand(self.h, ptr(v0), ptr(v1), ptr(clash), None))
+
+    def set_filter(self, W1, b1, W2, b2):
+        W1, b1, W2, b2 = (t.contiguous().float().reshape(-1) for t in (W1, b1, W2, b2))
+        _lib.check(lib(), lib().dlpd_set_filter(self.h, fptr(W1), fptr(b1), fptr(W2), fptr(b2)))
+
+    def search(self, R, tau, clash_rot=None, want_scores=False):
+        R = R.contiguous().float().reshape(-1, 9)
+        n, N = R.shape[0], 2 * self.L
+        best = torch.zeros(n, 4)
+        scores = torch.zeros(n, N, N, N) if want_scores else None
+        clash_rot = clash_rot.contiguous().float() if clash_rot is not None else None
+        _lib.check(lib(), lib().dlpd_search(self.h, ptr(R), ptr(clash_rot), n, float(tau), ptr(best), ptr(scores), None))
+        return best, scores
+
+    def search_host(self, R, tau):
+        R = R.contiguous().float().reshape(-1, 9)
+        best = torch.zeros(R.shape[0], 4)
+        _lib.check(lib(), lib().dlpd_search_host(self.h, ptr(R), R.shape[0], float(tau), ptr(best), None))
+        return best
+
+
+def volume_rotate(vol, R, center="box"):
+    vol, R = vol.contiguous().float(), R.contiguous().float()
+    out = torch.empty_like(vol)
+    B, C, L = vol.shape[:3]
+    _lib.check(lib(), lib().dlpd_volume_rotate(ptr(vol), ptr(R), ptr(out), B, C, L, _lib.CENTER_MODES[center], None))
+    return out
+
+
+def volume_correlate(v1, v2):
+    v1, v2 = v1.contiguous().float(), v2.contiguous().float()
+    B, C, L = v1.shape[:3]
+    out = torch.empty(B, C, 2 * L, 2 * L, 2 * L)
+    _lib.check(lib(), lib().dlpd_volume_correlate(ptr(v1), ptr(v2), ptr(out), B, C, L, None))
+    return out

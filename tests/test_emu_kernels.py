@@ -1,0 +1,122 @@
+"""Kernel bodies (host emulation, see tests/emu/driver.py) vs the oracle.  CPU only."""
+import os
+
+import pytest
+import torch
+
+from oracle import docking_oracle as O
+from deeplocalproteindocking_b200 import rotations as rot
+from tests.emu import driver as emu
+
+R20 = rot.Rotations(20).R
+
+
+def _case(L, C0, C1, seed):
+    g = torch.Generator().manual_seed(seed)
+    L1 = L // 2
+    # zero-mean features keep the filter well conditioned (all-positive volumes drive every hidden unit far
+    # from 0 and the score is then a small difference of large numbers -- even the fp32 oracle misses 1e-4 there)
+    rec = [torch.randn(1, C0, L, L, L, generator=g), torch.randn(1, C1, L1, L1, L1, generator=g)]
+    lig = [torch.randn(1, C0, L, L, L, generator=g), torch.randn(1, C1, L1, L1, L1, generator=g)]
+    rf = torch.rand(1, 1, L, L, L, generator=g) * 2
+    lf = torch.rand(L, L, L, generator=g) * 2
+    return rec, lig, rf, lf
+
+
+@pytest.mark.parametrize("L", [4, 8, 10, 16, 20])
+def test_emu_correlate_matches_oracle(L):
+    g = torch.Generator().manual_seed(L)
+    v1 = torch.randn(2, 2, L, L, L, generator=g)
+    v2 = torch.randn(2, 2, L, L, L, generator=g)
+    got = emu.volume_correlate(v1, v2)
+    want = O.correlate(v1.double(), v2.double())
+    assert (got.double() - want).abs().max() <= 2e-5 * want.abs().max()
+
+
+@pytest.mark.parametrize("L,center", [(8, "box"), (10, "box"), (9, "grid"), (16, "grid")])
+def test_emu_rotate_matches_oracle(L, center):
+    g = torch.Generator().manual_seed(L)
+    vol = torch.randn(2, 3, L, L, L, generator=g)
+    R = R20[[100, 900]]
+    got = emu.volume_rotate(vol, R, center)
+    want = O.rotate_volume(vol.double(), R, center)
+    assert (got.double() - want).abs().max() < 2e-5
+
+
+@pytest.mark.parametrize("L,C0,C1,H,n", [(8, 4, 6, 5, 3), (16, 4, 6, 5, 2), (20, 4, 6, 5, 3), (8, 16, 32, 24, 2)])
+def test_emu_search_matches_oracle(L, C0, C1, H, n):
+    rec, lig, rf, lf = _case(L, C0, C1, seed=L + C0)
+    filt = O.FilterWeights.random(C0 + C1, H, seed=3)
+    Rs = R20[torch.arange(n) * 311 + 5]
+    tau = float(torch.quantile(O.correlate(rf, lf[None, None]).flatten(), 0.7))
+    plan = emu.EmuPlan(L, C0, C1, H, max_rot=2)
+    try:
+        plan.set_receptor(rec[0][0], rec[1][0], rf[0, 0])
+        plan.set_ligand(lig[0][0], lig[1][0], lf)
+        plan.set_filter(filt.W1, filt.b1, filt.W2, filt.b2)
+        best, scores = plan.search(Rs, tau, want_scores=True)
+        best_h = plan.search_host(Rs, tau)
+    finally:
+        plan.close()
+    assert torch.equal(best, best_h)
+    d = lambda t: t.double()
+    spectra = O.ReceptorSpectra([d(r) for r in rec], d(rf))
+    f64 = filt.to(torch.float64)
+    for i in range(n):
+        V = O.score_rotation(spectra, [d(l) for l in lig], d(lf), Rs[i], f64, tau)
+        scale = V.abs().max()
+        # voxels whose clash value sits on the threshold may flip in fp32: compare away from it
+        clash = O.correlate(d(rf), O.rotate_volume(d(lf)[None, None], Rs[i][None]))[0, 0]
+        safe = (clash - tau).abs() > 1e-4 * clash.abs().max()
+        assert ((scores[i].double() - V).abs()[safe]).max() <= 1e-4 * scale
+        s, x, y, z = O.best_pose(V)
+        assert [int(v) for v in best[i, 1:]] == [x, y, z]
+        assert abs(float(best[i, 0]) - s) <= 1e-4 * max(abs(s), 1e-3 * float(scale))
+
+
+def test_emu_search_with_prerotated_clash_and_odd_count():
+    L, C0, C1, H = 8, 4, 6, 5
+    rec, lig, rf, lf = _case(L, C0, C1, seed=77)
+    filt = O.FilterWeights.random(C0 + C1, H, seed=5)
+    Rs = R20[[3, 700, 1500]]
+    clash_rot = torch.stack([O.rotate_volume(lf[None, None], Rs[i][None].float())[0, 0] for i in range(3)])
+    tau = 4.0
+    plan = emu.EmuPlan(L, C0, C1, H, max_rot=4)
+    try:
+        plan.set_receptor(rec[0][0], rec[1][0], rf[0, 0])
+        plan.set_ligand(lig[0][0], lig[1][0], None)
+        plan.set_filter(filt.W1, filt.b1, filt.W2, filt.b2)
+        best_ext, _ = plan.search(Rs, tau, clash_rot=clash_rot)
+        with pytest.raises(Exception):
+            plan.search(Rs, tau)                       # no clash volume available -> loud failure
+        plan.set_ligand(lig[0][0], lig[1][0], lf)
+        best_int, _ = plan.search(Rs, tau)
+    finally:
+        plan.close()
+    assert torch.equal(best_ext[:, 1:], best_int[:, 1:])
+    assert torch.allclose(best_ext[:, 0], best_int[:, 0], rtol=1e-5, atol=1e-6)
+
+
+def test_emu_global_model_golden(golden_dir):
+    """Reference GlobalDockingModel.forward output (tests/golden/global_model.pt) through the kernel bodies."""
+    g = torch.load(os.path.join(golden_dir, "global_model.pt"), weights_only=False)
+    L, C0, C1, H = 8, 4, 6, 5
+    plan = emu.EmuPlan(L, C0, C1, H, max_rot=2)
+    try:
+        plan.set_receptor(g["rec"][0][0], g["rec"][1][0], torch.zeros(L, L, L))
+        plan.set_ligand(g["lig"][0][0], g["lig"][1][0], torch.zeros(L, L, L))
+        plan.set_filter(g["W1"], g["b1"], g["W2"], g["b2"])
+        best, scores = plan.search(torch.eye(3)[None], tau=1.0, want_scores=True)
+    finally:
+        plan.close()
+    V = g["V_global"]
+    assert (scores[0].double() - V).abs().max() <= 1e-4 * V.abs().max()
+    s, x, y, z = O.best_pose(V)
+    assert [int(v) for v in best[0, 1:]] == [x, y, z]
+
+
+def test_emu_unsupported_configuration_fails_loudly():
+    with pytest.raises(Exception):
+        emu.EmuPlan(12, 4, 6, 5)
+    with pytest.raises(Exception):
+        emu.volume_correlate(torch.zeros(1, 1, 12, 12, 12), torch.zeros(1, 1, 12, 12, 12))
