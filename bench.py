@@ -1,0 +1,348 @@
+#!/usr/bin/env python
+"""bench.py -- rotations/s of the exhaustive docking search (BASELINE.json metric) on N B200s of one node.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P bench.py --gpus N ...
+
+Workload (BASELINE.json configs[1]): single receptor-ligand pair, synthetic atoms -> Gaussian densities ->
+randomly initialised E3MultiResRepr4x4(multiplier=8) -> 16@80^3 + 32@40^3 volumes, 48->24->1 SimpleFilter,
+rotations taken in file order from the oim10 set (14 868 rotations), fp32, every one of the 160^3 translations
+scored per rotation.  One "step" = one batch of `--rot-batch` rotations per GPU pushed through the search:
+per-rotation ligand clash volumes (re-projection of the rotated atoms, Docker.py:221-224, plain PyTorch) +
+the fused CUDA search (libdlpd.so).  At N > 1 the rotation set is sharded i mod N (weak scaling: every rank
+does `--rot-batch` rotations per step), with one NCCL all-gather of the best poses at the end of the timed region.
+
+Printed JSON line: see DESIGN.md "Measurement".  `--impl reference` times the CPU oracle (the reference
+correlation as CPU PyTorch with torch.fft, all host threads) on the same workload instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import tempfile
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import torch  # noqa: E402
+
+L, C0, C1, HID = 80, 16, 32, 24
+ANGLE_INC = 10
+TAU = 300.0
+
+
+def algorithmic_bytes_per_rotation(L=L, C0=C0, C1=C1):
+    """per channel of edge l (n = 2l, h = n*n*(n/2+1)): 4 l^3 + 24 h bytes; split by kernel as
+    FwdZ = 4 l^3 (read ligand), Plane = 16 h (receptor spectrum read + spectrum write), Epilogue = 8 h (read back)."""
+    def h(l):
+        n = 2 * l
+        return n * n * (n // 2 + 1)
+    lv0, lv1 = (C0 + 1), C1
+    parts = {
+        "fwdz_level0": lv0 * 4 * L ** 3, "fwdz_level1": lv1 * 4 * (L // 2) ** 3,
+        "plane_level0": lv0 * 16 * h(L), "plane_level1": lv1 * 16 * h(L // 2),
+        "epilogue": lv0 * 8 * h(L) + lv1 * 8 * h(L // 2),
+    }
+    parts["total"] = sum(parts.values())
+    return parts
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+def build_problem(device):
+    """Synthetic pair -> volumes (once, outside any timed region)."""
+    from deeplocalproteindocking_b200 import E3MultiResRepr4x4, SimpleFilter, synthetic
+    from deeplocalproteindocking_b200.docker import Atoms, TypedCoords2Volume, typed_layout
+    torch.manual_seed(1234 + 1)
+    rep = E3MultiResRepr4x4(multiplier=8).to(device).eval()
+    filt = SimpleFilter(rep.get_num_outputs())
+    rec, lig = synthetic.config_pair(L, seed=1234 + 1)
+    rec, lig = rec.centred(), lig.centred()
+    centre = L * 1.25 / 2.0
+    project = TypedCoords2Volume(L, 1.25)
+
+    def volumes(atoms):
+        coords, nat, off = typed_layout(Atoms((atoms.coords + centre).float(), atoms.types), device)
+        with torch.no_grad():
+            dens = project(coords, nat, off)
+            vols = rep(dens)
+        return [v[0].contiguous() for v in vols], dens.sum(dim=1)[0].contiguous()
+
+    rec_vols, rec_clash = volumes(rec)
+    lig_vols, _ = volumes(lig)
+    return rec_vols, rec_clash, lig_vols, lig.coords, filt
+
+
+def clash_volumes(lig_coords_dev, Rb64, device):
+    from deeplocalproteindocking_b200.docker import project_density_batched
+    moved = torch.einsum("nij,aj->nai", Rb64, lig_coords_dev) + L * 1.25 / 2.0
+    return project_density_batched(moved.to(torch.float32), L, 1.25)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms during the timed region (B200_PROFILING.md)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.f = tempfile.NamedTemporaryFile("w+", suffix=".csv", delete=False)
+        self.p = None
+        try:
+            self.p = subprocess.Popen(["nvidia-smi", "-i", str(gpu_index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits",
+                                       "-lms", "200"], stdout=self.f, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.p = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.p is None:
+            return out
+        self.p.terminate()
+        try:
+            self.p.wait(timeout=5)
+        except Exception:
+            self.p.kill()
+        self.f.flush()
+        self.f.seek(0)
+        sm, mx, reasons = [], [], set()
+        for line in self.f.read().splitlines():
+            c = [x.strip() for x in line.split(",")]
+            if len(c) < 9:
+                continue
+            try:
+                sm.append(float(c[1])); mx.append(float(c[2]))
+            except ValueError:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), c[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        self.f.close()
+        os.unlink(self.f.name)
+        if sm:
+            out.update(sm_mhz=statistics.median(sm), sm_max_mhz=max(mx), reasons=sorted(reasons), samples=len(sm))
+        return out
+
+
+def cpu_baseline(rec_vols, rec_clash, lig_vols, lig_coords, filt, Rs, n_rot, warm=1):
+    """The oracle (CPU PyTorch + torch.fft restatement of the reference loop, receptor spectra precomputed) timed on
+    all host cores over `n_rot` rotations.  kind = "port"."""
+    from oracle import docking_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    cpu = lambda t: t.detach().float().cpu()
+    f = O.FilterWeights(cpu(filt.fc[0].weight), cpu(filt.fc[0].bias), cpu(filt.fc[2].weight), cpu(filt.fc[2].bias))
+    spectra = O.ReceptorSpectra([cpu(v)[None] for v in rec_vols], cpu(rec_clash)[None, None])
+    ligs = [cpu(v)[None] for v in lig_vols]
+    lc = lig_coords.cpu()
+    times = []
+    for i in range(warm + n_rot):
+        t0 = time.perf_counter()
+        clash = O.ligand_clash_volume(lc, Rs[i % Rs.shape[0]], L, 1.25)
+        V = O.score_rotation(spectra, ligs, clash, Rs[i % Rs.shape[0]], f, TAU, ligand_forbidden_is_rotated=True)
+        O.best_pose(V)
+        if i >= warm:
+            times.append(time.perf_counter() - t0)
+    return sum(times), len(times)
+
+
+def run_reference(args, rank, world):
+    """`--impl reference`: the reference's own CPU formulation of the path (oracle port; TorchProteinLibrary's
+    compiled operators are not vendored) on the host cores.  Rank 0 only."""
+    if rank != 0:
+        return
+    from deeplocalproteindocking_b200 import rotations
+    rec_vols, rec_clash, lig_vols, lig_coords, filt = build_problem("cpu")
+    Rs = rotations.Rotations(ANGLE_INC).R
+    per_step = args.ref_rot_per_step
+    cpu_baseline(rec_vols, rec_clash, lig_vols, lig_coords, filt, Rs, per_step * args.warmup, warm=0)
+    t, n = cpu_baseline(rec_vols, rec_clash, lig_vols, lig_coords, filt, Rs[per_step * args.warmup:], per_step * args.steps, warm=0)
+    value = n / t
+    cores = os.cpu_count() or 1
+    line = {
+        "impl": "reference", "metric": "rotations/sec (all translations scored)", "value": value, "unit": "rotations/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": workload_config(per_step, 1),
+        "cpu_baseline": {"value": value, "unit": "rotations/s", "cores": cores, "kind": "port",
+                         "sample": "%d rotations of oim10 per step x %d steps, CPU PyTorch torch.fft, receptor spectra precomputed"
+                                   % (per_step, args.steps)},
+        "e2e": {"value": value, "unit": "rotations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(rot_batch, world):
+    return {"workload": "single pair, 80^3 grid, oim10 rotation set (14868 rotations, file order), 16@80^3+32@40^3 channels "
+                        "+ clash channel, 48->24->1 filter, all 160^3 translations scored per rotation, fp32",
+            "box_size": L, "channels": [C0, C1], "rotation_set": "oim10", "rotations_per_step_per_gpu": rot_batch,
+            "parallelism": "rotations sharded i mod %d" % world,
+            "l2_policy": "working set per step >> L2 (receptor spectra 0.69 GB + 0.86 GB workspace per rotation pair); no explicit flush"}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rot-batch", type=int, default=64, help="rotations per step per GPU")
+    ap.add_argument("--max-rot", type=int, default=32, help="rotations per internal chunk (workspace size)")
+    ap.add_argument("--cpu-rotations", type=int, default=8, help="rotations of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--ref-rot-per-step", type=int, default=2)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+
+    import torch.distributed as dist
+    from deeplocalproteindocking_b200 import DockingSearch, rotations
+    from deeplocalproteindocking_b200 import distributed as D
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=device)
+
+    rec_vols, rec_clash, lig_vols, lig_coords, filt = build_problem(device)
+    Rall = rotations.Rotations(ANGLE_INC).R                                  # [14868,3,3] float64 CPU
+    shard = D.shard_indices(Rall.shape[0], rank, world)
+    nb = args.rot_batch
+    n_steps_total = args.warmup + args.steps
+
+    def step_indices(s):
+        return shard[(torch.arange(nb) + s * nb) % shard.numel()]
+
+    eng = DockingSearch(L, (C0, C1), HID, max_rot=args.max_rot, device=device)
+    eng.set_receptor(rec_vols, rec_clash)
+    eng.set_ligand(lig_vols, None)
+    eng.set_filter(filt)
+    lig_dev = lig_coords.to(device)
+    R_dev = [Rall[step_indices(s)].to(device) for s in range(n_steps_total)]             # resident inputs (float64 like r_batch_cpu)
+    R_pin = [Rall[step_indices(s)].float().pin_memory() for s in range(n_steps_total)]   # host inputs for the e2e leg
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def device_step(s):
+        clash = clash_volumes(lig_dev, R_dev[s], device)
+        best, _ = eng.search(R_dev[s].to(torch.float32), TAU, clash)
+        return best
+
+    def host_step(s):
+        """End to end through the public API with HOST buffers: H2D of the step's rotation matrices from pinned
+        memory, clash re-projection + fused search, D2H of the step's best poses."""
+        Rd = R_pin[s].to(device, non_blocking=True)
+        clash = clash_volumes(lig_dev, Rd.double(), device)
+        best, _ = eng.search(Rd, TAU, clash)
+        return best.cpu()
+
+    # ---------------- device-resident leg (value, roofline) -------------------------------------------------
+    for s in range(args.warmup):
+        device_step(s)
+    barrier()
+    eng.profile(True)
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    launches0 = eng.launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    bests = []
+    for s in range(args.warmup, n_steps_total):
+        bests.append(device_step(s))
+    local_best = torch.cat(bests)
+    if world > 1:                                   # the one exchange of the path: final gather of the best poses
+        m = local_best.shape[0]
+        gathered = torch.empty(world * m, 4, device=device)
+        dist.all_gather_into_tensor(gathered, local_best)
+    ev1.record()
+    barrier()
+    clocks = sampler.stop() if sampler else None
+    ms = torch.tensor([ev0.elapsed_time(ev1)], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    launches = eng.launch_count() - launches0
+    prof = eng.profile_read()
+    eng.profile(False)
+    value = world * nb * args.steps / (ms_total * 1e-3)
+
+    # ---------------- end-to-end leg (host buffers) -----------------------------------------------------------
+    for s in range(min(args.warmup, 2)):
+        host_step(s)
+    barrier()
+    t0 = time.perf_counter()
+    ev0.record()
+    for s in range(args.warmup, n_steps_total):
+        host_step(s)
+    ev1.record()
+    barrier()
+    e2e_ms = torch.tensor([max(ev0.elapsed_time(ev1), 1e3 * (time.perf_counter() - t0))], device=device, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = world * nb * args.steps / (float(e2e_ms.item()) * 1e-3)
+
+    if rank == 0:
+        peak, peak_src = measured_peaks()
+        alg = algorithmic_bytes_per_rotation()
+        per_kernel = {}
+        for k, (tms, n) in prof.items():
+            if n == 0:
+                continue
+            rot_per_launch = nb * args.steps / n
+            gbs = alg[k] * rot_per_launch / (tms / n * 1e-3) / 1e9
+            per_kernel[k] = {"ms_per_launch": tms / n, "launches": n, "share_of_step": tms / ms_total,
+                             "algorithmic_GBps": gbs, "frac_of_hbm_peak": gbs / peak}
+        dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_launch"] * per_kernel[k]["launches"]) if per_kernel else None
+        roofline = None
+        if dom:
+            roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["algorithmic_GBps"], "peak": peak,
+                        "unit": "GB/s", "frac": per_kernel[dom]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
+                        "algorithmic_bytes_per_rotation": alg[dom]}
+        step_gbs = (value / world) * alg["total"] / 1e9
+        line = {
+            "metric": "rotations/sec (all translations scored)", "value": value, "unit": "rotations/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": workload_config(nb, world),
+            "e2e": {"value": e2e_value, "unit": "rotations/s", "h2d_bytes_per_step": nb * 36, "d2h_bytes_per_step": nb * 16},
+            "gpu_launches": launches,
+            "roofline": roofline,
+            "roofline_step": {"bound": "hbm", "achieved": step_gbs, "peak": peak, "unit": "GB/s", "frac": step_gbs / peak,
+                              "algorithmic_bytes_per_rotation": alg["total"], "note": "whole step per GPU (SURVEY.md 8d)"},
+            "kernels": per_kernel,
+            "clocks": clocks,
+        }
+        if world == 1 and args.cpu_rotations > 0:
+            t, n = cpu_baseline(rec_vols, rec_clash, lig_vols, lig_coords, filt, Rall, args.cpu_rotations)
+            line["cpu_baseline"] = {"value": n / t, "unit": "rotations/s", "cores": os.cpu_count() or 1, "kind": "port",
+                                    "sample": "%d rotations of oim10 (after 1 warm-up), CPU PyTorch torch.fft oracle, "
+                                              "receptor spectra precomputed" % n}
+        print(json.dumps(line), flush=True)
+    eng.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -26,6 +26,9 @@ SIGNATURES = {
     "dlpd_set_filter": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_float), POINTER(c_float)]),
     "dlpd_search": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "dlpd_search_host": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
+    "dlpd_profile_enable": (c_int, [c_void_p, c_int]),
+    "dlpd_profile_read": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_int), c_void_p]),
+    "dlpd_launch_count": (c_longlong, []),
     "dlpd_volume_rotate": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dlpd_volume_correlate": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
 }

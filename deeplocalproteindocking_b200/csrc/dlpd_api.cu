@@ -14,6 +14,7 @@
 // runtime shim
 // ------------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
+static long long g_launches = 0;     // kernels launched by this library (bench.py reports it as gpu_launches)
 static int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
@@ -38,6 +39,7 @@ template <class K> static int launch(dim3 g, const typename K::Params& p, dlpd_s
     for (unsigned z = 0; z < g.z; ++z)
         for (unsigned y = 0; y < g.y; ++y)
             for (unsigned x = 0; x < g.x; ++x) K::body(p, (int)x, (int)y, (int)z, smem.data());
+    ++g_launches;
     return 0;
 }
 #else
@@ -77,6 +79,7 @@ template <class K> static int launch(dim3 g, const typename K::Params& p, dlpd_s
     }
     dlpd_kernel<K><<<g, K::NT, K::SMEM, st>>>(p);
     CU(cudaGetLastError());
+    ++g_launches;
     return 0;
 }
 #endif
@@ -181,7 +184,50 @@ struct dlpd_plan {
     float b2;
     bool has_receptor, has_ligand, lig_has_clash, has_filter;
     long long bytes;
+    // optional per-kernel timing with CUDA events on the launching stream (dlpd_profile_*)
+    bool profile;
+    double prof_ms[DLPD_PROFILE_KINDS];
+    int prof_n[DLPD_PROFILE_KINDS];
+#if !defined(DLPD_EMU)
+    struct Span { int kind; cudaEvent_t a, b; };
+    std::vector<Span> spans;
+    std::vector<cudaEvent_t> pool;
+#endif
 };
+
+#if defined(DLPD_EMU)
+struct ProfScope { ProfScope(dlpd_plan*, int, dlpd_stream_t) {} };
+static int prof_collect(dlpd_plan*, dlpd_stream_t) { return 0; }
+#else
+static cudaEvent_t prof_event(dlpd_plan* p) {
+    cudaEvent_t e;
+    if (!p->pool.empty()) { e = p->pool.back(); p->pool.pop_back(); return e; }
+    cudaEventCreate(&e);
+    return e;
+}
+struct ProfScope {
+    dlpd_plan* p; int kind; dlpd_stream_t st; cudaEvent_t a, b;
+    ProfScope(dlpd_plan* p_, int kind_, dlpd_stream_t st_) : p(p_), kind(kind_), st(st_) {
+        if (p->profile) { a = prof_event(p); b = prof_event(p); cudaEventRecord(a, st); }
+    }
+    ~ProfScope() {
+        if (p->profile) { cudaEventRecord(b, st); p->spans.push_back({kind, a, b}); }
+    }
+};
+static int prof_collect(dlpd_plan* p, dlpd_stream_t st) {
+    CU(cudaStreamSynchronize(st));
+    for (auto& s : p->spans) {
+        float ms = 0.f;
+        CU(cudaEventElapsedTime(&ms, s.a, s.b));
+        p->prof_ms[s.kind] += ms;
+        p->prof_n[s.kind] += 1;
+        p->pool.push_back(s.a);
+        p->pool.push_back(s.b);
+    }
+    p->spans.clear();
+    return 0;
+}
+#endif
 
 static size_t n3(int n) { return (size_t)n * n * n; }
 
@@ -205,6 +251,10 @@ extern "C" int dlpd_plan_destroy(dlpd_plan* p) {
     rt_free(p->s1_0); rt_free(p->s1_1); rt_free(p->s2_0); rt_free(p->s2_1);
     rt_free(p->best); rt_free(p->dev_R); rt_free(p->dev_best);
     rt_free_host(p->pin_R); rt_free_host(p->pin_best);
+#if !defined(DLPD_EMU)
+    for (auto& sp : p->spans) { cudaEventDestroy(sp.a); cudaEventDestroy(sp.b); }
+    for (auto& e : p->pool) cudaEventDestroy(e);
+#endif
     delete p;
     return 0;
 }
@@ -228,6 +278,8 @@ extern "C" int dlpd_plan_create(dlpd_plan** out, int L, int C0, int C1, int H, i
     p->pin_R = p->pin_best = p->dev_R = p->dev_best = nullptr; p->host_cap = 0;
     p->has_receptor = p->has_ligand = p->lig_has_clash = p->has_filter = false;
     p->b2 = 0.f;
+    p->profile = false;
+    for (int i = 0; i < DLPD_PROFILE_KINDS; ++i) { p->prof_ms[i] = 0.0; p->prof_n[i] = 0; }
     const int N = 2 * L, L1 = L / 2, N1 = L;
     const size_t P = (size_t)p->P;
     struct { void** ptr; size_t bytes; } allocs[] = {
@@ -331,20 +383,23 @@ static int search_chunk(dlpd_plan* p, const float* R, const float* clash_rot, in
     FwdZParams f;
     f.src = p->lig0; f.src_pair_stride = 0; f.src_rot = clash_rot; f.R = R; f.out = p->s1_0; f.tw = p->tw0;
     f.C = p->C0 + 1; f.c_ext = p->C0; f.n_rot = n; f.center = center_of(L, p->center_mode);
-    TRY(launch_fwdz(L, f, P, st));
+    { ProfScope ps(p, DLPD_PROFILE_FWDZ0, st); TRY(launch_fwdz(L, f, P, st)); }
     f.src = p->lig1; f.src_rot = nullptr; f.out = p->s1_1; f.tw = p->tw1; f.C = p->C1; f.c_ext = -1;
     f.center = center_of(L1, p->center_mode);
-    TRY(launch_fwdz(L1, f, P, st));
+    { ProfScope ps(p, DLPD_PROFILE_FWDZ1, st); TRY(launch_fwdz(L1, f, P, st)); }
     PlaneParams q;
     q.in = p->s1_0; q.out = p->s2_0; q.spec = p->rspec0; q.spec_pair_stride = 0; q.tw = p->tw0; q.C = p->C0 + 1; q.P = P;
     q.scale = 1.f;
-    TRY(launch_plane(L, q, st));
+    { ProfScope ps(p, DLPD_PROFILE_PLANE0, st); TRY(launch_plane(L, q, st)); }
     q.in = p->s1_1; q.out = p->s2_1; q.spec = p->rspec1; q.tw = p->tw1; q.C = p->C1;
-    TRY(launch_plane(L1, q, st));
+    { ProfScope ps(p, DLPD_PROFILE_PLANE1, st); TRY(launch_plane(L1, q, st)); }
     int rc = DLPD_EINVAL;
+    {
+        ProfScope ps(p, DLPD_PROFILE_EPILOGUE, st);
 #define X(L_, A, B, C) if (p->L == L_ && p->C0 == A && p->C1 == B && p->H == C) rc = launch_epilogue<L_, A, B, C>(p, n, P, tau, out_scores, st);
-    DLPD_SEARCH_CONFIGS(X)
+        DLPD_SEARCH_CONFIGS(X)
 #undef X
+    }
     TRY(rc);
     DecodeParams d;
     d.best = p->best; d.out = out_best; d.n_rot = n; d.N = N;
@@ -390,6 +445,25 @@ extern "C" int dlpd_search_host(dlpd_plan* p, const float* R_host, int n, float 
     TRY(rt_copy(p->pin_best, p->dev_best, sizeof(float) * 4 * n, D2H, st));
     TRY(rt_sync(st));
     memcpy(best_host, p->pin_best, sizeof(float) * 4 * n);
+    return 0;
+}
+
+extern "C" long long dlpd_launch_count(void) { return g_launches; }
+
+extern "C" int dlpd_profile_enable(dlpd_plan* p, int on) {
+    if (!p) return fail(DLPD_EINVAL, "dlpd_profile_enable: NULL plan");
+    p->profile = on != 0;
+    return 0;
+}
+
+extern "C" int dlpd_profile_read(dlpd_plan* p, double* ms, int* launches, void* stream) {
+    if (!p || !ms || !launches) return fail(DLPD_EINVAL, "dlpd_profile_read: NULL argument");
+    TRY(rt_set_device(p->device));
+    TRY(prof_collect(p, (dlpd_stream_t)stream));
+    for (int i = 0; i < DLPD_PROFILE_KINDS; ++i) {
+        ms[i] = p->prof_ms[i]; launches[i] = p->prof_n[i];
+        p->prof_ms[i] = 0.0; p->prof_n[i] = 0;
+    }
     return 0;
 }
 

@@ -1,0 +1,51 @@
+"""Multi-GPU sharding of the rotation set: one process per GPU, rank r scores rotations
+{i : i mod W = r}; the only exchange is one all_gather of the per-rotation best poses at the end.
+
+The reference has no in-process parallelism (its 5-node run split *targets* across jobs, README.md:71), so there is
+nothing to mirror here beyond keeping the result identical to the single-GPU one.
+Works with any torch.distributed backend (nccl on the GPU box, gloo in the CPU tests)."""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def shard_indices(n_rot: int, rank: int, world: int) -> torch.Tensor:
+    """Interleaved shard: uniform cost per rank and file order preserved within a rank."""
+    if rank >= n_rot:
+        return torch.empty(0, dtype=torch.int64)
+    return torch.arange(rank, n_rot, world)
+
+
+def padded_shard_size(n_rot: int, world: int) -> int:
+    return (n_rot + world - 1) // world
+
+
+def gather_best(local_best: torch.Tensor, n_rot: int, rank: int, world: int, group=None) -> torch.Tensor:
+    """local_best [len(shard),4] (score,x,y,z) -> [n_rot,4] on every rank, rows in rotation order.
+
+    Shards are padded to ceil(n/W) rows with score=+inf so that one all_gather_into_tensor suffices."""
+    if world == 1:
+        return local_best
+    m = padded_shard_size(n_rot, world)
+    buf = torch.full((m, 4), float("inf"), device=local_best.device, dtype=local_best.dtype)
+    buf[:local_best.shape[0]] = local_best
+    out = torch.empty(world * m, 4, device=local_best.device, dtype=local_best.dtype)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    # rank r, local row j  ->  rotation j*W + r
+    full = out.reshape(world, m, 4).transpose(0, 1).reshape(world * m, 4)
+    return full[:n_rot].contiguous()
+
+
+def merge_top_lists(local_top: Sequence[Tuple[int, int, int, int, float]], K: int, group=None) -> List[tuple]:
+    """All-gather every rank's top list and reproduce the reference ordering (Docker.py:100-105): ascending score,
+    ties in rotation-file order (the order a single process would have appended them in)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        return list(local_top)[:K]
+    gathered: list = [None] * dist.get_world_size(group)
+    dist.all_gather_object(gathered, list(local_top), group=group)
+    merged = [t for part in gathered for t in part]
+    merged.sort(key=lambda t: (t[4], t[0]))
+    return merged[:K]

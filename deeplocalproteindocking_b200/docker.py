@@ -1,0 +1,245 @@
+"""`Docker`: the search driver with the reference's call surface (`/root/reference/src/Docker/Docker.py`).
+
+Same constructor arguments, `new_log` / `dockSE3` / `update_top`-ordering / `write_conformations` behaviour and
+pose-file format; the rotation loop (Docker.py:211-236) is one `DockingSearch.search` call per chunk of
+rotations instead of ~10 operator launches plus K host round trips per rotation.
+
+Proteins are given as `Atoms` (coords [Nat,3] Angstrom float64, types [Nat] in 0..10) -- PDB parsing and atom
+typing (`PDB2CoordsUnordered`, `Coords2TypedCoords`) are outside the search path; a `pdb_loader` callable can be
+supplied to accept paths like the reference does.
+"""
+from __future__ import annotations
+
+import atexit
+import os
+from dataclasses import dataclass
+from typing import Callable, List, Optional, Tuple
+
+import torch
+
+from .rotations import Rotations
+from .search import DockingSearch
+from .volume import TypedCoords2Volume
+
+NUM_ATOM_TYPES = 11
+
+
+@dataclass
+class Atoms:
+    coords: torch.Tensor      # [Nat,3] float64, Angstrom
+    types: torch.Tensor       # [Nat] int64 in [0, NUM_ATOM_TYPES)
+
+    def centred(self) -> "Atoms":
+        """bbox centre to the origin (`load_batch(bbox_center=False)`, Docker.py:54-59)."""
+        c = self.coords.to(torch.float64)
+        return Atoms(c - 0.5 * (c.min(dim=0).values + c.max(dim=0).values), self.types)
+
+
+def random_rotation(generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """Uniform random rotation [3,3] float64 (stands in for TPL `getRandomRotation`, Docker.py:44)."""
+    q = torch.randn(4, dtype=torch.float64, generator=generator)
+    w, x, y, z = (q / q.norm()).tolist()
+    return torch.tensor([[1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)],
+                         [2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)],
+                         [2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)]], dtype=torch.float64)
+
+
+def typed_layout(atoms: Atoms, device) -> Tuple[torch.Tensor, torch.Tensor, torch.Tensor]:
+    """Atoms -> (coords [1,3*Nat] sorted by type, num_atoms_of_type [1,11], offsets [1,11]): TPL's typed-coords layout."""
+    order = torch.argsort(atoms.types, stable=True)
+    coords = atoms.coords[order].reshape(1, -1)
+    counts = torch.bincount(atoms.types, minlength=NUM_ATOM_TYPES)[:NUM_ATOM_TYPES]
+    offsets = torch.cumsum(counts, 0) - counts
+    return coords.to(device), counts.reshape(1, -1).to(torch.int32), offsets.reshape(1, -1).to(torch.int32)
+
+
+def project_density_batched(coords: torch.Tensor, box_size: int, resolution: float) -> torch.Tensor:
+    """[n,Nat,3] float32 -> [n,L,L,L]: summed (all types) Gaussian density, same stencil as TypedCoords2Volume.
+    This is `project(...).sum(dim=1)` of the in-loop ligand re-projection (Docker.py:221-224), batched over rotations."""
+    n, nat, _ = coords.shape
+    L = box_size
+    d = torch.arange(-2, 3, device=coords.device)
+    stencil = torch.stack(torch.meshgrid(d, d, d, indexing="ij"), dim=-1).reshape(1, 1, -1, 3)
+    ijk = torch.floor(coords / resolution).to(torch.int64).unsqueeze(2) + stencil                  # [n,Nat,125,3]
+    ok = ((ijk >= 0) & (ijk < L)).all(dim=-1)
+    r2 = ((coords.unsqueeze(2) - ijk.to(coords.dtype) * resolution) ** 2).sum(dim=-1)
+    val = torch.exp(-r2 / 2.0) * ok.to(coords.dtype)
+    c = ijk.clamp(0, L - 1)
+    lin = (c[..., 0] * L + c[..., 1]) * L + c[..., 2]
+    out = torch.zeros(n, L * L * L, device=coords.device, dtype=coords.dtype)
+    out.scatter_add_(1, lin.reshape(n, -1), val.reshape(n, -1))
+    return out.reshape(n, L, L, L)
+
+
+def top_conformations(V: torch.Tensor, K: int) -> List[Tuple[int, int, int, float]]:
+    """The K-iteration extraction loop of `Docker.update_top` (Docker.py:88-98) without K host round trips.
+
+    Negative scores come out in (score, row-major index) order; once the minimum is >= 0 the reference's loop
+    keeps returning the first zero voxel (masked, or already extracted and overwritten with 0.0), which this
+    reproduces, duplicates included."""
+    N1, N2, N3 = V.shape
+    flat = V.reshape(-1)
+    vals, idx = torch.sort(flat, stable=True)
+    n_neg = int((vals < 0).sum())
+    take = min(K, n_neg)
+    v_h, i_h = vals[:take].tolist(), idx[:take].tolist()
+    top = [(i // (N2 * N3), (i // N3) % N2, i % N3, s) for s, i in zip(v_h, i_h)]
+    if len(top) == K:
+        return top
+    zeros = torch.nonzero(flat == 0).reshape(-1)
+    pool = ([int(zeros[0])] if zeros.numel() else []) + i_h
+    if not pool:
+        i = int(idx[0])
+        top.append((i // (N2 * N3), (i // N3) % N2, i % N3, float(vals[0])))
+        pool = [i]
+    i0 = min(pool)
+    s0 = float(flat[i0]) if (zeros.numel() and i0 == int(zeros[0])) else 0.0
+    while len(top) < K:
+        top.append((i0 // (N2 * N3), (i0 // N3) % N2, i0 % N3, s0))
+        s0 = 0.0
+    return top
+
+
+class Docker:
+    def __init__(self, docking_model, angle_inc=15.0, box_size=80, resolution=1.25, max_conf=1000, randomize_rot=False,
+                 rot_batch: int = 16, center: str = "box", clash_source: str = "project",
+                 pdb_loader: Optional[Callable[[str], Atoms]] = None, device=None, generator=None, verbose=False):
+        """Reference arguments first (Docker.py:18); then: `rot_batch` rotations per fused call, rotation `center`
+        convention, `clash_source` = 'project' (re-project rotated atoms, Docker.py:221-224) or 'rotate' (rotate the
+        summed ligand density with the feature volumes)."""
+        self.docking_model = docking_model
+        self.log = None
+        self.box_size, self.resolution = int(box_size), float(resolution)
+        self.box_length = box_size * resolution
+        self.max_conf = int(max_conf)
+        self.rot = Rotations(angle_inc=angle_inc, verbose=verbose)
+        self.device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+        self.project = TypedCoords2Volume(self.box_size, self.resolution)
+        self.box_center = torch.full((1, 3), self.box_length / 2.0, dtype=torch.float64)
+        self.randomize_rot = randomize_rot
+        if randomize_rot:
+            self.randR = random_rotation(generator).unsqueeze(0)
+            if verbose:
+                print("Adding random rotation to the receptor:", self.randR)
+        self.rot_batch, self.center, self.clash_source = int(rot_batch), center, clash_source
+        self.pdb_loader = pdb_loader
+        self.top_list: list = []
+        self.best_per_rotation: Optional[torch.Tensor] = None
+        self._engine: Optional[DockingSearch] = None
+        atexit.register(self.cleanup)
+
+    # ---- log handling: same resume rule as Docker.new_log (Docker.py:63-80) -----------------------------------
+    def new_log(self, log_file_name, rewrite=True):
+        if self.log is not None:
+            self.log.close()
+            self.log = None
+        if os.path.exists(log_file_name) and not rewrite:
+            with open(log_file_name, "r") as fin:
+                n_lines = sum(1 for line in fin if len(line.split()) > 0)
+            if n_lines > 1:
+                return False
+        self.log = open(log_file_name, "w")
+        return True
+
+    def cleanup(self):
+        if self.log is not None:
+            self.log.close()
+            self.log = None
+
+    # ---- set-up (Docker.py:190-209) ----------------------------------------------------------------------
+    def _atoms(self, protein) -> Atoms:
+        if isinstance(protein, Atoms):
+            return protein
+        if isinstance(protein, str):
+            if self.pdb_loader is None:
+                raise Exception("PDB input needs a pdb_loader (PDB parsing is outside the search path)", protein)
+            return self.pdb_loader(protein)
+        coords, types = protein
+        return Atoms(torch.as_tensor(coords, dtype=torch.float64), torch.as_tensor(types, dtype=torch.int64))
+
+    def _volumes(self, atoms: Atoms):
+        coords, nat, off = typed_layout(Atoms(atoms.coords.to(torch.float32), atoms.types), self.device)
+        density = self.project(coords, nat, off)                         # [1,11,L,L,L]
+        vols = self.docking_model.representation(density)
+        return [v[0] for v in vols], density.sum(dim=1)[0]
+
+    def _engine_for(self, vols) -> DockingSearch:
+        key = (self.box_size, vols[0].shape[0], vols[1].shape[0])
+        if self._engine is None or self._engine_key != key:
+            if self._engine is not None:
+                self._engine.close()
+            hidden = self.docking_model.filter.fc[0].out_features
+            self._engine = DockingSearch(self.box_size, (key[1], key[2]), hidden, max_rot=self.rot_batch,
+                                         center=self.center, device=self.device)
+            self._engine_key = key
+        return self._engine
+
+    # ---- the search ----------------------------------------------------------------------------------------
+    def dockSE3(self, ureceptor, uligand, batch_size=None, rotation_subset: Optional[torch.Tensor] = None):
+        """Dock two proteins (Docker.py:184-238).  `batch_size` is accepted for call compatibility (the reference
+        scores that many rotations per step; here `rot_batch` rotations go into every fused call)."""
+        self.top_list = []
+        self.docking_model.eval()
+        with torch.no_grad():
+            rec = self._atoms(ureceptor).centred()
+            lig = self._atoms(uligand).centred()
+            rcoords = rec.coords
+            if self.randomize_rot:
+                rcoords = rcoords @ self.randR[0].t()
+            rec_vols, rec_forbidden = self._volumes(Atoms(rcoords + self.box_center, rec.types))
+            lig_vols, lig_density = self._volumes(Atoms(lig.coords + self.box_center, lig.types))
+            eng = self._engine_for(rec_vols)
+            eng.set_receptor(rec_vols, rec_forbidden)
+            eng.set_ligand(lig_vols, lig_density if self.clash_source == "rotate" else None)
+            eng.set_filter(self.docking_model.filter)
+            tau = float(self.docking_model.threshold_clash)
+            rot_idx = torch.arange(len(self.rot)) if rotation_subset is None else torch.as_tensor(rotation_subset)
+            lig_dev = lig.coords.to(self.device)
+            best_all = torch.empty(rot_idx.numel(), 4, device=self.device)
+            exact_topk = self.max_conf > 1
+            for i0 in range(0, rot_idx.numel(), self.rot_batch):
+                sel = rot_idx[i0:i0 + self.rot_batch]
+                Rb = self.rot.R[sel].to(self.device)                     # float64, like r_batch_cpu (Docker.py:214)
+                clash_rot = None
+                if self.clash_source == "project":
+                    moved = torch.einsum("nij,aj->nai", Rb, lig_dev) + self.box_length / 2.0
+                    clash_rot = project_density_batched(moved.to(torch.float32), self.box_size, self.resolution)
+                best, scores = eng.search(Rb.to(torch.float32), tau, clash_rot, return_scores=exact_topk)
+                best_all[i0:i0 + sel.numel()] = best
+                if exact_topk:
+                    for j, r in enumerate(sel.tolist()):
+                        self.update_top(scores[j], r)
+            self.best_per_rotation = best_all.cpu()
+            if not exact_topk:
+                b = self.best_per_rotation
+                items = [(int(r), int(b[j, 1]), int(b[j, 2]), int(b[j, 3]), float(b[j, 0])) for j, r in enumerate(rot_idx.tolist())]
+                items.sort(key=lambda t: t[4])
+                self.top_list = items[:self.max_conf]
+        self.write_conformations()
+
+    def update_top(self, V, rotation_index):
+        """Merge the `max_conf` best translations of one rotation into the global list (Docker.py:86-105)."""
+        for x, y, z, score in top_conformations(V, self.max_conf):
+            self.top_list.append((rotation_index, x, y, z, score))
+        self.top_list.sort(key=lambda t: t[4])
+        self.top_list = self.top_list[:self.max_conf]
+
+    # ---- output (Docker.py:107-133) --------------------------------------------------------------------------
+    def conformation(self, entry):
+        i, x, y, z, score = entry
+        r = self.rot.R[i]
+        t = torch.tensor([a if a < self.box_size else -(2 * self.box_size - a) for a in (x, y, z)], dtype=torch.float64)
+        t = t * self.resolution
+        if self.randomize_rot:
+            rt = self.randR[0].t()
+            t, r = rt @ t, rt @ r
+        return r, t, score
+
+    def write_conformations(self):
+        if self.log is None:
+            return
+        for entry in self.top_list:
+            r, t, score = self.conformation(entry)
+            vals = [float(r[a, b]) for a in range(3) for b in range(3)] + [float(v) for v in t]
+            self.log.write("".join("%f\t" % v for v in vals) + "%f\n" % score)
+        self.log.flush()

@@ -79,6 +79,20 @@ int dlpd_search(dlpd_plan* plan, const float* R, const float* lig_clash_rot, int
  * and synchronises the stream before returning.  This is the end-to-end call bench.py times. */
 int dlpd_search_host(dlpd_plan* plan, const float* R_host, int n, float tau, float* best_host, void* stream);
 
+/* ---- measurement hooks (bench.py) ----------------------------------------------------------------------
+ * Per-kernel device time with CUDA events recorded on the launching stream around every launch of dlpd_search. */
+#define DLPD_PROFILE_FWDZ0 0     /* gather + z transform, level 0 (+ clash channel) */
+#define DLPD_PROFILE_FWDZ1 1     /* same, level 1 */
+#define DLPD_PROFILE_PLANE0 2    /* y/x transforms, receptor multiply, inverse x/y, level 0 */
+#define DLPD_PROFILE_PLANE1 3    /* same, level 1 */
+#define DLPD_PROFILE_EPILOGUE 4  /* inverse z + filter + mask + argmin */
+#define DLPD_PROFILE_KINDS 5
+int dlpd_profile_enable(dlpd_plan* plan, int on);
+/* Synchronises `stream`, returns accumulated milliseconds and launch counts per kind, and resets them. */
+int dlpd_profile_read(dlpd_plan* plan, double* ms, int* launches, void* stream);
+/* Number of kernels this library has launched in the calling process so far. */
+long long dlpd_launch_count(void);
+
 /* ---- standalone operators (module-level drop-ins) --------------------------------------------------------
  * TorchProteinLibrary.Volume.VolumeRotation.forward(volume, R)   (Docker.py:40,218)
  *   out[b,c,p] = trilinear(vol[b,c], ctr + R_b^T (p - ctr)), zero outside;  vol/out [B][C][L^3], R [B][9] */

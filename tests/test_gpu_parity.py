@@ -1,0 +1,193 @@
+"""GPU parity tests: the CUDA path (libdlpd.so through the package API) vs the CPU oracle and the golden fixtures.
+Tolerances: indices exact; scores |s - s_ref| <= 1e-4 * max(|s_ref|, 1e-3 * max|V|) (BASELINE.json north_star)."""
+import os
+
+import pytest
+import torch
+
+from oracle import docking_oracle as O
+from deeplocalproteindocking_b200 import (DockingSearch, VolumeConvolution, VolumeRotation, GlobalDockingModel,
+                                          SimpleFilter, rotations, synthetic, _lib)
+
+pytestmark = pytest.mark.gpu
+R20 = rotations.Rotations(20).R
+DEV = "cuda:0"
+
+
+def _d(t):
+    return t.double()
+
+
+@pytest.mark.parametrize("L,center", [(8, "box"), (16, "grid"), (40, "box"), (80, "box")])
+def test_volume_rotation_matches_oracle(L, center):
+    g = torch.Generator().manual_seed(L)
+    vol = torch.randn(2, 3, L, L, L, generator=g)
+    R = R20[[17, 1234]]
+    got = VolumeRotation(center)(vol.to(DEV), R.float().to(DEV)).cpu()
+    want = O.rotate_volume(_d(vol), R, center)
+    assert (got.double() - want).abs().max() < 5e-5
+    # inputs untouched, new tensor returned, identity rotation is exact
+    ident = VolumeRotation(center)(vol.to(DEV), torch.eye(3, device=DEV).repeat(2, 1, 1)).cpu()
+    assert torch.equal(ident, vol)
+
+
+@pytest.mark.parametrize("L", [4, 8, 10, 16, 20, 40, 80])
+def test_volume_convolution_matches_oracle(L):
+    g = torch.Generator().manual_seed(100 + L)
+    B, C = (2, 3) if L <= 40 else (1, 2)
+    v1 = torch.randn(B, C, L, L, L, generator=g)
+    v2 = torch.randn(B, C, L, L, L, generator=g)
+    got = VolumeConvolution(clip=5.0)(v1.to(DEV), v2.to(DEV)).cpu()
+    want = O.correlate(_d(v1), _d(v2))
+    assert got.shape == want.shape
+    assert (got.double() - want).abs().max() <= 2e-5 * want.abs().max()
+    assert got[:, :, L].abs().max() <= 2e-5 * want.abs().max()          # the d = -L plane has no overlap
+
+
+def test_volume_convolution_golden_multiply_volumes(golden_dir):
+    """Values produced by the reference's MultiplyVolumes.multiply (tests/golden/correlation.pt); the 6^3 fixture is
+    zero-padded to a compiled size (same sums for |d| < 6)."""
+    g = torch.load(os.path.join(golden_dir, "correlation.pt"), weights_only=False)
+    pad = lambda v: torch.nn.functional.pad(v.float(), (0, 2, 0, 2, 0, 2))
+    corr = VolumeConvolution()(pad(g["v1"])[None].to(DEV), pad(g["v2"])[None].to(DEV)).cpu()[0]
+    for d, val in zip(g["d"].tolist(), g["values"]):
+        t = [a % 16 for a in d]
+        assert torch.allclose(corr[:, t[0], t[1], t[2]].double(), val, rtol=0, atol=2e-5 * float(g["values"].abs().max()))
+
+
+def test_global_docking_model_golden(golden_dir):
+    """Reference GlobalDockingModel.forward output through (a) the module-level drop-in, (b) the fused search."""
+    g = torch.load(os.path.join(golden_dir, "global_model.pt"), weights_only=False)
+    V = g["V_global"]
+    filt = SimpleFilter([4, 6])
+    filt.fc[0].weight.data, filt.fc[0].bias.data = g["W1"].float(), g["b1"].float()
+    filt.fc[2].weight.data, filt.fc[2].bias.data = g["W2"].float(), g["b2"].float()
+    model = GlobalDockingModel(torch.nn.Identity(), filt).to(DEV)
+    with torch.no_grad():
+        Vm = model([v.float().to(DEV) for v in g["rec"]], [v.float().to(DEV) for v in g["lig"]]).cpu()[0]
+    assert (Vm.double() - V).abs().max() <= 1e-4 * V.abs().max()
+    eng = DockingSearch(8, (4, 6), 5, max_rot=2, device=DEV)
+    eng.set_receptor([v[0] for v in g["rec"]], torch.zeros(8, 8, 8))
+    eng.set_ligand([v[0] for v in g["lig"]], torch.zeros(8, 8, 8))
+    eng.set_filter(filt)
+    best, scores = eng.search(torch.eye(3)[None], 1.0, return_scores=True)
+    assert (scores[0].cpu().double() - V).abs().max() <= 1e-4 * V.abs().max()
+    s, x, y, z = O.best_pose(V)
+    assert [int(v) for v in best[0, 1:].cpu()] == [x, y, z]
+    eng.close()
+
+
+def _case(L, C0, C1, seed):
+    g = torch.Generator().manual_seed(seed)
+    L1 = L // 2
+    rec = [torch.randn(C0, L, L, L, generator=g), torch.randn(C1, L1, L1, L1, generator=g)]
+    lig = [torch.randn(C0, L, L, L, generator=g), torch.randn(C1, L1, L1, L1, generator=g)]
+    rf = torch.rand(L, L, L, generator=g) * 2
+    lf = torch.rand(L, L, L, generator=g) * 2
+    return rec, lig, rf, lf
+
+
+def _check_against_oracle(best, scores, rec, lig, rf, lf, Rs, filt, tau, clash_rot=None):
+    spectra = O.ReceptorSpectra([_d(r)[None] for r in rec], _d(rf)[None, None])
+    f64 = filt.to(torch.float64)
+    for i in range(Rs.shape[0]):
+        if clash_rot is None:
+            V = O.score_rotation(spectra, [_d(l)[None] for l in lig], _d(lf), Rs[i], f64, tau)
+            lrot = O.rotate_volume(_d(lf)[None, None], Rs[i][None])
+        else:
+            V = O.score_rotation(spectra, [_d(l)[None] for l in lig], _d(clash_rot[i]), Rs[i], f64, tau,
+                                 ligand_forbidden_is_rotated=True)
+            lrot = _d(clash_rot[i])[None, None]
+        scale = float(V.abs().max())
+        s, x, y, z = O.best_pose(V)
+        assert [int(v) for v in best[i, 1:]] == [x, y, z], (i, best[i], (s, x, y, z))
+        assert abs(float(best[i, 0]) - s) <= 1e-4 * max(abs(s), 1e-3 * scale)
+        if scores is not None:
+            clash = O.correlate(_d(rf)[None, None], lrot)[0, 0]
+            safe = (clash - tau).abs() > 1e-4 * clash.abs().max()      # threshold-straddling voxels may flip in fp32
+            assert (scores[i].double() - V).abs()[safe].max() <= 1e-4 * scale
+
+
+@pytest.mark.parametrize("L,C0,C1,H,n", [(8, 4, 6, 5, 5), (16, 4, 6, 5, 4), (20, 4, 6, 5, 3), (8, 16, 32, 24, 3),
+                                         (16, 16, 32, 24, 2), (20, 16, 32, 24, 5)])
+def test_search_small_matches_oracle(L, C0, C1, H, n):
+    rec, lig, rf, lf = _case(L, C0, C1, seed=L * 10 + C0)
+    filt = O.FilterWeights.random(C0 + C1, H, seed=3)
+    Rs = R20[torch.arange(n) * 311 + 5]
+    tau = float(torch.quantile(O.correlate(rf[None, None], lf[None, None]).flatten(), 0.7))
+    eng = DockingSearch(L, (C0, C1), H, max_rot=4, device=DEV)
+    eng.set_receptor(rec, rf); eng.set_ligand(lig, lf); eng.set_filter((filt.W1, filt.b1, filt.W2, filt.b2))
+    best, scores = eng.search(Rs, tau, return_scores=True)
+    best_host = eng.search_host(Rs.float(), tau)
+    eng.close()
+    assert torch.equal(best.cpu(), best_host)
+    _check_against_oracle(best.cpu(), scores.cpu(), rec, lig, rf, lf, Rs, filt, tau)
+
+
+def test_search_full_size_80_matches_oracle():
+    """BASELINE config shape: L=80, 16@80^3 + 32@40^3 + clash, 48->24->1 filter; 3 rotations (odd tail) vs fp64 oracle."""
+    L, C0, C1 = 80, 16, 32
+    rec, rec_clash = synthetic.learned_volumes(L, (C0, C1), seed=11)
+    lig, lig_clash = synthetic.learned_volumes(L, (C0, C1), seed=12)
+    filt = O.FilterWeights.random(C0 + C1, seed=13)
+    Rs = R20[[7, 777, 1777]]
+    tau = 30.0
+    eng = DockingSearch(L, (C0, C1), max_rot=4, device=DEV)
+    eng.set_receptor(rec, rec_clash); eng.set_ligand(lig, lig_clash); eng.set_filter((filt.W1, filt.b1, filt.W2, filt.b2))
+    best, scores = eng.search(Rs, tau, return_scores=True)
+    best2, _ = eng.search(Rs, tau)
+    eng.close()
+    assert torch.equal(best, best2)
+    _check_against_oracle(best.cpu(), scores.cpu(), rec, lig, rec_clash, lig_clash, Rs, filt, tau)
+
+
+def test_search_prerotated_clash_and_chunking_invariance():
+    L, C0, C1, H = 20, 16, 32, 24
+    rec, lig, rf, lf = _case(L, C0, C1, seed=5)
+    filt = O.FilterWeights.random(C0 + C1, H, seed=6)
+    Rs = R20[torch.arange(7) * 199 + 1]
+    clash_rot = torch.stack([O.rotate_volume(lf[None, None], Rs[i][None].float())[0, 0] for i in range(7)])
+    tau = 60.0
+    out = []
+    for max_rot in (2, 3, 16):
+        eng = DockingSearch(L, (C0, C1), H, max_rot=max_rot, device=DEV)
+        eng.set_receptor(rec, rf); eng.set_ligand(lig, None); eng.set_filter((filt.W1, filt.b1, filt.W2, filt.b2))
+        with pytest.raises(_lib.DlpdError):
+            eng.search(Rs, tau)                                     # no clash volume anywhere: loud failure
+        b, _ = eng.search(Rs, tau, ligand_forbidden_rotated=clash_rot)
+        out.append(b.cpu())
+        eng.close()
+    _check_against_oracle(out[0], None, rec, lig, rf, lf, Rs, filt, tau, clash_rot=clash_rot)
+    for b in out[1:]:
+        assert torch.equal(b[:, 1:], out[0][:, 1:])
+        assert torch.allclose(b[:, 0], out[0][:, 0], rtol=1e-5, atol=1e-6)
+
+
+def test_masked_ties_resolve_to_first_voxel():
+    """Everything forbidden (tau below every clash value) -> V == 0 everywhere -> argmin is voxel (0,0,0) (Docker.py:91-96)."""
+    L, C0, C1, H = 8, 4, 6, 5
+    rec, lig, rf, lf = _case(L, C0, C1, seed=9)
+    filt = O.FilterWeights.random(C0 + C1, H, seed=1)
+    eng = DockingSearch(L, (C0, C1), H, device=DEV)
+    eng.set_receptor(rec, rf); eng.set_ligand(lig, lf); eng.set_filter((filt.W1, filt.b1, filt.W2, filt.b2))
+    best, scores = eng.search(R20[:3], -1.0, return_scores=True)
+    eng.close()
+    assert torch.count_nonzero(scores) == 0
+    assert torch.equal(best.cpu(), torch.zeros(3, 4))
+
+
+def test_errors_are_loud():
+    with pytest.raises(_lib.DlpdError):
+        DockingSearch(12, (4, 6), 5, device=DEV)                    # not a compiled configuration
+    with pytest.raises(_lib.DlpdError):
+        VolumeConvolution()(torch.zeros(1, 1, 8, 8, 8), torch.zeros(1, 1, 8, 8, 8))   # CPU tensors: no CPU path
+    with pytest.raises(_lib.DlpdError):
+        VolumeConvolution()(torch.zeros(1, 1, 12, 12, 12, device=DEV), torch.zeros(1, 1, 12, 12, 12, device=DEV))
+    eng = DockingSearch(8, (4, 6), 5, device=DEV)
+    with pytest.raises(_lib.DlpdError):
+        eng.search(R20[:2], 1.0)                                    # nothing set yet
+    eng.close()
+    v = torch.zeros(1, 1, 8, 8, 8, device=DEV, requires_grad=True)
+    out = VolumeConvolution()(v, v.detach())
+    with pytest.raises(NotImplementedError):
+        out.sum().backward()

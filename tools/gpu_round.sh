@@ -1,0 +1,38 @@
+#!/bin/bash
+# One GPU-box visit: parity tests, smoke, bench, ncu launch list and full captures.  Everything lands in gpurun_out/.
+# usage: tools/gpu_round.sh [tag] [stages...]   stages default: tests smoke bench launches ncu
+set -u
+TAG=${1:-r01}; shift || true
+STAGES=${*:-tests smoke bench launches ncu}
+OUT=gpurun_out/$TAG
+mkdir -p $OUT
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,memory.total,power.limit --format=csv > $OUT/gpu.csv 2>&1
+python -c "import os; print('cpu_count', os.cpu_count())" >> $OUT/gpu.csv
+for s in $STAGES; do
+  case $s in
+    tests)
+      timeout 900 python -m pytest tests -m gpu -x -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log ;;
+    tests_all)
+      timeout 1200 python -m pytest tests -m gpu -q > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_gpu.log ;;
+    smoke)
+      timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?" >> $OUT/smoke.log ;;
+    bench)
+      timeout 900 python bench.py --steps 10 --warmup 3 > $OUT/bench.log 2>&1; echo "bench rc=$?" >> $OUT/bench.log ;;
+    launches)
+      timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:dlpd_kernel -c 60 --csv \
+        --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --cpu-rotations 0 --rot-batch 16 --max-rot 16 \
+        > $OUT/launches_run.log 2>&1 ;;
+    ncu)
+      timeout 900 ncu --set full --clock-control none --import-source on -k regex:dlpd_kernel -s 4 -c 5 -o $OUT/prof -f \
+        python bench.py --steps 1 --warmup 0 --cpu-rotations 0 --rot-batch 8 --max-rot 8 > $OUT/ncu_run.log 2>&1 ;;
+    sanitize)
+      timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -q -x -k "small or ties" \
+        > $OUT/memcheck.log 2>&1
+      timeout 600 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -q -x -k "small_matches_oracle and 8-4" \
+        > $OUT/racecheck.log 2>&1 ;;
+    scale2)
+      timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
+        bench.py --gpus 2 --steps 10 --warmup 3 > $OUT/bench_2gpu.log 2>&1 ;;
+  esac
+done
+tail -5 $OUT/*.log
