@@ -1,0 +1,32 @@
+"""Summarise an ncu raw CSV (ncu -i X.ncu-rep --page raw --csv) into the handful of metrics we track."""
+import csv
+import sys
+
+WANT = ['gpu__time_duration.sum', 'dram__bytes_read.sum', 'dram__bytes_write.sum',
+        'dram__throughput.avg.pct_of_peak_sustained_elapsed', 'lts__throughput.avg.pct_of_peak_sustained_elapsed',
+        'l1tex__throughput.avg.pct_of_peak_sustained_elapsed', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
+        'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'sm__warps_active.avg.pct_of_peak_sustained_active', 'launch__registers_per_thread',
+        'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_registers', 'launch__grid_size',
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'lts__t_sector_hit_rate.pct', 'l1tex__t_sector_hit_rate.pct', 'smsp__inst_executed.sum',
+        'smsp__average_warp_latency_issue_stalled_barrier.ratio', 'smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio',
+        'smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio', 'smsp__average_warp_latency_issue_stalled_mio_throttle.ratio',
+        'smsp__average_warp_latency_issue_stalled_lg_throttle.ratio', 'smsp__average_warp_latency_issue_stalled_math_pipe_throttle.ratio',
+        'smsp__average_warp_latency_issue_stalled_not_selected.ratio', 'smsp__average_warp_latency_issue_stalled_wait.ratio']
+
+
+def main(path):
+    rows = list(csv.reader(open(path)))
+    hdr, units, data = rows[0], rows[1], rows[2:]
+    idx = {h: i for i, h in enumerate(hdr)}
+    names = [r[idx['Kernel Name']].replace('void dlpd_kernel<', '').replace('>(Params)', '') for r in data]
+    print('%-72s' % 'metric', ' | '.join('%-22s' % n[:22] for n in names))
+    for w in WANT:
+        if w not in idx:
+            continue
+        print('%-72s' % (w + ' [' + units[idx[w]] + ']'), ' | '.join('%-22s' % r[idx[w]][:22] for r in data))
+
+
+if __name__ == '__main__':
+    main(sys.argv[1])
