@@ -10,7 +10,8 @@ import os
 from ctypes import POINTER, c_char_p, c_float, c_int, c_longlong, c_void_p
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdlpd.so")
+# DLPD_LIB_PATH selects another BUILD of the same CUDA library (tuning experiments); there is still no CPU path
+LIB_PATH = os.environ.get("DLPD_LIB_PATH") or os.path.join(_HERE, "libdlpd.so")
 
 # name -> (restype, argtypes); mirrors include/dlpd.h one to one
 SIGNATURES = {

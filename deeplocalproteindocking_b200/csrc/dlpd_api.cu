@@ -96,6 +96,8 @@ template <class K> static int launch(dim3 g, const typename K::Params& p, dlpd_s
 template <int L> struct Tile {
     static constexpr int FWD_YT = (L > 40) ? 40 : L;      // y lines per FwdZ CTA
     static constexpr int INV_YT = ((2 * L) % 8 == 0) ? 8 : (((2 * L) % 4 == 0) ? 4 : 2);
+    static constexpr int CL_YT = (L % 8 == 0) ? 8 : ((L % 4 == 0) ? 4 : 2);   // y lines per FwdZC CTA
+    static constexpr int CL_CG = 8;                                           // channels per FwdZC CTA
 };
 
 // box sizes the single-level kernels are compiled for
@@ -134,6 +136,10 @@ template <int L> static int launch_fwdz_t(const FwdZParams& p, int P, dlpd_strea
     typedef FwdZ<L, Tile<L>::FWD_YT> K;
     return launch<K>(dim3(L * K::YTILES, p.C, P), p, st);
 }
+template <int L> static int launch_fwdzc_t(const FwdZCParams& p, int P, dlpd_stream_t st) {
+    typedef FwdZC<L, Tile<L>::CL_CG, Tile<L>::CL_YT> K;
+    return launch<K>(dim3(L * K::YTILES, p.C / K::CG, P), p, st);
+}
 template <int L> static int launch_plane_t(const PlaneParams& p, dlpd_stream_t st) {
     return launch<Plane<L> >(dim3((unsigned)(p.P * 2 * L * p.C)), p, st);
 }
@@ -149,6 +155,15 @@ static int launch_fwdz(int L, const FwdZParams& p, int P, dlpd_stream_t st) {
     }
     return fail(DLPD_EINVAL, "unsupported box size");
 }
+static int launch_fwdzc(int L, const FwdZCParams& p, int P, dlpd_stream_t st) {
+    switch (L) {
+#define X(L_) case L_: return launch_fwdzc_t<L_>(p, P, st);
+        DLPD_OP_SIZES(X)
+#undef X
+    }
+    return fail(DLPD_EINVAL, "unsupported box size");
+}
+static bool channel_last_ok(int C) { return C % 8 == 0; }
 static int launch_plane(int L, const PlaneParams& p, dlpd_stream_t st) {
     switch (L) {
 #define X(L_) case L_: return launch_plane_t<L_>(p, st);
@@ -174,6 +189,7 @@ struct dlpd_plan {
     int P;                       // pairs per chunk
     cpx *tw0, *tw1, *tw2;        // tables of size 2L, L, L/2... (tw2 unused by kernels; kept for symmetry)
     float *lig0, *lig1;          // [(C0+1)][L^3], [C1][(L/2)^3]
+    float *lig0_cl, *lig1_cl;    // channel-last copies [L^3][C0], [(L/2)^3][C1] of the feature volumes (FwdZC)
     cpx *rspec0, *rspec1;        // receptor spectra [(C0+1)][N^3], [C1][L^3]
     cpx *s1_0, *s1_1, *s2_0, *s2_1;
     unsigned long long* best;    // [max_rot]
@@ -247,7 +263,7 @@ extern "C" int dlpd_plan_destroy(dlpd_plan* p) {
     if (!p) return 0;
     rt_set_device(p->device);
     rt_free(p->tw0); rt_free(p->tw1); rt_free(p->tw2);
-    rt_free(p->lig0); rt_free(p->lig1); rt_free(p->rspec0); rt_free(p->rspec1);
+    rt_free(p->lig0); rt_free(p->lig1); rt_free(p->lig0_cl); rt_free(p->lig1_cl); rt_free(p->rspec0); rt_free(p->rspec1);
     rt_free(p->s1_0); rt_free(p->s1_1); rt_free(p->s2_0); rt_free(p->s2_1);
     rt_free(p->best); rt_free(p->dev_R); rt_free(p->dev_best);
     rt_free_host(p->pin_R); rt_free_host(p->pin_best);
@@ -274,6 +290,7 @@ extern "C" int dlpd_plan_create(dlpd_plan** out, int L, int C0, int C1, int H, i
     p->L = L; p->C0 = C0; p->C1 = C1; p->H = H; p->max_rot = max_rot; p->center_mode = center_mode; p->device = device;
     p->P = (max_rot + 1) / 2;
     p->tw0 = p->tw1 = p->tw2 = nullptr; p->lig0 = p->lig1 = nullptr; p->rspec0 = p->rspec1 = nullptr;
+    p->lig0_cl = p->lig1_cl = nullptr;
     p->s1_0 = p->s1_1 = p->s2_0 = p->s2_1 = nullptr; p->best = nullptr;
     p->pin_R = p->pin_best = p->dev_R = p->dev_best = nullptr; p->host_cap = 0;
     p->has_receptor = p->has_ligand = p->lig_has_clash = p->has_filter = false;
@@ -285,6 +302,8 @@ extern "C" int dlpd_plan_create(dlpd_plan** out, int L, int C0, int C1, int H, i
     struct { void** ptr; size_t bytes; } allocs[] = {
         {(void**)&p->lig0, sizeof(float) * (C0 + 1) * n3(L)},
         {(void**)&p->lig1, sizeof(float) * C1 * n3(L1)},
+        {(void**)&p->lig0_cl, sizeof(float) * C0 * n3(L)},
+        {(void**)&p->lig1_cl, sizeof(float) * C1 * n3(L1)},
         {(void**)&p->rspec0, sizeof(cpx) * (C0 + 1) * n3(N)},
         {(void**)&p->rspec1, sizeof(cpx) * C1 * n3(N1)},
         {(void**)&p->s1_0, sizeof(cpx) * P * (C0 + 1) * N * L * L},
@@ -312,7 +331,7 @@ static int real_spectra(int L, const float* vols, int C, cpx* s1, cpx* spec, con
     const int N = 2 * L;
     FwdZParams f;
     f.src = vols; f.src_pair_stride = 0; f.src_rot = nullptr; f.R = nullptr; f.out = s1; f.tw = tw;
-    f.C = C; f.c_ext = -1; f.n_rot = 1; f.center = 0.f;
+    f.C = C; f.Ctot = C; f.c_out0 = 0; f.c_ext = -1; f.n_rot = 1; f.center = 0.f;
     TRY(launch_fwdz(L, f, 1, st));
     PlaneParams q;
     q.in = s1; q.out = spec; q.spec = nullptr; q.spec_pair_stride = 0; q.tw = tw; q.C = C; q.P = 1;
@@ -345,6 +364,11 @@ extern "C" int dlpd_set_ligand(dlpd_plan* p, const float* vol0, const float* vol
     if (clash) TRY(rt_copy(p->lig0 + p->C0 * n3(L), clash, sizeof(float) * n3(L), D2D, st));
     else TRY(rt_memset(p->lig0 + p->C0 * n3(L), 0, sizeof(float) * n3(L), st));
     TRY(rt_copy(p->lig1, vol1, sizeof(float) * p->C1 * n3(L1), D2D, st));
+    ChannelLastParams cl;
+    cl.in = p->lig0; cl.out = p->lig0_cl; cl.C = p->C0; cl.V = (int)n3(L);
+    TRY(launch<ToChannelLast>(dim3((cl.V + ToChannelLast::VOX_PER_CTA - 1) / ToChannelLast::VOX_PER_CTA), cl, st));
+    cl.in = p->lig1; cl.out = p->lig1_cl; cl.C = p->C1; cl.V = (int)n3(L1);
+    TRY(launch<ToChannelLast>(dim3((cl.V + ToChannelLast::VOX_PER_CTA - 1) / ToChannelLast::VOX_PER_CTA), cl, st));
     p->has_ligand = true;
     p->lig_has_clash = clash != nullptr;
     return 0;
@@ -380,13 +404,37 @@ static int search_chunk(dlpd_plan* p, const float* R, const float* clash_rot, in
     const int L = p->L, L1 = L / 2, N = 2 * L;
     const int P = (n + 1) / 2;
     TRY(rt_memset(p->best, 0xff, sizeof(unsigned long long) * n, st));
-    FwdZParams f;
-    f.src = p->lig0; f.src_pair_stride = 0; f.src_rot = clash_rot; f.R = R; f.out = p->s1_0; f.tw = p->tw0;
-    f.C = p->C0 + 1; f.c_ext = p->C0; f.n_rot = n; f.center = center_of(L, p->center_mode);
-    { ProfScope ps(p, DLPD_PROFILE_FWDZ0, st); TRY(launch_fwdz(L, f, P, st)); }
-    f.src = p->lig1; f.src_rot = nullptr; f.out = p->s1_1; f.tw = p->tw1; f.C = p->C1; f.c_ext = -1;
-    f.center = center_of(L1, p->center_mode);
-    { ProfScope ps(p, DLPD_PROFILE_FWDZ1, st); TRY(launch_fwdz(L1, f, P, st)); }
+    {   // level 0: C0 rotated feature channels + the clash channel (rotated here, or supplied already rotated)
+        ProfScope ps(p, DLPD_PROFILE_FWDZ0, st);
+        FwdZParams f;
+        f.src_pair_stride = 0; f.R = R; f.out = p->s1_0; f.tw = p->tw0; f.Ctot = p->C0 + 1; f.n_rot = n;
+        f.center = center_of(L, p->center_mode);
+        if (channel_last_ok(p->C0)) {
+            FwdZCParams g;
+            g.src = p->lig0_cl; g.R = R; g.out = p->s1_0; g.tw = p->tw0; g.C = p->C0; g.Ctot = p->C0 + 1; g.n_rot = n;
+            g.center = f.center;
+            TRY(launch_fwdzc(L, g, P, st));
+        } else {
+            f.src = p->lig0; f.src_rot = nullptr; f.C = p->C0; f.c_out0 = 0; f.c_ext = -1;
+            TRY(launch_fwdz(L, f, P, st));
+        }
+        f.src = p->lig0 + (size_t)p->C0 * n3(L); f.src_rot = clash_rot; f.C = 1; f.c_out0 = p->C0; f.c_ext = 0;
+        TRY(launch_fwdz(L, f, P, st));
+    }
+    {   // level 1
+        ProfScope ps(p, DLPD_PROFILE_FWDZ1, st);
+        if (channel_last_ok(p->C1)) {
+            FwdZCParams g;
+            g.src = p->lig1_cl; g.R = R; g.out = p->s1_1; g.tw = p->tw1; g.C = p->C1; g.Ctot = p->C1; g.n_rot = n;
+            g.center = center_of(L1, p->center_mode);
+            TRY(launch_fwdzc(L1, g, P, st));
+        } else {
+            FwdZParams f;
+            f.src = p->lig1; f.src_pair_stride = 0; f.src_rot = nullptr; f.R = R; f.out = p->s1_1; f.tw = p->tw1;
+            f.C = p->C1; f.Ctot = p->C1; f.c_out0 = 0; f.c_ext = -1; f.n_rot = n; f.center = center_of(L1, p->center_mode);
+            TRY(launch_fwdz(L1, f, P, st));
+        }
+    }
     PlaneParams q;
     q.in = p->s1_0; q.out = p->s2_0; q.spec = p->rspec0; q.spec_pair_stride = 0; q.tw = p->tw0; q.C = p->C0 + 1; q.P = P;
     q.scale = 1.f;
@@ -515,7 +563,7 @@ extern "C" int dlpd_volume_correlate(const float* v1, const float* v2, float* ou
         const int q = items - i0 < w.Q ? items - i0 : w.Q;
         FwdZParams f;
         f.src = v1 + n3(L) * i0; f.src_pair_stride = (long)n3(L); f.src_rot = nullptr; f.R = nullptr; f.out = w.s1; f.tw = w.tw;
-        f.C = 1; f.c_ext = -1; f.n_rot = 1; f.center = 0.f;
+        f.C = 1; f.Ctot = 1; f.c_out0 = 0; f.c_ext = -1; f.n_rot = 1; f.center = 0.f;
         TRY(launch_fwdz(L, f, q, st));
         PlaneParams pl;
         pl.in = w.s1; pl.out = w.spec; pl.spec = nullptr; pl.spec_pair_stride = 0; pl.tw = w.tw; pl.C = 1; pl.P = q;

@@ -2,11 +2,15 @@
 //
 // Every transform of the docking search is a length-N = 2L line whose input occupies the first half
 // (zero padding, Docker.py:225 / DockingModels.py:71 pad L -> 2L) or whose output is wanted in full:
-//   forward  = pruned radix-2 DIF step (copy + twiddle) followed by two independent length-L DIF FFTs
-//              (natural order in, digit-reversed order out);
-//   inverse  = two length-L DIT FFTs (digit-reversed in, natural out) followed by one radix-2 DIT step.
-// Forward and inverse use the same factor list mirrored, so the permuted spectra never have to be
+//   forward  = decimation in frequency, natural order in -> digit-reversed order out; the outermost radix-2 step
+//              has a zero upper half, so it degenerates to "copy + twiddle" and is fused with the next radix
+//              ("pruned" pass: only the first half of the line is read);
+//   inverse  = decimation in time, digit-reversed in -> natural out, with the mirrored factor list.
+// Forward and inverse share the factor list N = 2 * R0 * TA * TB, so the permuted spectra never have to be
 // reordered: the receptor spectrum is produced by the same forward code and multiplied pointwise.
+//
+// Two elementary radices are fused per pass in registers (RA x RB values per task), so a line needs at most two
+// shared-memory passes per direction:   head = (2, R0) at block N,   tail = (TA, TB) at block N / (2 R0).
 //
 // Work is distributed as "tasks" = (butterfly, line) pairs with the LINE index fastest, so that
 // consecutive lanes touch consecutive lines: shared-memory accesses are conflict free for any
@@ -22,6 +26,10 @@ DLPD_HD cpx cscale(cpx a, float s) { return make_float2(a.x * s, a.y * s); }
 
 // ---- small DFTs, sign + ------------------------------------------------------------------------
 template <int R> struct Dft;
+
+template <> struct Dft<1> {
+    static DLPD_HD void run(cpx*) {}
+};
 
 template <> struct Dft<2> {
     static DLPD_HD void run(cpx* a) {
@@ -77,104 +85,162 @@ template <> struct Dft<8> {
     }
 };
 
-// ---- factor lists of the HALF length M = L (first = outermost DIF stage) ---------------------------
-template <int M> struct HalfPlan;
-#define DLPD_HALFPLAN(M_, NS_, ...)                                   \
-    template <> struct HalfPlan<M_> {                                 \
-        static constexpr int NS = NS_;                                \
-        static DLPD_CE int radix(int i) { constexpr int r[] = {__VA_ARGS__}; return r[i]; } \
+// ---- factor lists: N = 2 * R0 * TA * TB ------------------------------------------------------------------
+template <int N> struct LinePlan;
+#define DLPD_LINEPLAN(N_, R0_, TA_, TB_)                                                    \
+    template <> struct LinePlan<N_> {                                                       \
+        static constexpr int R0 = R0_, TA = TA_, TB = TB_, TAIL = TA_ * TB_;                \
+        static_assert(2 * R0_ * TA_ * TB_ == N_, "bad factorisation");                      \
     };
-DLPD_HALFPLAN(4, 1, 4)
-DLPD_HALFPLAN(5, 1, 5)
-DLPD_HALFPLAN(8, 1, 8)
-DLPD_HALFPLAN(10, 2, 5, 2)
-DLPD_HALFPLAN(16, 2, 4, 4)
-DLPD_HALFPLAN(20, 2, 5, 4)
-DLPD_HALFPLAN(32, 2, 8, 4)
-DLPD_HALFPLAN(40, 2, 5, 8)
-DLPD_HALFPLAN(64, 2, 8, 8)
-DLPD_HALFPLAN(80, 3, 5, 4, 4)
-DLPD_HALFPLAN(128, 3, 8, 4, 4)
+DLPD_LINEPLAN(8, 4, 1, 1)
+DLPD_LINEPLAN(10, 5, 1, 1)
+DLPD_LINEPLAN(16, 8, 1, 1)
+DLPD_LINEPLAN(20, 5, 2, 1)
+DLPD_LINEPLAN(32, 4, 4, 1)
+DLPD_LINEPLAN(40, 5, 4, 1)
+DLPD_LINEPLAN(64, 8, 4, 1)
+DLPD_LINEPLAN(80, 5, 8, 1)
+DLPD_LINEPLAN(128, 8, 8, 1)
+DLPD_LINEPLAN(160, 5, 4, 4)
+DLPD_LINEPLAN(256, 8, 4, 4)
 
-// block size seen by DIF stage i of a length-M transform: M / (r0 * ... * r_{i-1})
-template <int M, int I> struct StageBlock {
-    static constexpr int value = StageBlock<M, I - 1>::value / HalfPlan<M>::radix(I - 1);
+// hooks of fft_pass: where a task's values come from / go to, and an optional pointwise multiplier
+struct NoHook {};
+// element `e` (index along the line) of line `l`
+template <class F> struct GlobalIn { F f; };      // f(l, e) -> cpx        : read from global instead of shared
+template <class F> struct GlobalOut { F f; };     // f(l, e, value)        : write to global instead of shared
+template <class F> struct PointMul { F f; };      // f(l, e) -> cpx        : multiply between the two halves of a MID pass
+
+enum PassKind {
+    PASS_DIF = 0,        // forward pair: outer radix RA at block NB, inner radix RB at block NB/RA
+    PASS_DIF_PRUNED = 1, // same with RA == 2 and an all-zero upper half: reads only the lower half
+    PASS_DIT = 2,        // inverse pair (inner first, then outer)
+    PASS_MID = 3         // DIF pair, pointwise multiply, DIT pair on the same registers (no round trip)
 };
-template <int M> struct StageBlock<M, 0> { static constexpr int value = M; };
 
-// One stage over a set of lines held in shared memory.
-//   R        radix;  DIT: twiddle-then-butterfly (inverse), else butterfly-then-twiddle (forward)
-//   NLINES   number of lines, LEN line length, NB block size of this stage (LEN % NB == 0)
-//   TWN      size of the twiddle table tw[k] = e^{+2 pi i k / TWN};  TWS = TWN / (transform size the
-//            blocks belong to) * (that size / NB), i.e. twiddle index = TWMUL * j * p
-//   LineOff  functor: line index -> offset (in cpx) of element 0;  ES element stride (in cpx)
-template <int R, bool DIT, int NLINES, int LEN, int NB, int TWMUL, int ES, int NT, class LineOff>
-DLPD_DEV void fft_stage(cpx* s, const cpx* tw, LineOff off) {
-    constexpr int MB = NB / R;             // sub-block size = butterfly stride
-    constexpr int BPL = LEN / R;           // butterflies per line
-    DLPD_FOR_TASKS(t, NLINES * BPL, NT) {
+// One fused pass over NLINES lines of LEN elements held in shared memory `s` (element stride ES, line offsets `off`).
+//   NB   block size of the outer radix (LEN % NB == 0);  TWN size of the twiddle table tw[k] = e^{+2 pi i k/TWN}
+//   In / Out / Mul: NoHook or the hook structs above
+template <int KIND, int RA, int RB, int NLINES, int LEN, int NB, int TWN, int ES, int NT, class LineOff,
+          class In = NoHook, class Out = NoHook, class Mul = NoHook>
+DLPD_DEV void fft_pass(cpx* s, const cpx* tw, LineOff off, In in = In(), Out out = Out(), Mul mul = Mul()) {
+    constexpr int M = NB / RA;             // outer sub-block
+    constexpr int M2 = M / RB;             // inner sub-block: range of the butterfly index j
+    constexpr int TPL = LEN / (RA * RB);   // tasks per line
+    constexpr int TWO = TWN / NB;          // outer twiddle w_NB^x = tw[TWO * x]
+    constexpr int TWI = TWN / M;           // inner twiddle w_M^x  = tw[TWI * x]
+    constexpr bool FWD = KIND == PASS_DIF || KIND == PASS_DIF_PRUNED || KIND == PASS_MID;
+    constexpr bool INV = KIND == PASS_DIT || KIND == PASS_MID;
+    static_assert(KIND != PASS_DIF_PRUNED || RA == 2, "pruned pass is the outermost radix-2 step");
+    DLPD_FOR_TASKS(t, NLINES * TPL, NT) {
         const int l = t % NLINES;
         const int b = t / NLINES;
-        const int blk = b / MB;
-        const int j = b - blk * MB;
-        cpx* p = s + off(l) + (blk * NB + j) * ES;
-        cpx a[R];
+        const int blk = b / M2;
+        const int j = b - blk * M2;
+        const int e0 = blk * NB + j;       // element index of (pa = 0, s = 0)
+        cpx* p = s + off(l) + e0 * ES;
+        cpx a[RA][RB];
+        // ---- load: a[i][k] <- element e0 + i*M + k*M2
         DLPD_UNROLL
-        for (int q = 0; q < R; ++q) a[q] = p[q * MB * ES];
-        if (DIT) {
+        for (int i = 0; i < RA; ++i) {
+            if (KIND == PASS_DIF_PRUNED && i > 0) break;
             DLPD_UNROLL
-            for (int q = 1; q < R; ++q) a[q] = cmul(a[q], tw[TWMUL * j * q]);
+            for (int k = 0; k < RB; ++k) {
+                if constexpr (std::is_same<In, NoHook>::value) a[i][k] = p[(i * M + k * M2) * ES];
+                else a[i][k] = in.f(l, e0 + i * M + k * M2);
+            }
         }
-        Dft<R>::run(a);
-        if (!DIT) {
+        if (FWD) {
+            // outer DFT over i for each k, then twiddle w_NB^{(j + k*M2) * pa}
             DLPD_UNROLL
-            for (int q = 1; q < R; ++q) a[q] = cmul(a[q], tw[TWMUL * j * q]);
+            for (int k = 0; k < RB; ++k) {
+                cpx c[RA];
+                if (KIND == PASS_DIF_PRUNED) {
+                    c[0] = a[0][k];
+                    c[RA - 1] = a[0][k];
+                } else {
+                    DLPD_UNROLL
+                    for (int i = 0; i < RA; ++i) c[i] = a[i][k];
+                    Dft<RA>::run(c);
+                }
+                a[0][k] = c[0];
+                DLPD_UNROLL
+                for (int i = 1; i < RA; ++i) a[i][k] = cmul(c[i], tw[TWO * (j + k * M2) * i]);
+            }
+            // inner DFT over k for each pa, then twiddle w_M^{j * s}
+            DLPD_UNROLL
+            for (int i = 0; i < RA; ++i) {
+                Dft<RB>::run(a[i]);
+                DLPD_UNROLL
+                for (int k = 1; k < RB; ++k) a[i][k] = cmul(a[i][k], tw[TWI * j * k]);
+            }
         }
+        if constexpr (!std::is_same<Mul, NoHook>::value) {
+            DLPD_UNROLL
+            for (int i = 0; i < RA; ++i) {
+                DLPD_UNROLL
+                for (int k = 0; k < RB; ++k) a[i][k] = cmul(a[i][k], mul.f(l, e0 + i * M + k * M2));
+            }
+        }
+        if (INV) {
+            // inner: twiddle w_M^{j * s}, DFT over s for each pa
+            DLPD_UNROLL
+            for (int i = 0; i < RA; ++i) {
+                DLPD_UNROLL
+                for (int k = 1; k < RB; ++k) a[i][k] = cmul(a[i][k], tw[TWI * j * k]);
+                Dft<RB>::run(a[i]);
+            }
+            // outer: twiddle w_NB^{(j + k*M2) * pa}, DFT over pa for each k
+            DLPD_UNROLL
+            for (int k = 0; k < RB; ++k) {
+                cpx c[RA];
+                c[0] = a[0][k];
+                DLPD_UNROLL
+                for (int i = 1; i < RA; ++i) c[i] = cmul(a[i][k], tw[TWO * (j + k * M2) * i]);
+                Dft<RA>::run(c);
+                DLPD_UNROLL
+                for (int i = 0; i < RA; ++i) a[i][k] = c[i];
+            }
+        }
+        // ---- store to the same positions
         DLPD_UNROLL
-        for (int q = 0; q < R; ++q) p[q * MB * ES] = a[q];
+        for (int i = 0; i < RA; ++i) {
+            DLPD_UNROLL
+            for (int k = 0; k < RB; ++k) {
+                if constexpr (std::is_same<Out, NoHook>::value) p[(i * M + k * M2) * ES] = a[i][k];
+                else out.f(l, e0 + i * M + k * M2, a[i][k]);
+            }
+        }
     }
     DLPD_SYNC();
 }
 
-// All DIF stages of NLINES length-M lines (forward, natural -> permuted).  tw has TWN = 2M entries.
-template <int M, int NLINES, int ES, int NT, int I, class LineOff> struct DifStages {
-    static DLPD_DEV void run(cpx* s, const cpx* tw, LineOff off) {
-        constexpr int NB = StageBlock<M, I>::value;
-        fft_stage<HalfPlan<M>::radix(I), false, NLINES, M, NB, (2 * M) / NB, ES, NT>(s, tw, off);
-        if constexpr (I + 1 < HalfPlan<M>::NS) DifStages<M, NLINES, ES, NT, I + 1, LineOff>::run(s, tw, off);
-    }
-};
-
-// All DIT stages (inverse, permuted -> natural): mirror order of DifStages.
-template <int M, int NLINES, int ES, int NT, int I, class LineOff> struct DitStages {
-    static DLPD_DEV void run(cpx* s, const cpx* tw, LineOff off) {
-        constexpr int NB = StageBlock<M, I>::value;
-        if constexpr (I + 1 < HalfPlan<M>::NS) DitStages<M, NLINES, ES, NT, I + 1, LineOff>::run(s, tw, off);
-        fft_stage<HalfPlan<M>::radix(I), true, NLINES, M, NB, (2 * M) / NB, ES, NT>(s, tw, off);
-    }
-};
-
-// Offsets of the 2*NLINES half lines (half h = l / NLINES, line = l % NLINES) given the base functor.
-template <int NLINES, int HALF_OFF, class LineOff> struct HalfLines {
-    LineOff base;
-    DLPD_DEV int operator()(int l) const {
-        const int h = l / NLINES;
-        return base(l - h * NLINES) + h * HALF_OFF;
-    }
-};
-
-// Forward sub-transforms: the caller has already applied the pruned radix-2 step
-//   s[j + M] = s[j] * tw[j]   (j < M),  then both halves get a length-M DIF FFT.
-template <int M, int NLINES, int ES, int NT, class LineOff>
-DLPD_DEV void fft_forward_halves(cpx* s, const cpx* tw, LineOff off) {
-    HalfLines<NLINES, M * ES, LineOff> h{off};
-    DifStages<M, 2 * NLINES, ES, NT, 0, HalfLines<NLINES, M * ES, LineOff>>::run(s, tw, h);
+// ---- whole-line helpers -------------------------------------------------------------------------------------
+// forward head: pruned (2, R0) pair at block N; reads elements [0, N/2) only (optionally from global via `in`)
+template <int N, int NLINES, int ES, int NT, class LineOff, class In = NoHook>
+DLPD_DEV void fft_fwd_head(cpx* s, const cpx* tw, LineOff off, In in = In()) {
+    fft_pass<PASS_DIF_PRUNED, 2, LinePlan<N>::R0, NLINES, N, N, N, ES, NT>(s, tw, off, in);
 }
-
-// Full inverse of a length-2M line: DIT on the halves, then the radix-2 DIT step of block 2M.
-template <int M, int NLINES, int ES, int NT, class LineOff>
-DLPD_DEV void fft_inverse_full(cpx* s, const cpx* tw, LineOff off) {
-    HalfLines<NLINES, M * ES, LineOff> h{off};
-    DitStages<M, 2 * NLINES, ES, NT, 0, HalfLines<NLINES, M * ES, LineOff>>::run(s, tw, h);
-    fft_stage<2, true, NLINES, 2 * M, 2 * M, 1, ES, NT>(s, tw, off);
+// forward tail: (TA, TB) pair at block N / (2 R0)   (nothing to do when TAIL == 1)
+template <int N, int NLINES, int ES, int NT, class LineOff>
+DLPD_DEV void fft_fwd_tail(cpx* s, const cpx* tw, LineOff off) {
+    typedef LinePlan<N> P;
+    if constexpr (P::TAIL > 1) fft_pass<PASS_DIF, P::TA, P::TB, NLINES, N, P::TAIL, N, ES, NT>(s, tw, off);
+}
+// forward tail, pointwise multiply, inverse tail in one pass (a plain multiply pass when TAIL == 1)
+template <int N, int NLINES, int ES, int NT, class LineOff, class Mul>
+DLPD_DEV void fft_mid(cpx* s, const cpx* tw, LineOff off, Mul mul) {
+    typedef LinePlan<N> P;
+    fft_pass<PASS_MID, P::TA, P::TB, NLINES, N, P::TAIL, N, ES, NT>(s, tw, off, NoHook(), NoHook(), mul);
+}
+template <int N, int NLINES, int ES, int NT, class LineOff, class In = NoHook>
+DLPD_DEV void fft_inv_tail(cpx* s, const cpx* tw, LineOff off, In in = In()) {
+    typedef LinePlan<N> P;
+    if constexpr (P::TAIL > 1 || !std::is_same<In, NoHook>::value)
+        fft_pass<PASS_DIT, P::TA, P::TB, NLINES, N, P::TAIL, N, ES, NT>(s, tw, off, in);
+}
+// inverse head: (2, R0) pair at block N (optionally writing to global via `out`)
+template <int N, int NLINES, int ES, int NT, class LineOff, class Out = NoHook>
+DLPD_DEV void fft_inv_head(cpx* s, const cpx* tw, LineOff off, Out out = Out()) {
+    fft_pass<PASS_DIT, 2, LinePlan<N>::R0, NLINES, N, N, N, ES, NT>(s, tw, off, NoHook(), out);
 }

@@ -17,6 +17,17 @@
 #pragma once
 #include "dlpd_fft.h"
 
+// tunables (overridable with -D for experiments; the defaults are what ships)
+#ifndef DLPD_PLANE_NT
+#define DLPD_PLANE_NT 800
+#endif
+#ifndef DLPD_EPI_NT
+#define DLPD_EPI_NT 256
+#endif
+#ifndef DLPD_FWDZC_NT
+#define DLPD_FWDZC_NT 256
+#endif
+
 template <int S> struct LineMul {
     DLPD_DEV int operator()(int l) const { return l * S; }
 };
@@ -104,16 +115,20 @@ struct RotateVolume {
 };
 
 // ------------------------------------------------------------------------------------------------------
-// FwdZ: gather (rotate) + pruned forward FFT along z.
+// FwdZ: gather (rotate) + pruned forward FFT along z, one channel per CTA.
+// Used for the clash channel, the receptor / standalone operators and channel counts the channel-last kernel
+// (FwdZC below) does not take.
 // ------------------------------------------------------------------------------------------------------
 struct FwdZParams {
     const float* src;        // [.. pair_stride ..][C][L^3] source volumes
     long src_pair_stride;    // 0: every pair reads the same volumes (search); C*L^3: one real volume per "pair"
     const float* src_rot;    // optional [n_rot][L^3]: volumes that are ALREADY rotated, used for channel c_ext
     const float* R;          // [n_rot][9] rotation matrices, or nullptr: identity, imaginary part = 0
-    cpx* out;                // S1 [P][C][N][L][L]
+    cpx* out;                // S1 [P][Ctot][N][L][L]
     const cpx* tw;           // [N] e^{+2 pi i k/N}
-    int C, c_ext, n_rot;
+    int C;                   // channels of this launch (grid.y)
+    int Ctot, c_out0;        // channel count of S1 and index of this launch's first channel in it
+    int c_ext, n_rot;
     float center;
 };
 
@@ -140,7 +155,6 @@ template <int L_, int YT_> struct FwdZ {
         }
         const float* src = p.src + (long)pair * p.src_pair_stride + (long)c * L3;
         DLPD_FOR_TASKS(t, N, NT) tw[t] = p.tw[t];
-        DLPD_SYNC();
         DLPD_FOR_TASKS(t, YT * L, NT) {
             const int yl = t % YT, z = t / YT, y = y0 + yl;
             const int idx = (x * L + y) * L + z;
@@ -159,13 +173,12 @@ template <int L_, int YT_> struct FwdZ {
             } else {
                 a = __ldg(src + idx);                          // plain real volume (receptor / standalone operator)
             }
-            const cpx v = make_float2(a, b);
-            buf[z * YT + yl] = v;
-            buf[(z + L) * YT + yl] = cmul(v, tw[z]);          // pruned radix-2 step: upper half input is zero
+            buf[z * YT + yl] = make_float2(a, b);              // lower half only: the pruned head never reads z >= L
         }
         DLPD_SYNC();
-        fft_forward_halves<L, YT, YT, NT>(buf, tw, LineMul<1>());
-        cpx* out = p.out + ((((long)pair * p.C + c) * N) * L + x) * L + y0;
+        fft_fwd_head<N, YT, YT, NT>(buf, tw, LineMul<1>());
+        fft_fwd_tail<N, YT, YT, NT>(buf, tw, LineMul<1>());
+        cpx* out = p.out + ((((long)pair * p.Ctot + p.c_out0 + c) * N) * L + x) * L + y0;
         DLPD_FOR_TASKS(t, N * YT, NT) {
             const int kz = t / YT, yl = t % YT;
             out[(long)kz * L * L + yl] = buf[t];
@@ -174,12 +187,133 @@ template <int L_, int YT_> struct FwdZ {
 };
 
 // ------------------------------------------------------------------------------------------------------
+// ToChannelLast: [C][V] -> [V][C]  (ligand feature volumes, once per pair)
+// ------------------------------------------------------------------------------------------------------
+struct ChannelLastParams {
+    const float* in;
+    float* out;
+    int C, V;
+};
+struct ToChannelLast {
+    typedef ChannelLastParams Params;
+    static constexpr int NT = 256;
+    static constexpr int SMEM = 0;
+    static constexpr int VOX_PER_CTA = 256;
+    // grid: x = ceil(V / VOX_PER_CTA)
+    static DLPD_DEV void body(const Params& p, int bx, int, int, char*) {
+        DLPD_FOR_TASKS(t, VOX_PER_CTA * p.C, NT) {
+            const int c = t % p.C, v = bx * VOX_PER_CTA + t / p.C;
+            if (v < p.V) p.out[(long)v * p.C + c] = p.in[(long)c * p.V + v];
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// FwdZC: same as FwdZ for the rotated feature channels, reading a CHANNEL-LAST ligand volume [x][y][z][C]:
+// the source position and the 8 interpolation weights of a voxel are computed once for CG channels and every tap is
+// one 16-byte load per 4 channels (full 32-byte sectors for CG = 8) instead of CG scattered 4-byte loads.
+// ------------------------------------------------------------------------------------------------------
+struct FwdZCParams {
+    const float* src;        // [L^3][C] channel-last
+    const float* R;          // [n_rot][9]
+    cpx* out;                // S1 [P][Ctot][N][L][L]
+    const cpx* tw;
+    int C, Ctot, n_rot;
+    float center;
+};
+
+DLPD_DEV float4 f4_fma(float w, float4 v, float4 acc) {
+    return make_float4(fmaf_(w, v.x, acc.x), fmaf_(w, v.y, acc.y), fmaf_(w, v.z, acc.z), fmaf_(w, v.w, acc.w));
+}
+
+// trilinear sample of 4 consecutive channels of a channel-last volume, zero outside
+DLPD_DEV float4 trilinear_zero_cl4(const float* DLPD_RESTRICT v, int L, int C, float sx, float sy, float sz) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    const float fx = floorf(sx), fy = floorf(sy), fz = floorf(sz);
+    const int ix = (int)fx, iy = (int)fy, iz = (int)fz;
+    if (ix < -1 || iy < -1 || iz < -1 || ix >= L || iy >= L || iz >= L) return acc;
+    const float wx1 = sx - fx, wy1 = sy - fy, wz1 = sz - fz;
+    const float wx0 = 1.0f - wx1, wy0 = 1.0f - wy1, wz0 = 1.0f - wz1;
+    const bool x0 = ix >= 0, x1 = ix + 1 < L;
+    const bool y0 = iy >= 0, y1 = iy + 1 < L;
+    const bool z0 = iz >= 0, z1 = iz + 1 < L;
+    const float* p = v + (((long)ix * L + iy) * L + iz) * C;
+    const long sxs = (long)L * L * C, sys = (long)L * C, szs = C;
+#define DLPD_TAP(cond, off, w) if (cond) acc = f4_fma(w, __ldg(reinterpret_cast<const float4*>(p + (off))), acc);
+    DLPD_TAP(x0 && y0 && z0, 0, wx0 * wy0 * wz0)
+    DLPD_TAP(x0 && y0 && z1, szs, wx0 * wy0 * wz1)
+    DLPD_TAP(x0 && y1 && z0, sys, wx0 * wy1 * wz0)
+    DLPD_TAP(x0 && y1 && z1, sys + szs, wx0 * wy1 * wz1)
+    DLPD_TAP(x1 && y0 && z0, sxs, wx1 * wy0 * wz0)
+    DLPD_TAP(x1 && y0 && z1, sxs + szs, wx1 * wy0 * wz1)
+    DLPD_TAP(x1 && y1 && z0, sxs + sys, wx1 * wy1 * wz0)
+    DLPD_TAP(x1 && y1 && z1, sxs + sys + szs, wx1 * wy1 * wz1)
+#undef DLPD_TAP
+    return acc;
+}
+
+template <int L_, int CG_, int YT_> struct FwdZC {
+    typedef FwdZCParams Params;
+    static constexpr int L = L_, N = 2 * L_, CG = CG_, YT = YT_, YTILES = L_ / YT_, CQ = CG_ / 4;
+    static constexpr int CS = N * YT + 8;          // per-channel stride: +8 keeps 4 channel groups of a warp on distinct banks
+    static constexpr int NT = DLPD_FWDZC_NT;
+    static constexpr int SMEM = (CG * CS + N) * (int)sizeof(cpx);
+    static_assert(L_ % YT_ == 0 && CG_ % 4 == 0, "tile shape");
+    struct Lines {
+        DLPD_DEV int operator()(int l) const { return (l / YT) * CS + (l % YT); }
+    };
+    // grid: x = L * YTILES, y = C / CG, z = P
+    static DLPD_DEV void body(const Params& p, int bx, int by, int bz, char* smem) {
+        cpx* buf = reinterpret_cast<cpx*>(smem);       // [CG][N][YT]
+        cpx* tw = buf + CG * CS;
+        const int x = bx / YTILES, y0 = (bx % YTILES) * YT, c0 = by * CG, pair = bz;
+        const int rotA = 2 * pair, rotB = 2 * pair + 1;
+        const bool hasB = rotB < p.n_rot;
+        float ra[9], rb[9];
+        for (int i = 0; i < 9; ++i) {
+            ra[i] = p.R[9 * rotA + i];
+            rb[i] = hasB ? p.R[9 * rotB + i] : 0.0f;
+        }
+        DLPD_FOR_TASKS(t, N, NT) tw[t] = p.tw[t];
+        const float* src = p.src + c0;
+        DLPD_FOR_TASKS(t, CQ * YT * L, NT) {
+            const int cq = t % CQ, yl = (t / CQ) % YT, z = t / (CQ * YT), y = y0 + yl;
+            float sx, sy, sz;
+            rotate_point(ra, p.center, x, y, z, sx, sy, sz);
+            const float4 a = trilinear_zero_cl4(src + 4 * cq, L, p.C, sx, sy, sz);
+            float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (hasB) {
+                rotate_point(rb, p.center, x, y, z, sx, sy, sz);
+                b = trilinear_zero_cl4(src + 4 * cq, L, p.C, sx, sy, sz);
+            }
+            cpx* d = buf + (4 * cq) * CS + z * YT + yl;
+            d[0] = make_float2(a.x, b.x);
+            d[CS] = make_float2(a.y, b.y);
+            d[2 * CS] = make_float2(a.z, b.z);
+            d[3 * CS] = make_float2(a.w, b.w);
+        }
+        DLPD_SYNC();
+        fft_fwd_head<N, CG * YT, YT, NT>(buf, tw, Lines());
+        fft_fwd_tail<N, CG * YT, YT, NT>(buf, tw, Lines());
+        cpx* out = p.out + ((((long)pair * p.Ctot + c0) * N) * L + x) * L + y0;
+        DLPD_FOR_TASKS(t, CG * N * YT, NT) {
+            const int yl = t % YT, kz = (t / YT) % N, c = t / (YT * N);
+            out[((long)c * N + kz) * L * L + yl] = buf[c * CS + kz * YT + yl];
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------
 // Plane: for one (pair, channel, kz') the whole (x,y) plane lives in shared memory.
+//   forward x (head reads S1 from global, columns y < L) -> forward y head (rows) -> [forward y tail . receptor
+//   multiply . inverse y tail] in registers -> inverse y head -> inverse x tail -> inverse x head (writes S2 to global).
+// The receptor spectrum is stored TRANSPOSED ([kz'][ky'][kx']) so that the multiply, whose lanes run over rows kx',
+// reads it coalesced.
 // ------------------------------------------------------------------------------------------------------
 struct PlaneParams {
     const cpx* in;           // S1 [P][C][N][L][L]
-    cpx* out;                // S2 [P][C][N][N][N]   (or, in spectrum mode, [P][C][N][N][N] spectra)
-    const cpx* spec;         // receptor spectrum [..][C][N][N][N]; nullptr = spectrum mode (write conj(fwd) * scale)
+    cpx* out;                // S2 [P][C][N][N][N]   (or, in spectrum mode, [P][C][N][ky'][kx'] spectra)
+    const cpx* spec;         // receptor spectrum [..][C][N][ky'][kx']; nullptr = spectrum mode (write conj(fwd) * scale)
     long spec_pair_stride;   // 0: all pairs share the receptor (search); C*N^3: one spectrum per "pair"
     const cpx* tw;           // [N]
     int C, P;
@@ -189,8 +323,20 @@ struct PlaneParams {
 template <int L_> struct Plane {
     typedef PlaneParams Params;
     static constexpr int L = L_, N = 2 * L_, NP = N + 1;     // odd pitch: conflict-free along both axes
-    static constexpr int NT = (N >= 128) ? 512 : 256;
+    static constexpr int NT = (N >= 128) ? DLPD_PLANE_NT : ((N >= 64) ? 512 : 256);   // 800 = 5 x 160 lanes: whole passes per round, <= 80 registers
     static constexpr int SMEM = (N * NP + N) * (int)sizeof(cpx);
+    struct LoadS1 {          // element e = x of column l = y
+        const cpx* in;
+        DLPD_DEV cpx operator()(int l, int e) const { return in[e * L + l]; }
+    };
+    struct MulSpec {         // element e = ky' of row l = kx'
+        const cpx* spec;
+        DLPD_DEV cpx operator()(int l, int e) const { return __ldg(spec + e * N + l); }
+    };
+    struct StoreS2 {         // element e = x of column l = y
+        cpx* out;
+        DLPD_DEV void operator()(int l, int e, cpx v) const { out[e * N + l] = v; }
+    };
     // grid: x = P * N * C  with the pair index fastest (CTAs that share a receptor plane run together -> L2 reuse)
     static DLPD_DEV void body(const Params& p, int bx, int, int, char* smem) {
         cpx* pl = reinterpret_cast<cpx*>(smem);        // [x][y], pitch NP
@@ -198,43 +344,27 @@ template <int L_> struct Plane {
         const int pair = bx % p.P, kz = (bx / p.P) % N, c = bx / (p.P * N);
         DLPD_FOR_TASKS(t, N, NT) tw[t] = p.tw[t];
         DLPD_SYNC();
-        const cpx* in = p.in + (((long)pair * p.C + c) * N + kz) * L * L;
-        DLPD_FOR_TASKS(t, L * L, NT) {
-            const int x = t / L, y = t % L;
-            const cpx v = in[t];
-            pl[x * NP + y] = v;
-            pl[x * NP + y + L] = cmul(v, tw[y]);
-        }
-        DLPD_SYNC();
-        fft_forward_halves<L, L, 1, NT>(pl, tw, LineMul<NP>());                 // along y, rows x < L
-        DLPD_FOR_TASKS(t, L * N, NT) {
-            const int x = t / N, ky = t % N;
-            pl[(x + L) * NP + ky] = cmul(pl[x * NP + ky], tw[x]);
-        }
-        DLPD_SYNC();
-        fft_forward_halves<L, N, NP, NT>(pl, tw, LineMul<1>());                 // along x, all ky
+        const long plane = ((long)pair * p.C + c) * N + kz;
+        GlobalIn<LoadS1> in{LoadS1{p.in + plane * L * L}};
+        fft_fwd_head<N, L, NP, NT>(pl, tw, LineMul<1>(), in);                   // along x, columns y < L
+        fft_fwd_tail<N, L, NP, NT>(pl, tw, LineMul<1>());
+        fft_fwd_head<N, N, 1, NT>(pl, tw, LineMul<NP>());                       // along y, all rows kx'
         if (p.spec == nullptr) {
-            cpx* out = p.out + (((long)pair * p.C + c) * N + kz) * N * N;
+            fft_fwd_tail<N, N, 1, NT>(pl, tw, LineMul<NP>());
+            cpx* out = p.out + plane * N * N;
             DLPD_FOR_TASKS(t, N * N, NT) {
-                const int kx = t / N, ky = t % N;
+                const int kx = t % N, ky = t / N;                               // transposed store, coalesced over kx
                 const cpx v = pl[kx * NP + ky];
                 out[t] = make_float2(v.x * p.scale, -v.y * p.scale);
             }
             return;
         }
-        const cpx* spec = p.spec + (long)pair * p.spec_pair_stride + ((long)c * N + kz) * N * N;
-        DLPD_FOR_TASKS(t, N * N, NT) {
-            const int kx = t / N, ky = t % N;
-            pl[kx * NP + ky] = cmul(pl[kx * NP + ky], __ldg(spec + t));
-        }
-        DLPD_SYNC();
-        fft_inverse_full<L, N, NP, NT>(pl, tw, LineMul<1>());                   // along x
-        fft_inverse_full<L, N, 1, NT>(pl, tw, LineMul<NP>());                   // along y
-        cpx* out = p.out + (((long)pair * p.C + c) * N + kz) * N * N;
-        DLPD_FOR_TASKS(t, N * N, NT) {
-            const int x = t / N, y = t % N;
-            out[t] = pl[x * NP + y];
-        }
+        PointMul<MulSpec> mul{MulSpec{p.spec + (long)pair * p.spec_pair_stride + ((long)c * N + kz) * N * N}};
+        fft_mid<N, N, 1, NT>(pl, tw, LineMul<NP>(), mul);                       // y tail . multiply . inverse y tail
+        fft_inv_head<N, N, 1, NT>(pl, tw, LineMul<NP>());                       // inverse y
+        fft_inv_tail<N, N, NP, NT>(pl, tw, LineMul<1>());                       // inverse x
+        GlobalOut<StoreS2> out{StoreS2{p.out + plane * N * N}};
+        fft_inv_head<N, N, NP, NT>(pl, tw, LineMul<1>(), out);
     }
 };
 
@@ -265,7 +395,8 @@ template <int L_, int YT_> struct InvZStore {
             buf[kz * YP + yl] = in[(long)kz * N * N + yl];
         }
         DLPD_SYNC();
-        fft_inverse_full<L, YT, YP, NT>(buf, tw, LineMul<1>());
+        fft_inv_tail<N, YT, YP, NT>(buf, tw, LineMul<1>());
+        fft_inv_head<N, YT, YP, NT>(buf, tw, LineMul<1>());
         float* out = p.out + (long)by * N * N * N + ((long)x * N + y0) * N;
         DLPD_FOR_TASKS(t, N * YT, NT) {
             const int z = t % N, yl = t / N;
@@ -334,95 +465,118 @@ template <int C0, int C1, int H> struct EpiParams {
     FilterW<C0, C1, H> filt;
 };
 
+// hidden-layer contribution of the level-1 (half resolution) channels for JG hidden units starting at J0:
+//   out[jj] = sum_c W1[J0+jj][C0+c] * v[c]      (v = one component of the C1 level-1 correlations at one z')
+template <int C0, int C1, int H, int JG, int J0> struct Level1Hidden {
+    static DLPD_DEV void run(const FilterW<C0, C1, H>& f, const float* v, int stride, float* out) {
+        float acc[JG];
+        DLPD_UNROLL
+        for (int jj = 0; jj < JG; ++jj) acc[jj] = 0.0f;
+        DLPD_UNROLL
+        for (int c = 0; c < C1; ++c) {
+            const float x = v[c * stride];
+            DLPD_UNROLL
+            for (int jj = 0; jj < JG; ++jj) acc[jj] = fmaf_(f.W1[(J0 + jj) * (C0 + C1) + C0 + c], x, acc[jj]);
+        }
+        DLPD_UNROLL
+        for (int jj = 0; jj < JG; ++jj) out[jj] = acc[jj];
+    }
+};
+template <int C0, int C1, int H, int JG, int G> struct Level1Dispatch {      // warp-uniform switch over hidden groups
+    static DLPD_DEV void run(const FilterW<C0, C1, H>& f, int jg, const float* v, int stride, float* out) {
+        if (jg == G) Level1Hidden<C0, C1, H, JG, G * JG>::run(f, v, stride, out);
+        else if constexpr (G + 1 < H / JG) Level1Dispatch<C0, C1, H, JG, G + 1>::run(f, jg, v, stride, out);
+    }
+};
+
 template <int L_, int C0, int C1, int H> struct Epilogue {
     typedef EpiParams<C0, C1, H> Params;
     static constexpr int L = L_, N = 2 * L_, N1 = L_, M1 = L_ / 2;
-    static constexpr int NL0 = 4 * (C0 + 1), NL1 = C1;
-    static constexpr int NT = 256;
-    static constexpr int SMEM = (N * NL0 + N1 * NL1 + N + N1) * (int)sizeof(cpx) + 64 * 8;
+    static constexpr int NL0 = 4 * (C0 + 1);       // level-0 lines of a 2x2 tile (even pitch: 16-byte stores)
+    static constexpr int NL1 = C1, P1 = C1 + 1;    // level-1 lines, odd pitch (conflict-free component reads)
+    static constexpr int JG = (H % 8 == 0) ? 8 : H;          // hidden units per level-1 task
+    static constexpr int N1P = (N1 + 15) / 16 * 16;          // z' padded so that 2*N1P lanes are whole warps
+    static constexpr int NT = DLPD_EPI_NT;
+    // level-1 lines alias the level-0 buffer: they are consumed (into h1) before level 0 is loaded
+    static constexpr int B0 = (N * NL0 > N1 * P1) ? N * NL0 : N1 * P1;
+    static constexpr int SMEM = (B0 + N + N1) * (int)sizeof(cpx) + N1 * 2 * H * 4 + 64 * 8;
     // grid: x = N/2 (y tiles), y = N/2 (x tiles), z = P
     static DLPD_DEV void body(const Params& p, int bx, int by, int bz, char* smem) {
         cpx* b0 = reinterpret_cast<cpx*>(smem);        // [kz][NL0]   line = c*4 + xl*2 + yl
-        cpx* b1 = b0 + N * NL0;                        // [kz1][NL1]
-        cpx* tw0 = b1 + N1 * NL1;
+        cpx* b1 = b0;                                  // [kz1][P1]   (before level 0 is loaded)
+        cpx* tw0 = b0 + B0;
         cpx* tw1 = tw0 + N;
+        float* h1 = reinterpret_cast<float*>(tw1 + N1);                // [z'][rot][H] level-1 hidden contribution
         const int y0 = 2 * bx, x0 = 2 * by, pair = bz;
         const int rotA = 2 * pair, rotB = 2 * pair + 1;
         const bool hasB = rotB < p.n_rot;
         DLPD_FOR_TASKS(t, N, NT) tw0[t] = p.tw0[t];
         DLPD_FOR_TASKS(t, N1, NT) tw1[t] = p.tw1[t];
+        {   // level-1 lines at (x0/2, y0/2)
+            const cpx* s = p.s2_1 + (long)pair * C1 * N1 * N1 * N1 + (long)(x0 >> 1) * N1 + (y0 >> 1);
+            DLPD_FOR_TASKS(t, C1 * N1, NT) {
+                const int kz = t % N1, c = t / N1;
+                b1[kz * P1 + c] = __ldg(s + ((long)c * N1 + kz) * N1 * N1);
+            }
+        }
+        DLPD_SYNC();
+        fft_inv_tail<N1, NL1, P1, NT>(b1, tw1, LineMul<1>());
+        fft_inv_head<N1, NL1, P1, NT>(b1, tw1, LineMul<1>());
+        // the first filter layer is linear, so the C1 up-sampled channels (U[c,t] = corr1[c, t//2], DockingModels.py:74-76)
+        // contribute one hidden vector per level-1 voxel, shared by the 8 level-0 voxels above it
+        DLPD_FOR_TASKS(t, (H / JG) * 2 * N1P, NT) {
+            const int rot = t & 1, z1 = (t >> 1) % N1P, jg = t / (2 * N1P);
+            if (z1 < N1) {
+                float out[JG];
+                Level1Dispatch<C0, C1, H, JG, 0>::run(p.filt, jg, reinterpret_cast<const float*>(b1 + z1 * P1) + rot, 2, out);
+                DLPD_UNROLL
+                for (int jj = 0; jj < JG; ++jj) h1[(z1 * 2 + rot) * H + jg * JG + jj] = out[jj];
+            }
+        }
+        DLPD_SYNC();
         {   // level-0 lines: two complex (y0, y0+1) = 16 bytes per (channel, kz, xl)
             const cpx* s = p.s2_0 + (long)pair * (C0 + 1) * N * N * N + (long)x0 * N + y0;
             DLPD_FOR_TASKS(t, (C0 + 1) * N * 2, NT) {
                 const int xl = t & 1, kz = (t >> 1) % N, c = t / (2 * N);
                 const float4 v = __ldg(reinterpret_cast<const float4*>(s + (((long)c * N + kz) * N + xl) * N));
-                cpx* d = b0 + kz * NL0 + c * 4 + xl * 2;
-                d[0] = make_float2(v.x, v.y);
-                d[1] = make_float2(v.z, v.w);
-            }
-        }
-        {   // level-1 lines at (x0/2, y0/2)
-            const cpx* s = p.s2_1 + (long)pair * C1 * N1 * N1 * N1 + (long)(x0 >> 1) * N1 + (y0 >> 1);
-            DLPD_FOR_TASKS(t, C1 * N1, NT) {
-                const int kz = t % N1, c = t / N1;
-                b1[kz * NL1 + c] = __ldg(s + ((long)c * N1 + kz) * N1 * N1);
+                *reinterpret_cast<float4*>(b0 + kz * NL0 + c * 4 + xl * 2) = v;       // 16-byte aligned: all terms even
             }
         }
         DLPD_SYNC();
-        fft_inverse_full<L, NL0, NL0, NT>(b0, tw0, LineMul<1>());
-        fft_inverse_full<M1, NL1, NL1, NT>(b1, tw1, LineMul<1>());
+        fft_inv_tail<N, NL0, NL0, NT>(b0, tw0, LineMul<1>());
+        fft_inv_head<N, NL0, NL0, NT>(b0, tw0, LineMul<1>());
 
         unsigned long long bestA = ~0ull, bestB = ~0ull;
         constexpr int CT = C0 + C1;
-        DLPD_FOR_TASKS(t, 4 * N, NT) {
-            const int xy = t & 3, z = t >> 2;
-            float ha[H], hb[H];
+        DLPD_FOR_TASKS(t, 8 * N, NT) {
+            const int rot = t & 1, xy = (t >> 1) & 3, z = t >> 3;
+            const float* v0 = reinterpret_cast<const float*>(b0 + z * NL0 + xy) + rot;     // component `rot` of the pair
+            const float* hz = h1 + ((z >> 1) * 2 + rot) * H;
+            float h[H];
             DLPD_UNROLL
-            for (int j = 0; j < H; ++j) { ha[j] = p.filt.b1[j]; hb[j] = p.filt.b1[j]; }
-            const cpx* v0 = b0 + z * NL0 + xy;
+            for (int j = 0; j < H; ++j) h[j] = p.filt.b1[j] + hz[j];
             DLPD_UNROLL
             for (int c = 0; c < C0; ++c) {
-                const cpx v = v0[c * 4];
+                const float v = v0[c * 8];
                 DLPD_UNROLL
-                for (int j = 0; j < H; ++j) {
-                    ha[j] = fmaf_(p.filt.W1[j * CT + c], v.x, ha[j]);
-                    hb[j] = fmaf_(p.filt.W1[j * CT + c], v.y, hb[j]);
-                }
+                for (int j = 0; j < H; ++j) h[j] = fmaf_(p.filt.W1[j * CT + c], v, h[j]);
             }
-            const cpx* v1 = b1 + (z >> 1) * NL1;
+            float sc = p.filt.b2;
             DLPD_UNROLL
-            for (int c = 0; c < C1; ++c) {
-                const cpx v = v1[c];
-                DLPD_UNROLL
-                for (int j = 0; j < H; ++j) {
-                    ha[j] = fmaf_(p.filt.W1[j * CT + C0 + c], v.x, ha[j]);
-                    hb[j] = fmaf_(p.filt.W1[j * CT + C0 + c], v.y, hb[j]);
-                }
-            }
-            float sa = p.filt.b2, sb = p.filt.b2;
-            DLPD_UNROLL
-            for (int j = 0; j < H; ++j) {
-                sa = fmaf_(p.filt.W2[j], fmaxf(ha[j], 0.0f), sa);
-                sb = fmaf_(p.filt.W2[j], fmaxf(hb[j], 0.0f), sb);
-            }
-            const cpx clash = v0[C0 * 4];
-            const float Va = clash.x < p.tau ? sa : 0.0f;      // (clash < tau).float() * score   (Docker.py:226,232)
-            const float Vb = clash.y < p.tau ? sb : 0.0f;
+            for (int j = 0; j < H; ++j) sc = fmaf_(p.filt.W2[j], fmaxf(h[j], 0.0f), sc);
+            const float clash = v0[C0 * 8];
+            const float V = clash < p.tau ? sc : 0.0f;          // (clash < tau).float() * score   (Docker.py:226,232)
             const unsigned int lin = (unsigned int)(((x0 + (xy >> 1)) * N + (y0 + (xy & 1))) * N + z);
-            const unsigned long long ka = ((unsigned long long)score_key(Va) << 32) | lin;
-            const unsigned long long kb = ((unsigned long long)score_key(Vb) << 32) | lin;
-            bestA = ka < bestA ? ka : bestA;
-            bestB = kb < bestB ? kb : bestB;
-            if (p.score_out != nullptr) {
-                p.score_out[(long)rotA * N * N * N + lin] = Va;
-                if (hasB) p.score_out[(long)rotB * N * N * N + lin] = Vb;
-            }
+            const unsigned long long key = ((unsigned long long)score_key(V) << 32) | lin;
+            if (rot == 0) bestA = key < bestA ? key : bestA;
+            else bestB = key < bestB ? key : bestB;
+            if (p.score_out != nullptr && (rot == 0 || hasB)) p.score_out[(long)(rotA + rot) * N * N * N + lin] = V;
         }
 #if defined(DLPD_EMU)
         if (bestA < p.best[rotA]) p.best[rotA] = bestA;
         if (hasB && bestB < p.best[rotB]) p.best[rotB] = bestB;
 #else
-        unsigned long long* red = reinterpret_cast<unsigned long long*>(tw1 + N1);
+        unsigned long long* red = reinterpret_cast<unsigned long long*>(h1 + N1 * 2 * H);
         bestA = block_min_u64<NT>(bestA, red);
         bestB = block_min_u64<NT>(bestB, red + 32);
         if (threadIdx.x == 0) {

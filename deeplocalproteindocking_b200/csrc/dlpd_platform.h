@@ -7,6 +7,7 @@
 #include <stdint.h>
 #include <math.h>
 #include <string.h>
+#include <type_traits>
 
 #if defined(DLPD_EMU)
   #define DLPD_HD inline

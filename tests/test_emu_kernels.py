@@ -43,7 +43,8 @@ def test_emu_rotate_matches_oracle(L, center):
     assert (got.double() - want).abs().max() < 2e-5
 
 
-@pytest.mark.parametrize("L,C0,C1,H,n", [(8, 4, 6, 5, 3), (16, 4, 6, 5, 2), (20, 4, 6, 5, 3), (8, 16, 32, 24, 2)])
+@pytest.mark.parametrize("L,C0,C1,H,n", [(8, 4, 6, 5, 3), (16, 4, 6, 5, 2), (20, 4, 6, 5, 3), (8, 16, 32, 24, 2),
+                                         (20, 16, 32, 24, 3)])
 def test_emu_search_matches_oracle(L, C0, C1, H, n):
     rec, lig, rf, lf = _case(L, C0, C1, seed=L + C0)
     filt = O.FilterWeights.random(C0 + C1, H, seed=3)
