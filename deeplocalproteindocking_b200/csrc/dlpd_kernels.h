@@ -516,9 +516,10 @@ template <int L_, int C0, int C1, int H> struct Epilogue {
             const cpx* s = p.s2_1 + (long)pair * C1 * N1 * N1 * N1 + (long)(x0 >> 1) * N1 + (y0 >> 1);
             DLPD_FOR_TASKS(t, C1 * N1, NT) {
                 const int kz = t % N1, c = t / N1;
-                b1[kz * P1 + c] = __ldg(s + ((long)c * N1 + kz) * N1 * N1);
+                cp_async8(b1 + kz * P1 + c, s + ((long)c * N1 + kz) * N1 * N1);
             }
         }
+        cp_async_wait_all();
         DLPD_SYNC();
         fft_inv_tail<N1, NL1, P1, NT>(b1, tw1, LineMul<1>());
         fft_inv_head<N1, NL1, P1, NT>(b1, tw1, LineMul<1>());
@@ -538,10 +539,10 @@ template <int L_, int C0, int C1, int H> struct Epilogue {
             const cpx* s = p.s2_0 + (long)pair * (C0 + 1) * N * N * N + (long)x0 * N + y0;
             DLPD_FOR_TASKS(t, (C0 + 1) * N * 2, NT) {
                 const int xl = t & 1, kz = (t >> 1) % N, c = t / (2 * N);
-                const float4 v = __ldg(reinterpret_cast<const float4*>(s + (((long)c * N + kz) * N + xl) * N));
-                *reinterpret_cast<float4*>(b0 + kz * NL0 + c * 4 + xl * 2) = v;       // 16-byte aligned: all terms even
+                cp_async16(b0 + kz * NL0 + c * 4 + xl * 2, s + (((long)c * N + kz) * N + xl) * N);   // 16-byte aligned: all terms even
             }
         }
+        cp_async_wait_all();
         DLPD_SYNC();
         fft_inv_tail<N, NL0, NL0, NT>(b0, tw0, LineMul<1>());
         fft_inv_head<N, NL0, NL0, NT>(b0, tw0, LineMul<1>());

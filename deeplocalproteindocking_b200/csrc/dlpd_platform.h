@@ -24,6 +24,10 @@
   // one emulated "thread": tasks run in order
   #define DLPD_FOR_TASKS(t, n, NT) for (int t = 0; t < (n); ++t)
   #define DLPD_SYNC() do {} while (0)
+  // asynchronous global->shared copies (cp.async on the device)
+  static inline void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
+  static inline void cp_async8(void* dst, const void* src) { memcpy(dst, src, 8); }
+  static inline void cp_async_wait_all() {}
   #define DLPD_UNROLL
   #define DLPD_RESTRICT
   typedef void* dlpd_stream_t;
@@ -37,6 +41,19 @@
   #define DLPD_UNROLL _Pragma("unroll")
   #define DLPD_RESTRICT __restrict__
   DLPD_DEV float fmaf_(float a, float b, float c) { return fmaf(a, b, c); }
+  // asynchronous global->shared copies: no register staging, every copy of a thread is in flight at once
+  DLPD_DEV void cp_async16(void* dst, const void* src) {
+      const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+      asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(src) : "memory");
+  }
+  DLPD_DEV void cp_async8(void* dst, const void* src) {
+      const unsigned d = (unsigned)__cvta_generic_to_shared(dst);
+      asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(d), "l"(src) : "memory");
+  }
+  DLPD_DEV void cp_async_wait_all() {
+      asm volatile("cp.async.commit_group;" ::: "memory");
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
+  }
   typedef cudaStream_t dlpd_stream_t;
 #endif
 

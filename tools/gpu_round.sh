@@ -23,7 +23,8 @@ for s in $STAGES; do
         --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --cpu-rotations 0 --rot-batch 16 --max-rot 16 \
         > $OUT/launches_run.log 2>&1 ;;
     ncu)
-      timeout 900 ncu --set full --clock-control none --import-source on -k regex:dlpd_kernel -s 4 -c 5 -o $OUT/prof -f \
+      timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
+        -k "regex:Epilogue|Plane<80>|Plane<40>|FwdZC<80|FwdZC<40" -s 2 -c 5 -o $OUT/prof -f \
         python bench.py --steps 1 --warmup 0 --cpu-rotations 0 --rot-batch 8 --max-rot 8 > $OUT/ncu_run.log 2>&1 ;;
     sanitize)
       timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -q -x -k "small or ties" \
