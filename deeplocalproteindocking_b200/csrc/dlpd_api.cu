@@ -391,7 +391,8 @@ static int launch_epilogue(dlpd_plan* p, int n, int P, float tau, float* out_sco
     typename K::Params e;
     e.s2_0 = p->s2_0; e.s2_1 = p->s2_1; e.best = p->best; e.score_out = out_scores;
     e.tw0 = p->tw0; e.tw1 = p->tw1; e.n_rot = n; e.tau = tau;
-    memcpy(e.filt.W1, p->W1.data(), sizeof(float) * H * (C0 + C1));
+    for (int j = 0; j < H; ++j)
+        for (int c = 0; c < C0 + C1; ++c) e.filt.W1t[c * H + j] = p->W1[(size_t)j * (C0 + C1) + c];
     memcpy(e.filt.b1, p->b1.data(), sizeof(float) * H);
     memcpy(e.filt.W2, p->W2.data(), sizeof(float) * H);
     e.filt.b2 = p->b2;

@@ -18,21 +18,27 @@
 #pragma once
 #include "dlpd_platform.h"
 
-DLPD_HD cpx cadd(cpx a, cpx b) { return make_float2(a.x + b.x, a.y + b.y); }
-DLPD_HD cpx csub(cpx a, cpx b) { return make_float2(a.x - b.x, a.y - b.y); }
-DLPD_HD cpx cmul(cpx a, cpx b) { return make_float2(a.x * b.x - a.y * b.y, a.x * b.y + a.y * b.x); }
-DLPD_HD cpx cmul_i(cpx a) { return make_float2(-a.y, a.x); }          // a * (+i)
-DLPD_HD cpx cscale(cpx a, float s) { return make_float2(a.x * s, a.y * s); }
+// Complex arithmetic on packed fp32x2 instructions (sm_100 FADD2 / FMUL2 / FFMA2): a complex add is ONE instruction,
+// a complex multiply TWO (the swap / negate of halves folds into operand modifiers).
+DLPD_DEV cpx cadd(cpx a, cpx b) { return fadd2_(a, b); }
+DLPD_DEV cpx csub(cpx a, cpx b) { return fadd2_(a, make_float2(-b.x, -b.y)); }
+DLPD_DEV cpx cmul_i(cpx a) { return make_float2(-a.y, a.x); }          // a * (+i)
+DLPD_DEV cpx cscale(cpx a, float s) { return fmul2_(make_float2(s, s), a); }
+DLPD_DEV cpx cmul(cpx a, cpx w) {                                       // a.x * w + a.y * (i w)
+    const cpx t = fmul2_(make_float2(a.y, a.y), make_float2(w.y, w.x));
+    return ffma2_(make_float2(a.x, a.x), w, make_float2(-t.x, t.y));
+}
+DLPD_DEV cpx caxpy(float s, cpx x, cpx y) { return ffma2_(make_float2(s, s), x, y); }   // s * x + y
 
 // ---- small DFTs, sign + ------------------------------------------------------------------------
 template <int R> struct Dft;
 
 template <> struct Dft<1> {
-    static DLPD_HD void run(cpx*) {}
+    static DLPD_DEV void run(cpx*) {}
 };
 
 template <> struct Dft<2> {
-    static DLPD_HD void run(cpx* a) {
+    static DLPD_DEV void run(cpx* a) {
         cpx t = a[0];
         a[0] = cadd(t, a[1]);
         a[1] = csub(t, a[1]);
@@ -40,7 +46,7 @@ template <> struct Dft<2> {
 };
 
 template <> struct Dft<4> {
-    static DLPD_HD void run(cpx* a) {
+    static DLPD_DEV void run(cpx* a) {
         cpx s02 = cadd(a[0], a[2]), d02 = csub(a[0], a[2]);
         cpx s13 = cadd(a[1], a[3]), d13 = cmul_i(csub(a[1], a[3]));
         a[0] = cadd(s02, s13);
@@ -51,16 +57,16 @@ template <> struct Dft<4> {
 };
 
 template <> struct Dft<5> {
-    static DLPD_HD void run(cpx* a) {
+    static DLPD_DEV void run(cpx* a) {
         const float c1 = 0.30901699437494742f, c2 = -0.80901699437494742f;   // cos(2pi/5), cos(4pi/5)
         const float s1 = 0.95105651629515357f, s2 = 0.58778525229247313f;    // sin(2pi/5), sin(4pi/5)
         cpx t1 = cadd(a[1], a[4]), t2 = cadd(a[2], a[3]);
         cpx t3 = csub(a[1], a[4]), t4 = csub(a[2], a[3]);
-        cpx m1 = make_float2(a[0].x + c1 * t1.x + c2 * t2.x, a[0].y + c1 * t1.y + c2 * t2.y);
-        cpx m2 = make_float2(a[0].x + c2 * t1.x + c1 * t2.x, a[0].y + c2 * t1.y + c1 * t2.y);
-        cpx n1 = cmul_i(make_float2(s1 * t3.x + s2 * t4.x, s1 * t3.y + s2 * t4.y));
-        cpx n2 = cmul_i(make_float2(s2 * t3.x - s1 * t4.x, s2 * t3.y - s1 * t4.y));
-        a[0] = make_float2(a[0].x + t1.x + t2.x, a[0].y + t1.y + t2.y);
+        cpx m1 = caxpy(c2, t2, caxpy(c1, t1, a[0]));
+        cpx m2 = caxpy(c1, t2, caxpy(c2, t1, a[0]));
+        cpx n1 = cmul_i(caxpy(s2, t4, cscale(t3, s1)));
+        cpx n2 = cmul_i(caxpy(-s1, t4, cscale(t3, s2)));
+        a[0] = cadd(a[0], cadd(t1, t2));
         a[1] = cadd(m1, n1);
         a[4] = csub(m1, n1);
         a[2] = cadd(m2, n2);
@@ -69,15 +75,15 @@ template <> struct Dft<5> {
 };
 
 template <> struct Dft<8> {
-    static DLPD_HD void run(cpx* a) {
+    static DLPD_DEV void run(cpx* a) {
         const float h = 0.70710678118654752f;
         cpx e[4] = {a[0], a[2], a[4], a[6]};
         cpx o[4] = {a[1], a[3], a[5], a[7]};
         Dft<4>::run(e);
         Dft<4>::run(o);
-        cpx w1 = make_float2(h * (o[1].x - o[1].y), h * (o[1].x + o[1].y));      // o1 * e^{+i pi/4}
+        cpx w1 = cscale(cadd(o[1], cmul_i(o[1])), h);                             // o1 * e^{+i pi/4}
         cpx w2 = cmul_i(o[2]);                                                    // o2 * i
-        cpx w3 = make_float2(-h * (o[3].x + o[3].y), h * (o[3].x - o[3].y));     // o3 * e^{+3i pi/4}
+        cpx w3 = cscale(csub(cmul_i(o[3]), o[3]), h);                             // o3 * e^{+3i pi/4}
         a[0] = cadd(e[0], o[0]); a[4] = csub(e[0], o[0]);
         a[1] = cadd(e[1], w1);   a[5] = csub(e[1], w1);
         a[2] = cadd(e[2], w2);   a[6] = csub(e[2], w2);

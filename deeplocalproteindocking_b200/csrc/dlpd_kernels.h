@@ -22,7 +22,7 @@
 #define DLPD_PLANE_NT 800
 #endif
 #ifndef DLPD_EPI_NT
-#define DLPD_EPI_NT 256
+#define DLPD_EPI_NT 384
 #endif
 #ifndef DLPD_FWDZC_NT
 #define DLPD_FWDZC_NT 256
@@ -408,12 +408,16 @@ template <int L_, int YT_> struct InvZStore {
 // ------------------------------------------------------------------------------------------------------
 // Epilogue
 // ------------------------------------------------------------------------------------------------------
+// SimpleFilter weights as kernel-parameter constants.  The MLP applies each weight to the two rotations of a pair
+// (real / imaginary part of the correlation) with one packed FFMA2 whose weight operand is a broadcast scalar.
 template <int C0, int C1, int H> struct FilterW {
-    float W1[H * (C0 + C1)];   // row-major [H][C0+C1]  (nn.Linear weight, DockingModels.py:29)
+    float W1t[(C0 + C1) * H];  // TRANSPOSED nn.Linear weight (DockingModels.py:29): W1t[c][j] = W1[j][c], so the H
+                               // weights of one input channel are contiguous (one 128-bit constant load per 4)
     float b1[H];
     float W2[H];               // [1][H]                (DockingModels.py:31)
     float b2;
 };
+DLPD_DEV float2 dup2(float w) { return make_float2(w, w); }
 
 // order-preserving map float -> uint32 (a < b  <=>  key(a) < key(b)); +-0 collapse to +0 like torch.min
 DLPD_HD unsigned int score_key(float s) {
@@ -465,27 +469,27 @@ template <int C0, int C1, int H> struct EpiParams {
     FilterW<C0, C1, H> filt;
 };
 
-// hidden-layer contribution of the level-1 (half resolution) channels for JG hidden units starting at J0:
-//   out[jj] = sum_c W1[J0+jj][C0+c] * v[c]      (v = one component of the C1 level-1 correlations at one z')
+// hidden-layer contribution of the level-1 (half resolution) channels for JG hidden units starting at J0, both
+// rotations of the pair at once:  out[jj] = b1[J0+jj] + sum_c W1[J0+jj][C0+c] * v[c]
 template <int C0, int C1, int H, int JG, int J0> struct Level1Hidden {
-    static DLPD_DEV void run(const FilterW<C0, C1, H>& f, const float* v, int stride, float* out) {
-        float acc[JG];
+    static DLPD_DEV void run(const FilterW<C0, C1, H>& f, const cpx* v, cpx* out) {
+        float2 acc[JG];
         DLPD_UNROLL
-        for (int jj = 0; jj < JG; ++jj) acc[jj] = 0.0f;
+        for (int jj = 0; jj < JG; ++jj) acc[jj] = dup2(f.b1[J0 + jj]);
         DLPD_UNROLL
         for (int c = 0; c < C1; ++c) {
-            const float x = v[c * stride];
+            const float2 x = v[c];
             DLPD_UNROLL
-            for (int jj = 0; jj < JG; ++jj) acc[jj] = fmaf_(f.W1[(J0 + jj) * (C0 + C1) + C0 + c], x, acc[jj]);
+            for (int jj = 0; jj < JG; ++jj) acc[jj] = ffma2_(dup2(f.W1t[(C0 + c) * H + J0 + jj]), x, acc[jj]);
         }
         DLPD_UNROLL
         for (int jj = 0; jj < JG; ++jj) out[jj] = acc[jj];
     }
 };
 template <int C0, int C1, int H, int JG, int G> struct Level1Dispatch {      // warp-uniform switch over hidden groups
-    static DLPD_DEV void run(const FilterW<C0, C1, H>& f, int jg, const float* v, int stride, float* out) {
-        if (jg == G) Level1Hidden<C0, C1, H, JG, G * JG>::run(f, v, stride, out);
-        else if constexpr (G + 1 < H / JG) Level1Dispatch<C0, C1, H, JG, G + 1>::run(f, jg, v, stride, out);
+    static DLPD_DEV void run(const FilterW<C0, C1, H>& f, int jg, const cpx* v, cpx* out) {
+        if (jg == G) Level1Hidden<C0, C1, H, JG, G * JG>::run(f, v, out);
+        else if constexpr (G + 1 < H / JG) Level1Dispatch<C0, C1, H, JG, G + 1>::run(f, jg, v, out);
     }
 };
 
@@ -495,18 +499,18 @@ template <int L_, int C0, int C1, int H> struct Epilogue {
     static constexpr int NL0 = 4 * (C0 + 1);       // level-0 lines of a 2x2 tile (even pitch: 16-byte stores)
     static constexpr int NL1 = C1, P1 = C1 + 1;    // level-1 lines, odd pitch (conflict-free component reads)
     static constexpr int JG = (H % 8 == 0) ? 8 : H;          // hidden units per level-1 task
-    static constexpr int N1P = (N1 + 15) / 16 * 16;          // z' padded so that 2*N1P lanes are whole warps
+    static constexpr int N1P = (N1 + 31) / 32 * 32;          // z' padded to whole warps (warp-uniform hidden group)
     static constexpr int NT = DLPD_EPI_NT;
     // level-1 lines alias the level-0 buffer: they are consumed (into h1) before level 0 is loaded
     static constexpr int B0 = (N * NL0 > N1 * P1) ? N * NL0 : N1 * P1;
-    static constexpr int SMEM = (B0 + N + N1) * (int)sizeof(cpx) + N1 * 2 * H * 4 + 64 * 8;
+    static constexpr int SMEM = (B0 + N + N1 + N1 * H) * (int)sizeof(cpx) + 64 * 8;
     // grid: x = N/2 (y tiles), y = N/2 (x tiles), z = P
     static DLPD_DEV void body(const Params& p, int bx, int by, int bz, char* smem) {
         cpx* b0 = reinterpret_cast<cpx*>(smem);        // [kz][NL0]   line = c*4 + xl*2 + yl
         cpx* b1 = b0;                                  // [kz1][P1]   (before level 0 is loaded)
         cpx* tw0 = b0 + B0;
         cpx* tw1 = tw0 + N;
-        float* h1 = reinterpret_cast<float*>(tw1 + N1);                // [z'][rot][H] level-1 hidden contribution
+        cpx* h1 = tw1 + N1;                            // [z'][H] (rotA, rotB): b1 + level-1 part of the hidden layer
         const int y0 = 2 * bx, x0 = 2 * by, pair = bz;
         const int rotA = 2 * pair, rotB = 2 * pair + 1;
         const bool hasB = rotB < p.n_rot;
@@ -525,13 +529,13 @@ template <int L_, int C0, int C1, int H> struct Epilogue {
         fft_inv_head<N1, NL1, P1, NT>(b1, tw1, LineMul<1>());
         // the first filter layer is linear, so the C1 up-sampled channels (U[c,t] = corr1[c, t//2], DockingModels.py:74-76)
         // contribute one hidden vector per level-1 voxel, shared by the 8 level-0 voxels above it
-        DLPD_FOR_TASKS(t, (H / JG) * 2 * N1P, NT) {
-            const int rot = t & 1, z1 = (t >> 1) % N1P, jg = t / (2 * N1P);
+        DLPD_FOR_TASKS(t, (H / JG) * N1P, NT) {
+            const int z1 = t % N1P, jg = t / N1P;
             if (z1 < N1) {
-                float out[JG];
-                Level1Dispatch<C0, C1, H, JG, 0>::run(p.filt, jg, reinterpret_cast<const float*>(b1 + z1 * P1) + rot, 2, out);
+                cpx out[JG];
+                Level1Dispatch<C0, C1, H, JG, 0>::run(p.filt, jg, b1 + z1 * P1, out);
                 DLPD_UNROLL
-                for (int jj = 0; jj < JG; ++jj) h1[(z1 * 2 + rot) * H + jg * JG + jj] = out[jj];
+                for (int jj = 0; jj < JG; ++jj) h1[z1 * H + jg * JG + jj] = out[jj];
             }
         }
         DLPD_SYNC();
@@ -548,36 +552,40 @@ template <int L_, int C0, int C1, int H> struct Epilogue {
         fft_inv_head<N, NL0, NL0, NT>(b0, tw0, LineMul<1>());
 
         unsigned long long bestA = ~0ull, bestB = ~0ull;
-        constexpr int CT = C0 + C1;
-        DLPD_FOR_TASKS(t, 8 * N, NT) {
-            const int rot = t & 1, xy = (t >> 1) & 3, z = t >> 3;
-            const float* v0 = reinterpret_cast<const float*>(b0 + z * NL0 + xy) + rot;     // component `rot` of the pair
-            const float* hz = h1 + ((z >> 1) * 2 + rot) * H;
-            float h[H];
+        DLPD_FOR_TASKS(t, 4 * N, NT) {
+            const int xy = t & 3, z = t >> 2;
+            const cpx* v0 = b0 + z * NL0 + xy;
+            const cpx* hz = h1 + (z >> 1) * H;
+            float2 h[H];                                        // (rotA, rotB) per hidden unit
             DLPD_UNROLL
-            for (int j = 0; j < H; ++j) h[j] = p.filt.b1[j] + hz[j];
+            for (int j = 0; j < H; ++j) h[j] = hz[j];
             DLPD_UNROLL
             for (int c = 0; c < C0; ++c) {
-                const float v = v0[c * 8];
+                const float2 v = v0[c * 4];
                 DLPD_UNROLL
-                for (int j = 0; j < H; ++j) h[j] = fmaf_(p.filt.W1[j * CT + c], v, h[j]);
+                for (int j = 0; j < H; ++j) h[j] = ffma2_(dup2(p.filt.W1t[c * H + j]), v, h[j]);
             }
-            float sc = p.filt.b2;
+            float2 sc = dup2(p.filt.b2);
             DLPD_UNROLL
-            for (int j = 0; j < H; ++j) sc = fmaf_(p.filt.W2[j], fmaxf(h[j], 0.0f), sc);
-            const float clash = v0[C0 * 8];
-            const float V = clash < p.tau ? sc : 0.0f;          // (clash < tau).float() * score   (Docker.py:226,232)
+            for (int j = 0; j < H; ++j) sc = ffma2_(dup2(p.filt.W2[j]), make_float2(fmaxf(h[j].x, 0.0f), fmaxf(h[j].y, 0.0f)), sc);
+            const cpx clash = v0[C0 * 4];
+            const float Va = clash.x < p.tau ? sc.x : 0.0f;     // (clash < tau).float() * score   (Docker.py:226,232)
+            const float Vb = clash.y < p.tau ? sc.y : 0.0f;
             const unsigned int lin = (unsigned int)(((x0 + (xy >> 1)) * N + (y0 + (xy & 1))) * N + z);
-            const unsigned long long key = ((unsigned long long)score_key(V) << 32) | lin;
-            if (rot == 0) bestA = key < bestA ? key : bestA;
-            else bestB = key < bestB ? key : bestB;
-            if (p.score_out != nullptr && (rot == 0 || hasB)) p.score_out[(long)(rotA + rot) * N * N * N + lin] = V;
+            const unsigned long long ka = ((unsigned long long)score_key(Va) << 32) | lin;
+            const unsigned long long kb = ((unsigned long long)score_key(Vb) << 32) | lin;
+            bestA = ka < bestA ? ka : bestA;
+            bestB = kb < bestB ? kb : bestB;
+            if (p.score_out != nullptr) {
+                p.score_out[(long)rotA * N * N * N + lin] = Va;
+                if (hasB) p.score_out[(long)rotB * N * N * N + lin] = Vb;
+            }
         }
 #if defined(DLPD_EMU)
         if (bestA < p.best[rotA]) p.best[rotA] = bestA;
         if (hasB && bestB < p.best[rotB]) p.best[rotB] = bestB;
 #else
-        unsigned long long* red = reinterpret_cast<unsigned long long*>(h1 + N1 * 2 * H);
+        unsigned long long* red = reinterpret_cast<unsigned long long*>(h1 + N1 * H);
         bestA = block_min_u64<NT>(bestA, red);
         bestB = block_min_u64<NT>(bestB, red + 32);
         if (threadIdx.x == 0) {

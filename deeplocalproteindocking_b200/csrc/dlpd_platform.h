@@ -21,6 +21,10 @@
   static inline float2 __ldg(const float2* p) { return *p; }
   static inline float4 __ldg(const float4* p) { return *p; }
   static inline float fmaf_(float a, float b, float c) { return fmaf(a, b, c); }
+  // packed fp32x2 arithmetic (FFMA2 / FADD2 on sm_100)
+  static inline float2 ffma2_(float2 a, float2 b, float2 c) { return make_float2(fmaf(a.x, b.x, c.x), fmaf(a.y, b.y, c.y)); }
+  static inline float2 fadd2_(float2 a, float2 b) { return make_float2(a.x + b.x, a.y + b.y); }
+  static inline float2 fmul2_(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
   // one emulated "thread": tasks run in order
   #define DLPD_FOR_TASKS(t, n, NT) for (int t = 0; t < (n); ++t)
   #define DLPD_SYNC() do {} while (0)
@@ -41,6 +45,10 @@
   #define DLPD_UNROLL _Pragma("unroll")
   #define DLPD_RESTRICT __restrict__
   DLPD_DEV float fmaf_(float a, float b, float c) { return fmaf(a, b, c); }
+  // packed fp32x2 arithmetic: one FFMA2 / FADD2 instruction does two fp32 operations per lane (Blackwell)
+  DLPD_DEV float2 ffma2_(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+  DLPD_DEV float2 fadd2_(float2 a, float2 b) { return __fadd2_rn(a, b); }
+  DLPD_DEV float2 fmul2_(float2 a, float2 b) { return __fmul2_rn(a, b); }
   // asynchronous global->shared copies: no register staging, every copy of a thread is in flight at once
   DLPD_DEV void cp_async16(void* dst, const void* src) {
       const unsigned d = (unsigned)__cvta_generic_to_shared(dst);

@@ -24,7 +24,7 @@ for s in $STAGES; do
         > $OUT/launches_run.log 2>&1 ;;
     ncu)
       timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-        -k "regex:Epilogue|Plane<80>|Plane<40>|FwdZC<80|FwdZC<40" -s 2 -c 5 -o $OUT/prof -f \
+        -k "regex:Epilogue|Plane|FwdZC" -s 2 -c 5 -o $OUT/prof -f \
         python bench.py --steps 1 --warmup 0 --cpu-rotations 0 --rot-batch 8 --max-rot 8 > $OUT/ncu_run.log 2>&1 ;;
     sanitize)
       timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -q -x -k "small or ties" \
