@@ -39,7 +39,8 @@ TAU = 300.0
 
 def algorithmic_bytes_per_rotation(L=L, C0=C0, C1=C1):
     """per channel of edge l (n = 2l, h = n*n*(n/2+1)): 4 l^3 + 24 h bytes; split by kernel as
-    FwdZ = 4 l^3 (read ligand), Plane = 16 h (receptor spectrum read + spectrum write), Epilogue = 8 h (read back)."""
+    FwdZ = 4 l^3 (read ligand), Plane = 16 h (receptor spectrum read + spectrum write), Epilogue (level 0) and
+    HiddenL1 (level 1) = 8 h (read back)."""
     def h(l):
         n = 2 * l
         return n * n * (n // 2 + 1)
@@ -47,7 +48,7 @@ def algorithmic_bytes_per_rotation(L=L, C0=C0, C1=C1):
     parts = {
         "fwdz_level0": lv0 * 4 * L ** 3, "fwdz_level1": lv1 * 4 * (L // 2) ** 3,
         "plane_level0": lv0 * 16 * h(L), "plane_level1": lv1 * 16 * h(L // 2),
-        "epilogue": lv0 * 8 * h(L) + lv1 * 8 * h(L // 2),
+        "epilogue": lv0 * 8 * h(L), "hidden_level1": lv1 * 8 * h(L // 2),
     }
     parts["total"] = sum(parts.values())
     return parts

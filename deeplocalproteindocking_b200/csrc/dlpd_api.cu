@@ -26,6 +26,7 @@ struct dim3 {
     dim3(unsigned a = 1, unsigned b = 1, unsigned c = 1) : x(a), y(b), z(c) {}
 };
 static int rt_set_device(int) { return 0; }
+static int rt_sm_count(int) { return 3; }       // the emulation walks the persistent kernels with 3 "CTAs"
 static int rt_malloc(void** p, size_t n) { *p = calloc(n ? n : 1, 1); return *p ? 0 : fail(DLPD_ECUDA, "emu: out of memory"); }
 static int rt_malloc_host(void** p, size_t n) { return rt_malloc(p, n); }
 static void rt_free(void* p) { free(p); }
@@ -50,6 +51,10 @@ template <class K> static int launch(dim3 g, const typename K::Params& p, dlpd_s
             return fail(DLPD_ECUDA, std::string(#call) + ": " + cudaGetErrorString(e_));             \
     } while (0)
 static int rt_set_device(int d) { CU(cudaSetDevice(d)); return 0; }
+static int rt_sm_count(int d) {
+    int n = 0;
+    return cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, d) == cudaSuccess && n > 0 ? n : 148;
+}
 static int rt_malloc(void** p, size_t n) { CU(cudaMalloc(p, n ? n : 1)); return 0; }
 static int rt_malloc_host(void** p, size_t n) { CU(cudaMallocHost(p, n ? n : 1)); return 0; }
 static void rt_free(void* p) { if (p) cudaFree(p); }
@@ -192,6 +197,8 @@ struct dlpd_plan {
     float *lig0_cl, *lig1_cl;    // channel-last copies [L^3][C0], [(L/2)^3][C1] of the feature volumes (FwdZC)
     cpx *rspec0, *rspec1;        // receptor spectra [(C0+1)][N^3], [C1][L^3]
     cpx *s1_0, *s1_1, *s2_0, *s2_1;
+    cpx* h1;                     // [P][L^3][H] level-1 part of the hidden layer (HiddenL1 -> Epilogue)
+    int sm_count;
     unsigned long long* best;    // [max_rot]
     float *pin_R, *pin_best;     // pinned staging for dlpd_search_host
     float *dev_R, *dev_best;
@@ -264,7 +271,7 @@ extern "C" int dlpd_plan_destroy(dlpd_plan* p) {
     rt_set_device(p->device);
     rt_free(p->tw0); rt_free(p->tw1); rt_free(p->tw2);
     rt_free(p->lig0); rt_free(p->lig1); rt_free(p->lig0_cl); rt_free(p->lig1_cl); rt_free(p->rspec0); rt_free(p->rspec1);
-    rt_free(p->s1_0); rt_free(p->s1_1); rt_free(p->s2_0); rt_free(p->s2_1);
+    rt_free(p->s1_0); rt_free(p->s1_1); rt_free(p->s2_0); rt_free(p->s2_1); rt_free(p->h1);
     rt_free(p->best); rt_free(p->dev_R); rt_free(p->dev_best);
     rt_free_host(p->pin_R); rt_free_host(p->pin_best);
 #if !defined(DLPD_EMU)
@@ -291,7 +298,8 @@ extern "C" int dlpd_plan_create(dlpd_plan** out, int L, int C0, int C1, int H, i
     p->P = (max_rot + 1) / 2;
     p->tw0 = p->tw1 = p->tw2 = nullptr; p->lig0 = p->lig1 = nullptr; p->rspec0 = p->rspec1 = nullptr;
     p->lig0_cl = p->lig1_cl = nullptr;
-    p->s1_0 = p->s1_1 = p->s2_0 = p->s2_1 = nullptr; p->best = nullptr;
+    p->s1_0 = p->s1_1 = p->s2_0 = p->s2_1 = nullptr; p->best = nullptr; p->h1 = nullptr;
+    p->sm_count = rt_sm_count(device);
     p->pin_R = p->pin_best = p->dev_R = p->dev_best = nullptr; p->host_cap = 0;
     p->has_receptor = p->has_ligand = p->lig_has_clash = p->has_filter = false;
     p->b2 = 0.f;
@@ -310,6 +318,7 @@ extern "C" int dlpd_plan_create(dlpd_plan** out, int L, int C0, int C1, int H, i
         {(void**)&p->s1_1, sizeof(cpx) * P * C1 * N1 * L1 * L1},
         {(void**)&p->s2_0, sizeof(cpx) * P * (C0 + 1) * n3(N)},
         {(void**)&p->s2_1, sizeof(cpx) * P * C1 * n3(N1)},
+        {(void**)&p->h1, sizeof(cpx) * P * n3(N1) * H},
         {(void**)&p->best, sizeof(unsigned long long) * (size_t)max_rot},
     };
     p->bytes = 0;
@@ -334,7 +343,7 @@ static int real_spectra(int L, const float* vols, int C, cpx* s1, cpx* spec, con
     f.C = C; f.Ctot = C; f.c_out0 = 0; f.c_ext = -1; f.n_rot = 1; f.center = 0.f;
     TRY(launch_fwdz(L, f, 1, st));
     PlaneParams q;
-    q.in = s1; q.out = spec; q.spec = nullptr; q.spec_pair_stride = 0; q.tw = tw; q.C = C; q.P = 1;
+    q.in = s1; q.out = spec; q.spec = nullptr; q.spec_pair_stride = 0; q.tw = tw; q.C = C; q.P = 1; q.tiled = 0;
     q.scale = (float)(1.0 / ((double)N * N * N));
     TRY(launch_plane(L, q, st));
     return 0;
@@ -385,18 +394,32 @@ extern "C" int dlpd_set_filter(dlpd_plan* p, const float* W1, const float* b1, c
     return 0;
 }
 
+template <int C0, int C1, int H> static void fill_filter(const dlpd_plan* p, FilterW<C0, C1, H>& f) {
+    for (int j = 0; j < H; ++j)
+        for (int c = 0; c < C0 + C1; ++c) f.W1t[c * H + j] = p->W1[(size_t)j * (C0 + C1) + c];
+    memcpy(f.b1, p->b1.data(), sizeof(float) * H);
+    memcpy(f.W2, p->W2.data(), sizeof(float) * H);
+    f.b2 = p->b2;
+}
+
+template <int L, int C0, int C1, int H> static int launch_hidden(dlpd_plan* p, int P, dlpd_stream_t st) {
+    typedef HiddenL1<L, C0, C1, H> K;
+    typename K::Params e;
+    e.s2_1 = p->s2_1; e.h1 = p->h1; e.tw1 = p->tw1;
+    fill_filter(p, e.filt);
+    return launch<K>(dim3(K::N1 / K::YT, K::N1, P), e, st);
+}
+
 template <int L, int C0, int C1, int H>
 static int launch_epilogue(dlpd_plan* p, int n, int P, float tau, float* out_scores, dlpd_stream_t st) {
     typedef Epilogue<L, C0, C1, H> K;
     typename K::Params e;
-    e.s2_0 = p->s2_0; e.s2_1 = p->s2_1; e.best = p->best; e.score_out = out_scores;
-    e.tw0 = p->tw0; e.tw1 = p->tw1; e.n_rot = n; e.tau = tau;
-    for (int j = 0; j < H; ++j)
-        for (int c = 0; c < C0 + C1; ++c) e.filt.W1t[c * H + j] = p->W1[(size_t)j * (C0 + C1) + c];
-    memcpy(e.filt.b1, p->b1.data(), sizeof(float) * H);
-    memcpy(e.filt.W2, p->W2.data(), sizeof(float) * H);
-    e.filt.b2 = p->b2;
-    return launch<K>(dim3(L, L, P), e, st);
+    e.s2_0 = p->s2_0; e.h1 = p->h1; e.best = p->best; e.score_out = out_scores;
+    e.tw0 = p->tw0; e.n_rot = n; e.tau = tau;
+    e.n_tiles = P * L * L;
+    e.grid = e.n_tiles < p->sm_count ? e.n_tiles : p->sm_count;
+    fill_filter(p, e.filt);
+    return launch<K>(dim3(e.grid), e, st);
 }
 
 // one chunk of n <= max_rot rotations
@@ -438,11 +461,19 @@ static int search_chunk(dlpd_plan* p, const float* R, const float* clash_rot, in
     }
     PlaneParams q;
     q.in = p->s1_0; q.out = p->s2_0; q.spec = p->rspec0; q.spec_pair_stride = 0; q.tw = p->tw0; q.C = p->C0 + 1; q.P = P;
-    q.scale = 1.f;
+    q.scale = 1.f; q.tiled = 1;
     { ProfScope ps(p, DLPD_PROFILE_PLANE0, st); TRY(launch_plane(L, q, st)); }
-    q.in = p->s1_1; q.out = p->s2_1; q.spec = p->rspec1; q.tw = p->tw1; q.C = p->C1;
+    q.in = p->s1_1; q.out = p->s2_1; q.spec = p->rspec1; q.tw = p->tw1; q.C = p->C1; q.tiled = 0;
     { ProfScope ps(p, DLPD_PROFILE_PLANE1, st); TRY(launch_plane(L1, q, st)); }
     int rc = DLPD_EINVAL;
+    {
+        ProfScope ps(p, DLPD_PROFILE_HIDDEN1, st);
+#define X(L_, A, B, C) if (p->L == L_ && p->C0 == A && p->C1 == B && p->H == C) rc = launch_hidden<L_, A, B, C>(p, P, st);
+        DLPD_SEARCH_CONFIGS(X)
+#undef X
+    }
+    TRY(rc);
+    rc = DLPD_EINVAL;
     {
         ProfScope ps(p, DLPD_PROFILE_EPILOGUE, st);
 #define X(L_, A, B, C) if (p->L == L_ && p->C0 == A && p->C1 == B && p->H == C) rc = launch_epilogue<L_, A, B, C>(p, n, P, tau, out_scores, st);
@@ -567,7 +598,7 @@ extern "C" int dlpd_volume_correlate(const float* v1, const float* v2, float* ou
         f.C = 1; f.Ctot = 1; f.c_out0 = 0; f.c_ext = -1; f.n_rot = 1; f.center = 0.f;
         TRY(launch_fwdz(L, f, q, st));
         PlaneParams pl;
-        pl.in = w.s1; pl.out = w.spec; pl.spec = nullptr; pl.spec_pair_stride = 0; pl.tw = w.tw; pl.C = 1; pl.P = q;
+        pl.in = w.s1; pl.out = w.spec; pl.spec = nullptr; pl.spec_pair_stride = 0; pl.tw = w.tw; pl.C = 1; pl.P = q; pl.tiled = 0;
         pl.scale = (float)(1.0 / ((double)N * N * N));
         TRY(launch_plane(L, pl, st));
         f.src = v2 + n3(L) * i0;

@@ -115,7 +115,10 @@ struct NoHook {};
 // element `e` (index along the line) of line `l`
 template <class F> struct GlobalIn { F f; };      // f(l, e) -> cpx        : read from global instead of shared
 template <class F> struct GlobalOut { F f; };     // f(l, e, value)        : write to global instead of shared
+template <class F> struct GlobalOutPair { F f; }; // f(l, e, v_e, v_e1)    : elements e (even) and e+1 of line l together
 template <class F> struct PointMul { F f; };      // f(l, e) -> cpx        : multiply between the two halves of a MID pass
+template <class T> struct is_pair_out : std::false_type {};
+template <class F> struct is_pair_out<GlobalOutPair<F> > : std::true_type {};
 
 enum PassKind {
     PASS_DIF = 0,        // forward pair: outer radix RA at block NB, inner radix RB at block NB/RA
@@ -127,25 +130,19 @@ enum PassKind {
 // One fused pass over NLINES lines of LEN elements held in shared memory `s` (element stride ES, line offsets `off`).
 //   NB   block size of the outer radix (LEN % NB == 0);  TWN size of the twiddle table tw[k] = e^{+2 pi i k/TWN}
 //   In / Out / Mul: NoHook or the hook structs above
-template <int KIND, int RA, int RB, int NLINES, int LEN, int NB, int TWN, int ES, int NT, class LineOff,
-          class In = NoHook, class Out = NoHook, class Mul = NoHook>
-DLPD_DEV void fft_pass(cpx* s, const cpx* tw, LineOff off, In in = In(), Out out = Out(), Mul mul = Mul()) {
-    constexpr int M = NB / RA;             // outer sub-block
-    constexpr int M2 = M / RB;             // inner sub-block: range of the butterfly index j
-    constexpr int TPL = LEN / (RA * RB);   // tasks per line
-    constexpr int TWO = TWN / NB;          // outer twiddle w_NB^x = tw[TWO * x]
-    constexpr int TWI = TWN / M;           // inner twiddle w_M^x  = tw[TWI * x]
-    constexpr bool FWD = KIND == PASS_DIF || KIND == PASS_DIF_PRUNED || KIND == PASS_MID;
-    constexpr bool INV = KIND == PASS_DIT || KIND == PASS_MID;
+template <int KIND, int RA, int RB, int LEN, int NB, int TWN, int ES> struct FftTask {
+    static constexpr int M = NB / RA;             // outer sub-block
+    static constexpr int M2 = M / RB;             // inner sub-block: range of the butterfly index j
+    static constexpr int TPL = LEN / (RA * RB);   // tasks per line
+    static constexpr int TWO = TWN / NB;          // outer twiddle w_NB^x = tw[TWO * x]
+    static constexpr int TWI = TWN / M;           // inner twiddle w_M^x  = tw[TWI * x]
+    static constexpr bool FWD = KIND == PASS_DIF || KIND == PASS_DIF_PRUNED || KIND == PASS_MID;
+    static constexpr bool INV = KIND == PASS_DIT || KIND == PASS_MID;
     static_assert(KIND != PASS_DIF_PRUNED || RA == 2, "pruned pass is the outermost radix-2 step");
-    DLPD_FOR_TASKS(t, NLINES * TPL, NT) {
-        const int l = t % NLINES;
-        const int b = t / NLINES;
-        const int blk = b / M2;
-        const int j = b - blk * M2;
-        const int e0 = blk * NB + j;       // element index of (pa = 0, s = 0)
-        cpx* p = s + off(l) + e0 * ES;
-        cpx a[RA][RB];
+
+    // load the RA x RB values of the task whose first element is e0 = blk*NB + j (line l at `p`) and transform them
+    template <class In, class Mul>
+    static DLPD_DEV void run(cpx (&a)[RA][RB], const cpx* p, const cpx* tw, int l, int e0, int j, In& in, Mul& mul) {
         // ---- load: a[i][k] <- element e0 + i*M + k*M2
         DLPD_UNROLL
         for (int i = 0; i < RA; ++i) {
@@ -208,17 +205,60 @@ DLPD_DEV void fft_pass(cpx* s, const cpx* tw, LineOff off, In in = In(), Out out
                 for (int i = 0; i < RA; ++i) a[i][k] = c[i];
             }
         }
-        // ---- store to the same positions
-        DLPD_UNROLL
-        for (int i = 0; i < RA; ++i) {
+    }
+};
+
+template <int KIND, int RA, int RB, int NLINES, int LEN, int NB, int TWN, int ES, class TM, class LineOff,
+          class In = NoHook, class Out = NoHook, class Mul = NoHook>
+DLPD_DEV void fft_pass_team(const TM& tm, cpx* s, const cpx* tw, LineOff off, In in = In(), Out out = Out(), Mul mul = Mul()) {
+    typedef FftTask<KIND, RA, RB, LEN, NB, TWN, ES> T;
+    constexpr int M = T::M, M2 = T::M2, TPL = T::TPL;
+    if constexpr (is_pair_out<Out>::value) {
+        // two neighbouring butterflies (elements e, e+1) per task: the hook stores 16-byte pairs
+        static_assert(M2 % 2 == 0, "paired output needs an even inner sub-block");
+        DLPD_TEAM_TASKS(tm, t, NLINES * (TPL / 2)) {
+            const int l = t % NLINES;
+            const int b = 2 * (t / NLINES);
+            const int blk = b / M2;
+            const int j = b - blk * M2;
+            const int e0 = blk * NB + j;
+            const cpx* p = s + off(l) + e0 * ES;
+            cpx a0[RA][RB], a1[RA][RB];
+            T::run(a0, p, tw, l, e0, j, in, mul);
+            T::run(a1, p + ES, tw, l, e0 + 1, j + 1, in, mul);
             DLPD_UNROLL
-            for (int k = 0; k < RB; ++k) {
-                if constexpr (std::is_same<Out, NoHook>::value) p[(i * M + k * M2) * ES] = a[i][k];
-                else out.f(l, e0 + i * M + k * M2, a[i][k]);
+            for (int i = 0; i < RA; ++i) {
+                DLPD_UNROLL
+                for (int k = 0; k < RB; ++k) out.f(l, e0 + i * M + k * M2, a0[i][k], a1[i][k]);
+            }
+        }
+    } else {
+        DLPD_TEAM_TASKS(tm, t, NLINES * TPL) {
+            const int l = t % NLINES;
+            const int b = t / NLINES;
+            const int blk = b / M2;
+            const int j = b - blk * M2;
+            const int e0 = blk * NB + j;       // element index of (pa = 0, s = 0)
+            cpx* p = s + off(l) + e0 * ES;
+            cpx a[RA][RB];
+            T::run(a, p, tw, l, e0, j, in, mul);
+            // ---- store to the same positions
+            DLPD_UNROLL
+            for (int i = 0; i < RA; ++i) {
+                DLPD_UNROLL
+                for (int k = 0; k < RB; ++k) {
+                    if constexpr (std::is_same<Out, NoHook>::value) p[(i * M + k * M2) * ES] = a[i][k];
+                    else out.f(l, e0 + i * M + k * M2, a[i][k]);
+                }
             }
         }
     }
-    DLPD_SYNC();
+    tm.sync();
+}
+template <int KIND, int RA, int RB, int NLINES, int LEN, int NB, int TWN, int ES, int NT, class LineOff,
+          class In = NoHook, class Out = NoHook, class Mul = NoHook>
+DLPD_DEV void fft_pass(cpx* s, const cpx* tw, LineOff off, In in = In(), Out out = Out(), Mul mul = Mul()) {
+    fft_pass_team<KIND, RA, RB, NLINES, LEN, NB, TWN, ES>(CtaTeam<NT>(), s, tw, off, in, out, mul);
 }
 
 // ---- whole-line helpers -------------------------------------------------------------------------------------
@@ -249,4 +289,30 @@ DLPD_DEV void fft_inv_tail(cpx* s, const cpx* tw, LineOff off, In in = In()) {
 template <int N, int NLINES, int ES, int NT, class LineOff, class Out = NoHook>
 DLPD_DEV void fft_inv_head(cpx* s, const cpx* tw, LineOff off, Out out = Out()) {
     fft_pass<PASS_DIT, 2, LinePlan<N>::R0, NLINES, N, N, N, ES, NT>(s, tw, off, NoHook(), out);
+}
+
+// ---- the same helpers for an explicit team (SubTeam / CtaTeam) ------------------------------------------------
+template <int N, int NLINES, int ES, class TM, class LineOff, class In = NoHook>
+DLPD_DEV void team_fwd_head(const TM& tm, cpx* s, const cpx* tw, LineOff off, In in = In()) {
+    fft_pass_team<PASS_DIF_PRUNED, 2, LinePlan<N>::R0, NLINES, N, N, N, ES>(tm, s, tw, off, in);
+}
+template <int N, int NLINES, int ES, class TM, class LineOff>
+DLPD_DEV void team_fwd_tail(const TM& tm, cpx* s, const cpx* tw, LineOff off) {
+    typedef LinePlan<N> P;
+    if constexpr (P::TAIL > 1) fft_pass_team<PASS_DIF, P::TA, P::TB, NLINES, N, P::TAIL, N, ES>(tm, s, tw, off);
+}
+template <int N, int NLINES, int ES, class TM, class LineOff, class Mul>
+DLPD_DEV void team_mid(const TM& tm, cpx* s, const cpx* tw, LineOff off, Mul mul) {
+    typedef LinePlan<N> P;
+    fft_pass_team<PASS_MID, P::TA, P::TB, NLINES, N, P::TAIL, N, ES>(tm, s, tw, off, NoHook(), NoHook(), mul);
+}
+template <int N, int NLINES, int ES, class TM, class LineOff, class In = NoHook>
+DLPD_DEV void team_inv_tail(const TM& tm, cpx* s, const cpx* tw, LineOff off, In in = In()) {
+    typedef LinePlan<N> P;
+    if constexpr (P::TAIL > 1 || !std::is_same<In, NoHook>::value)
+        fft_pass_team<PASS_DIT, P::TA, P::TB, NLINES, N, P::TAIL, N, ES>(tm, s, tw, off, in);
+}
+template <int N, int NLINES, int ES, class TM, class LineOff, class Out = NoHook>
+DLPD_DEV void team_inv_head(const TM& tm, cpx* s, const cpx* tw, LineOff off, Out out = Out()) {
+    fft_pass_team<PASS_DIT, 2, LinePlan<N>::R0, NLINES, N, N, N, ES>(tm, s, tw, off, NoHook(), out);
 }

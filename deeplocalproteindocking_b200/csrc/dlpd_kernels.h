@@ -22,7 +22,13 @@
 #define DLPD_PLANE_NT 800
 #endif
 #ifndef DLPD_EPI_NT
-#define DLPD_EPI_NT 384
+#define DLPD_EPI_NT 768
+#endif
+#ifndef DLPD_HID_NT
+#define DLPD_HID_NT 512
+#endif
+#ifndef DLPD_PLANE_PREFETCH
+#define DLPD_PLANE_PREFETCH 1
 #endif
 #ifndef DLPD_FWDZC_NT
 #define DLPD_FWDZC_NT 256
@@ -317,6 +323,7 @@ struct PlaneParams {
     long spec_pair_stride;   // 0: all pairs share the receptor (search); C*N^3: one spectrum per "pair"
     const cpx* tw;           // [N]
     int C, P;
+    int tiled;               // S2 rows in natural [x][y] order (0) or in 2x2 tiles [x/2][y/2][x&1][y&1] (1, fused search)
     float scale;
 };
 
@@ -333,9 +340,20 @@ template <int L_> struct Plane {
         const cpx* spec;
         DLPD_DEV cpx operator()(int l, int e) const { return __ldg(spec + e * N + l); }
     };
-    struct StoreS2 {         // element e = x of column l = y
+    struct StoreS2 {         // element e = x of column l = y, natural [x][y] rows
         cpx* out;
         DLPD_DEV void operator()(int l, int e, cpx v) const { out[e * N + l] = v; }
+    };
+    // tiled S2 (fused search): [x/2][y/2][y&1][x&1] -- the 2x2 (x,y) tile of the epilogue is 32 contiguous bytes
+    struct StoreS2Tiled {
+        cpx* out;
+        DLPD_DEV void operator()(int l, int e, cpx v) const { out[((((e >> 1) * L) + (l >> 1)) << 2) + ((l & 1) << 1) + (e & 1)] = v; }
+    };
+    struct StoreS2TiledPair {   // elements x = e (even) and e + 1 of column y = l: one 16-byte store, 512 contiguous bytes per warp
+        cpx* out;
+        DLPD_DEV void operator()(int l, int e, cpx v0, cpx v1) const {
+            store_cpx2(out + ((((e >> 1) * L) + (l >> 1)) << 2) + ((l & 1) << 1), v0, v1);
+        }
     };
     // grid: x = P * N * C  with the pair index fastest (CTAs that share a receptor plane run together -> L2 reuse)
     static DLPD_DEV void body(const Params& p, int bx, int, int, char* smem) {
@@ -345,6 +363,11 @@ template <int L_> struct Plane {
         DLPD_FOR_TASKS(t, N, NT) tw[t] = p.tw[t];
         DLPD_SYNC();
         const long plane = ((long)pair * p.C + c) * N + kz;
+        const cpx* spec = p.spec ? p.spec + (long)pair * p.spec_pair_stride + ((long)c * N + kz) * N * N : nullptr;
+#if DLPD_PLANE_PREFETCH
+        // pull the receptor plane towards L2 now; it is consumed three passes later
+        if (spec) DLPD_FOR_TASKS(t, N * N / 16, NT) prefetch_l2(reinterpret_cast<const char*>(spec) + 128 * t);
+#endif
         GlobalIn<LoadS1> in{LoadS1{p.in + plane * L * L}};
         fft_fwd_head<N, L, NP, NT>(pl, tw, LineMul<1>(), in);                   // along x, columns y < L
         fft_fwd_tail<N, L, NP, NT>(pl, tw, LineMul<1>());
@@ -359,12 +382,22 @@ template <int L_> struct Plane {
             }
             return;
         }
-        PointMul<MulSpec> mul{MulSpec{p.spec + (long)pair * p.spec_pair_stride + ((long)c * N + kz) * N * N}};
+        PointMul<MulSpec> mul{MulSpec{spec}};
         fft_mid<N, N, 1, NT>(pl, tw, LineMul<NP>(), mul);                       // y tail . multiply . inverse y tail
         fft_inv_head<N, N, 1, NT>(pl, tw, LineMul<NP>());                       // inverse y
         fft_inv_tail<N, N, NP, NT>(pl, tw, LineMul<1>());                       // inverse x
-        GlobalOut<StoreS2> out{StoreS2{p.out + plane * N * N}};
-        fft_inv_head<N, N, NP, NT>(pl, tw, LineMul<1>(), out);
+        if (p.tiled) {
+            if constexpr ((N / 2 / LinePlan<N>::R0) % 2 == 0) {
+                GlobalOutPair<StoreS2TiledPair> out{StoreS2TiledPair{p.out + plane * N * N}};
+                fft_inv_head<N, N, NP, NT>(pl, tw, LineMul<1>(), out);
+            } else {
+                GlobalOut<StoreS2Tiled> out{StoreS2Tiled{p.out + plane * N * N}};
+                fft_inv_head<N, N, NP, NT>(pl, tw, LineMul<1>(), out);
+            }
+        } else {
+            GlobalOut<StoreS2> out{StoreS2{p.out + plane * N * N}};
+            fft_inv_head<N, N, NP, NT>(pl, tw, LineMul<1>(), out);
+        }
     }
 };
 
@@ -457,28 +490,16 @@ DLPD_DEV unsigned long long block_min_u64(unsigned long long v, unsigned long lo
 }
 #endif
 
-template <int C0, int C1, int H> struct EpiParams {
-    const cpx* s2_0;              // [P][C0+1][N][N][N]   (kz', x, y); channel C0 = clash
-    const cpx* s2_1;              // [P][C1][L][L][L]     level 1 (N1 = L)
-    unsigned long long* best;     // [n_rot] packed (score_key << 32 | linear index), pre-set to ~0
-    float* score_out;             // optional [n_rot][N^3] masked score volume (module-level drop-in / tests)
-    const cpx* tw0;               // [N]
-    const cpx* tw1;               // [L]
-    int n_rot;
-    float tau;
-    FilterW<C0, C1, H> filt;
-};
-
 // hidden-layer contribution of the level-1 (half resolution) channels for JG hidden units starting at J0, both
-// rotations of the pair at once:  out[jj] = b1[J0+jj] + sum_c W1[J0+jj][C0+c] * v[c]
-template <int C0, int C1, int H, int JG, int J0> struct Level1Hidden {
+// rotations of the pair at once:  out[jj] = b1[J0+jj] + sum_c W1[J0+jj][C0+c] * v[c * CS]
+template <int C0, int C1, int H, int JG, int J0, int CS> struct Level1Hidden {
     static DLPD_DEV void run(const FilterW<C0, C1, H>& f, const cpx* v, cpx* out) {
         float2 acc[JG];
         DLPD_UNROLL
         for (int jj = 0; jj < JG; ++jj) acc[jj] = dup2(f.b1[J0 + jj]);
         DLPD_UNROLL
         for (int c = 0; c < C1; ++c) {
-            const float2 x = v[c];
+            const float2 x = v[c * CS];
             DLPD_UNROLL
             for (int jj = 0; jj < JG; ++jj) acc[jj] = ffma2_(dup2(f.W1t[(C0 + c) * H + J0 + jj]), x, acc[jj]);
         }
@@ -486,106 +507,114 @@ template <int C0, int C1, int H, int JG, int J0> struct Level1Hidden {
         for (int jj = 0; jj < JG; ++jj) out[jj] = acc[jj];
     }
 };
-template <int C0, int C1, int H, int JG, int G> struct Level1Dispatch {      // warp-uniform switch over hidden groups
+template <int C0, int C1, int H, int JG, int G, int CS> struct Level1Dispatch {      // warp-uniform switch over hidden groups
     static DLPD_DEV void run(const FilterW<C0, C1, H>& f, int jg, const cpx* v, cpx* out) {
-        if (jg == G) Level1Hidden<C0, C1, H, JG, G * JG>::run(f, v, out);
-        else if constexpr (G + 1 < H / JG) Level1Dispatch<C0, C1, H, JG, G + 1>::run(f, jg, v, out);
+        if (jg == G) Level1Hidden<C0, C1, H, JG, G * JG, CS>::run(f, v, out);
+        else if constexpr (G + 1 < H / JG) Level1Dispatch<C0, C1, H, JG, G + 1, CS>::run(f, jg, v, out);
     }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// HiddenL1: level-1 (half resolution) part of the filter's hidden layer.
+// The first filter layer is linear, so the C1 nearest-up-sampled channels (U[c,t] = corr1[c, t//2], DockingModels.py:74-76)
+// contribute ONE hidden pre-activation vector per level-1 voxel, shared by the 8 level-0 voxels above it:
+//     h1[x1,y1,z1][j] = b1[j] + sum_c W1[j][C0+c] * corr1[c][x1,y1,z1]
+// One CTA: inverse z-FFT of the C1 lines of YT level-1 columns (x1, y0..y0+YT-1), then the C1 -> H contraction.
+// The level-1 correlation volumes never reach HBM; only h1 (H complex = 2 rotations per level-1 voxel) does.
+// ------------------------------------------------------------------------------------------------------
+template <int C0, int C1, int H> struct HidParams {
+    const cpx* s2_1;              // [P][C1][N1][N1][N1]  (kz', x1, y1)
+    cpx* h1;                      // [P][N1][N1][N1][H]   (x1, y1, z1, j)
+    const cpx* tw1;               // [N1]
+    FilterW<C0, C1, H> filt;
+};
+
+template <int L_, int C0, int C1, int H> struct HiddenL1 {
+    typedef HidParams<C0, C1, H> Params;
+    static constexpr int N1 = L_, YT = 4, NL = C1 * YT;
+    static constexpr int P1 = NL + 4;                        // row pitch: 16-byte rows, conflict-free (yl, z1) reads
+    static constexpr int JG = (H % 8 == 0) ? 8 : H;          // hidden units per task
+    static constexpr int VP = (YT * N1 + 31) / 32 * 32;      // (yl, z1) padded to whole warps (warp-uniform hidden group)
+    static constexpr int NT = (N1 >= 64) ? DLPD_HID_NT : 128;
+    static constexpr int SMEM = (N1 * P1 + N1) * (int)sizeof(cpx);
+    static_assert(N1 % YT == 0, "level-1 y tile");
+    // grid: x = N1 / YT, y = N1 (x1), z = P
+    static DLPD_DEV void body(const Params& p, int bx, int by, int bz, char* smem) {
+        cpx* b1 = reinterpret_cast<cpx*>(smem);        // [kz1][P1]   line = c*YT + yl
+        cpx* tw1 = b1 + N1 * P1;
+        const int y0 = YT * bx, x1 = by, pair = bz;
+        DLPD_FOR_TASKS(t, N1, NT) tw1[t] = p.tw1[t];
+        {
+            const cpx* s = p.s2_1 + (long)pair * C1 * N1 * N1 * N1 + (long)x1 * N1 + y0;
+            DLPD_FOR_TASKS(t, C1 * N1 * (YT / 2), NT) {
+                const int h = t % (YT / 2), q = t / (YT / 2), kz = q % N1, c = q / N1;
+                cp_async16(b1 + kz * P1 + c * YT + 2 * h, s + (long)q * N1 * N1 + 2 * h);     // q = c*N1 + kz
+            }
+        }
+        cp_async_wait_all();
+        DLPD_SYNC();
+        fft_inv_tail<N1, NL, P1, NT>(b1, tw1, LineMul<1>());
+        fft_inv_head<N1, NL, P1, NT>(b1, tw1, LineMul<1>());
+        cpx* h1 = p.h1 + (((long)pair * N1 + x1) * N1 + y0) * N1 * H;
+        DLPD_FOR_TASKS(t, (H / JG) * VP, NT) {
+            const int v = t % VP, jg = t / VP;
+            if (v < YT * N1) {
+                const int yl = v % YT, z1 = v / YT;
+                cpx out[JG];
+                Level1Dispatch<C0, C1, H, JG, 0, YT>::run(p.filt, jg, b1 + z1 * P1 + yl, out);
+                cpx* d = h1 + ((long)yl * N1 + z1) * H + jg * JG;
+                DLPD_UNROLL
+                for (int jj = 0; jj < JG; ++jj) d[jj] = out[jj];
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// Epilogue (persistent): per 2x2 (x,y) tile and all z: inverse z-FFT of the 4 (C0+1) level-0 lines, filter
+// (DockingModels.py:28-32,79-82) with the level-1 hidden contribution from HiddenL1, clash mask (Docker.py:226,232),
+// running argmin (Docker.py:91-97).  One CTA per SM walks over tiles; the lines of the NEXT tile are copied into the
+// second shared-memory buffer (cp.async) while the current tile is transformed and scored, so no load is exposed.
+// ------------------------------------------------------------------------------------------------------
+template <int C0, int C1, int H> struct EpiParams {
+    const cpx* s2_0;              // [P][C0+1][N][N/2][N/2][2][2]   (kz', x/2, y/2, y&1, x&1); channel C0 = clash
+    const cpx* h1;                // [P][N1][N1][N1][H]
+    unsigned long long* best;     // [n_rot] packed (score_key << 32 | linear index), pre-set to ~0
+    float* score_out;             // optional [n_rot][N^3] masked score volume (module-level drop-in / tests)
+    const cpx* tw0;               // [N]
+    int n_rot, n_tiles, grid;     // tiles = P * (N/2)^2; grid = number of CTAs walking over them
+    float tau;
+    FilterW<C0, C1, H> filt;
 };
 
 template <int L_, int C0, int C1, int H> struct Epilogue {
     typedef EpiParams<C0, C1, H> Params;
-    static constexpr int L = L_, N = 2 * L_, N1 = L_, M1 = L_ / 2;
-    static constexpr int NL0 = 4 * (C0 + 1);       // level-0 lines of a 2x2 tile (even pitch: 16-byte stores)
-    static constexpr int NL1 = C1, P1 = C1 + 1;    // level-1 lines, odd pitch (conflict-free component reads)
-    static constexpr int JG = (H % 8 == 0) ? 8 : H;          // hidden units per level-1 task
-    static constexpr int N1P = (N1 + 31) / 32 * 32;          // z' padded to whole warps (warp-uniform hidden group)
-    static constexpr int NT = DLPD_EPI_NT;
-    // level-1 lines alias the level-0 buffer: they are consumed (into h1) before level 0 is loaded
-    static constexpr int B0 = (N * NL0 > N1 * P1) ? N * NL0 : N1 * P1;
-    static constexpr int SMEM = (B0 + N + N1 + N1 * H) * (int)sizeof(cpx) + 64 * 8;
-    // grid: x = N/2 (y tiles), y = N/2 (x tiles), z = P
-    static DLPD_DEV void body(const Params& p, int bx, int by, int bz, char* smem) {
-        cpx* b0 = reinterpret_cast<cpx*>(smem);        // [kz][NL0]   line = c*4 + xl*2 + yl
-        cpx* b1 = b0;                                  // [kz1][P1]   (before level 0 is loaded)
-        cpx* tw0 = b0 + B0;
-        cpx* tw1 = tw0 + N;
-        cpx* h1 = tw1 + N1;                            // [z'][H] (rotA, rotB): b1 + level-1 part of the hidden layer
-        const int y0 = 2 * bx, x0 = 2 * by, pair = bz;
+    static constexpr int L = L_, N = 2 * L_, N1 = L_, T = L_;      // T tiles per axis
+    static constexpr int NL0 = 4 * (C0 + 1);       // level-0 lines of a 2x2 tile: line = c*4 + (y&1)*2 + (x&1)
+    static constexpr int NT = (N >= 128) ? DLPD_EPI_NT : 128;
+    static constexpr int BUF = N * NL0, HB = N1 * H;
+    static constexpr int SMEM = (2 * BUF + 2 * HB + N) * (int)sizeof(cpx) + 64 * 8;
+
+    static DLPD_DEV void issue_loads(const Params& p, int tile, cpx* b0, cpx* hb) {
+        const int pair = tile / (T * T), r = tile % (T * T);            // r = (x/2) * T + (y/2)
+        const cpx* s = p.s2_0 + ((long)pair * (C0 + 1) * N * T * T + r) * 4;
+        DLPD_FOR_TASKS(t, (C0 + 1) * N * 2, NT) {
+            const int h = t & 1, q = t >> 1, kz = q % N, c = q / N;     // q = c*N + kz: 32 contiguous bytes per (c, kz)
+            cp_async16(b0 + kz * NL0 + c * 4 + 2 * h, s + (long)q * (T * T * 4) + 2 * h);
+        }
+        const cpx* hs = p.h1 + ((long)pair * T * T + r) * HB;           // level-1 column (x/2, y/2): N1*H contiguous
+        DLPD_FOR_TASKS(t, HB / 2, NT) cp_async16(hb + 2 * t, hs + 2 * t);
+    }
+
+    static DLPD_DEV void flush_best(const Params& p, int pair, unsigned long long bestA, unsigned long long bestB,
+                                    unsigned long long* red) {
         const int rotA = 2 * pair, rotB = 2 * pair + 1;
         const bool hasB = rotB < p.n_rot;
-        DLPD_FOR_TASKS(t, N, NT) tw0[t] = p.tw0[t];
-        DLPD_FOR_TASKS(t, N1, NT) tw1[t] = p.tw1[t];
-        {   // level-1 lines at (x0/2, y0/2)
-            const cpx* s = p.s2_1 + (long)pair * C1 * N1 * N1 * N1 + (long)(x0 >> 1) * N1 + (y0 >> 1);
-            DLPD_FOR_TASKS(t, C1 * N1, NT) {
-                const int kz = t % N1, c = t / N1;
-                cp_async8(b1 + kz * P1 + c, s + ((long)c * N1 + kz) * N1 * N1);
-            }
-        }
-        cp_async_wait_all();
-        DLPD_SYNC();
-        fft_inv_tail<N1, NL1, P1, NT>(b1, tw1, LineMul<1>());
-        fft_inv_head<N1, NL1, P1, NT>(b1, tw1, LineMul<1>());
-        // the first filter layer is linear, so the C1 up-sampled channels (U[c,t] = corr1[c, t//2], DockingModels.py:74-76)
-        // contribute one hidden vector per level-1 voxel, shared by the 8 level-0 voxels above it
-        DLPD_FOR_TASKS(t, (H / JG) * N1P, NT) {
-            const int z1 = t % N1P, jg = t / N1P;
-            if (z1 < N1) {
-                cpx out[JG];
-                Level1Dispatch<C0, C1, H, JG, 0>::run(p.filt, jg, b1 + z1 * P1, out);
-                DLPD_UNROLL
-                for (int jj = 0; jj < JG; ++jj) h1[z1 * H + jg * JG + jj] = out[jj];
-            }
-        }
-        DLPD_SYNC();
-        {   // level-0 lines: two complex (y0, y0+1) = 16 bytes per (channel, kz, xl)
-            const cpx* s = p.s2_0 + (long)pair * (C0 + 1) * N * N * N + (long)x0 * N + y0;
-            DLPD_FOR_TASKS(t, (C0 + 1) * N * 2, NT) {
-                const int xl = t & 1, kz = (t >> 1) % N, c = t / (2 * N);
-                cp_async16(b0 + kz * NL0 + c * 4 + xl * 2, s + (((long)c * N + kz) * N + xl) * N);   // 16-byte aligned: all terms even
-            }
-        }
-        cp_async_wait_all();
-        DLPD_SYNC();
-        fft_inv_tail<N, NL0, NL0, NT>(b0, tw0, LineMul<1>());
-        fft_inv_head<N, NL0, NL0, NT>(b0, tw0, LineMul<1>());
-
-        unsigned long long bestA = ~0ull, bestB = ~0ull;
-        DLPD_FOR_TASKS(t, 4 * N, NT) {
-            const int xy = t & 3, z = t >> 2;
-            const cpx* v0 = b0 + z * NL0 + xy;
-            const cpx* hz = h1 + (z >> 1) * H;
-            float2 h[H];                                        // (rotA, rotB) per hidden unit
-            DLPD_UNROLL
-            for (int j = 0; j < H; ++j) h[j] = hz[j];
-            DLPD_UNROLL
-            for (int c = 0; c < C0; ++c) {
-                const float2 v = v0[c * 4];
-                DLPD_UNROLL
-                for (int j = 0; j < H; ++j) h[j] = ffma2_(dup2(p.filt.W1t[c * H + j]), v, h[j]);
-            }
-            float2 sc = dup2(p.filt.b2);
-            DLPD_UNROLL
-            for (int j = 0; j < H; ++j) sc = ffma2_(dup2(p.filt.W2[j]), make_float2(fmaxf(h[j].x, 0.0f), fmaxf(h[j].y, 0.0f)), sc);
-            const cpx clash = v0[C0 * 4];
-            const float Va = clash.x < p.tau ? sc.x : 0.0f;     // (clash < tau).float() * score   (Docker.py:226,232)
-            const float Vb = clash.y < p.tau ? sc.y : 0.0f;
-            const unsigned int lin = (unsigned int)(((x0 + (xy >> 1)) * N + (y0 + (xy & 1))) * N + z);
-            const unsigned long long ka = ((unsigned long long)score_key(Va) << 32) | lin;
-            const unsigned long long kb = ((unsigned long long)score_key(Vb) << 32) | lin;
-            bestA = ka < bestA ? ka : bestA;
-            bestB = kb < bestB ? kb : bestB;
-            if (p.score_out != nullptr) {
-                p.score_out[(long)rotA * N * N * N + lin] = Va;
-                if (hasB) p.score_out[(long)rotB * N * N * N + lin] = Vb;
-            }
-        }
 #if defined(DLPD_EMU)
+        (void)red;
         if (bestA < p.best[rotA]) p.best[rotA] = bestA;
         if (hasB && bestB < p.best[rotB]) p.best[rotB] = bestB;
 #else
-        unsigned long long* red = reinterpret_cast<unsigned long long*>(h1 + N1 * H);
         bestA = block_min_u64<NT>(bestA, red);
         bestB = block_min_u64<NT>(bestB, red + 32);
         if (threadIdx.x == 0) {
@@ -593,6 +622,69 @@ template <int L_, int C0, int C1, int H> struct Epilogue {
             if (hasB) atomicMin(p.best + rotB, bestB);
         }
 #endif
+    }
+
+    // grid: x = p.grid persistent CTAs
+    static DLPD_DEV void body(const Params& p, int bx, int, int, char* smem) {
+        static_assert(HB % 2 == 0, "h1 column copied in 16-byte pieces");
+        cpx* bufs = reinterpret_cast<cpx*>(smem);      // [2][kz][NL0]
+        cpx* hbufs = bufs + 2 * BUF;                   // [2][z'][H]  (rotA, rotB): b1 + level-1 part of the hidden layer
+        cpx* tw0 = hbufs + 2 * HB;
+        unsigned long long* red = reinterpret_cast<unsigned long long*>(tw0 + N);
+        DLPD_FOR_TASKS(t, N, NT) tw0[t] = p.tw0[t];
+        if (bx < p.n_tiles) issue_loads(p, bx, bufs, hbufs);
+        cp_async_commit();
+        unsigned long long bestA = ~0ull, bestB = ~0ull;
+        int cur_pair = -1, slot = 0;
+        for (int tile = bx; tile < p.n_tiles; tile += p.grid, slot ^= 1) {
+            cp_async_wait_pending();
+            DLPD_SYNC();                               // this tile has landed; everyone is done with the other buffer
+            if (tile + p.grid < p.n_tiles) issue_loads(p, tile + p.grid, bufs + (slot ^ 1) * BUF, hbufs + (slot ^ 1) * HB);
+            cp_async_commit();
+            cpx* b0 = bufs + slot * BUF;
+            const cpx* h1 = hbufs + slot * HB;
+            const int pair = tile / (T * T), r = tile % (T * T);
+            const int x0 = 2 * (r / T), y0 = 2 * (r % T);
+            if (pair != cur_pair) {
+                if (cur_pair >= 0) flush_best(p, cur_pair, bestA, bestB, red);
+                cur_pair = pair;
+                bestA = bestB = ~0ull;
+            }
+            const int rotA = 2 * pair, rotB = 2 * pair + 1;
+            const bool hasB = rotB < p.n_rot;
+            fft_inv_tail<N, NL0, NL0, NT>(b0, tw0, LineMul<1>());
+            fft_inv_head<N, NL0, NL0, NT>(b0, tw0, LineMul<1>());
+            DLPD_FOR_TASKS(t, 4 * N, NT) {
+                const int xy = t & 3, z = t >> 2;
+                const cpx* v0 = b0 + z * NL0 + xy;
+                const cpx* hz = h1 + (z >> 1) * H;
+                float2 h[H];                                        // (rotA, rotB) per hidden unit
+                DLPD_UNROLL
+                for (int j = 0; j < H; ++j) h[j] = hz[j];
+                DLPD_UNROLL
+                for (int c = 0; c < C0; ++c) {
+                    const float2 v = v0[c * 4];
+                    DLPD_UNROLL
+                    for (int j = 0; j < H; ++j) h[j] = ffma2_(dup2(p.filt.W1t[c * H + j]), v, h[j]);
+                }
+                float2 sc = dup2(p.filt.b2);
+                DLPD_UNROLL
+                for (int j = 0; j < H; ++j) sc = ffma2_(dup2(p.filt.W2[j]), make_float2(fmaxf(h[j].x, 0.0f), fmaxf(h[j].y, 0.0f)), sc);
+                const cpx clash = v0[C0 * 4];
+                const float Va = clash.x < p.tau ? sc.x : 0.0f;     // (clash < tau).float() * score   (Docker.py:226,232)
+                const float Vb = clash.y < p.tau ? sc.y : 0.0f;
+                const unsigned int lin = (unsigned int)(((x0 + (xy & 1)) * N + (y0 + (xy >> 1))) * N + z);
+                const unsigned long long ka = ((unsigned long long)score_key(Va) << 32) | lin;
+                const unsigned long long kb = ((unsigned long long)score_key(Vb) << 32) | lin;
+                bestA = ka < bestA ? ka : bestA;
+                bestB = kb < bestB ? kb : bestB;
+                if (p.score_out != nullptr) {
+                    p.score_out[(long)rotA * N * N * N + lin] = Va;
+                    if (hasB) p.score_out[(long)rotB * N * N * N + lin] = Vb;
+                }
+            }
+        }
+        if (cur_pair >= 0) flush_best(p, cur_pair, bestA, bestB, red);
     }
 };
 

@@ -32,6 +32,14 @@
   static inline void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
   static inline void cp_async8(void* dst, const void* src) { memcpy(dst, src, 8); }
   static inline void cp_async_wait_all() {}
+  static inline void cp_async_commit() {}
+  static inline void cp_async_wait_pending() {}
+  static inline void prefetch_l2(const void*) {}
+  // teams: the emulation runs the teams of a CTA one after the other (DLPD_FOR_TEAMS), each as one "thread"
+  #define DLPD_FOR_TEAMS(g, G, TNT) for (int g = 0; g < (G); ++g)
+  #define DLPD_TEAM_TID(TNT) 0
+  static inline void named_barrier_sync(int, int) {}
+  static inline void store_cpx2(float2* dst, float2 a, float2 b) { dst[0] = a; dst[1] = b; }
   #define DLPD_UNROLL
   #define DLPD_RESTRICT
   typedef void* dlpd_stream_t;
@@ -62,7 +70,42 @@
       asm volatile("cp.async.commit_group;" ::: "memory");
       asm volatile("cp.async.wait_group 0;" ::: "memory");
   }
+  DLPD_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+  DLPD_DEV void cp_async_wait_pending() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+  DLPD_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
+  // teams: G contiguous groups of TNT threads, each working on its own sub-problem with its own named barrier
+  #define DLPD_FOR_TEAMS(g, G, TNT) for (int g = threadIdx.x / (TNT), g##_once = 1; g##_once; g##_once = 0)
+  #define DLPD_TEAM_TID(TNT) ((int)(threadIdx.x % (TNT)))
+  DLPD_DEV void named_barrier_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+  DLPD_DEV void store_cpx2(float2* dst, float2 a, float2 b) {       // 16-byte aligned destination
+      *reinterpret_cast<float4*>(dst) = make_float4(a.x, a.y, b.x, b.y);
+  }
   typedef cudaStream_t dlpd_stream_t;
+#endif
+
+// A team is the set of threads that share one "parallel for over tasks" and its barrier.
+//   CtaTeam<NT>  : the whole CTA (NT threads, __syncthreads)
+//   SubTeam<NT>  : NT threads of a larger CTA with named barrier `bar` (1..15); lets independent sub-problems of one
+//                  CTA drift apart instead of marching through every pass in lock step
+template <int NT_> struct CtaTeam {
+    static constexpr int NT = NT_;
+#if defined(DLPD_EMU)
+    DLPD_DEV int tid() const { return 0; }
+#else
+    DLPD_DEV int tid() const { return (int)threadIdx.x; }
+#endif
+    DLPD_DEV void sync() const { DLPD_SYNC(); }
+};
+template <int NT_> struct SubTeam {
+    static constexpr int NT = NT_;
+    int tid_, bar_;
+    DLPD_DEV int tid() const { return tid_; }
+    DLPD_DEV void sync() const { named_barrier_sync(bar_, NT_); }
+};
+#if defined(DLPD_EMU)
+  #define DLPD_TEAM_TASKS(tm, t, n) for (int t = 0; t < (n); ++t)
+#else
+  #define DLPD_TEAM_TASKS(tm, t, n) for (int t = (tm).tid(); t < (n); t += (tm).NT)
 #endif
 
 typedef float2 cpx;

@@ -151,7 +151,7 @@ class DockingSearch:
         return out
 
     # -- measurement hooks (bench.py) ------------------------------------------------------------------
-    PROFILE_KINDS = ("fwdz_level0", "fwdz_level1", "plane_level0", "plane_level1", "epilogue")
+    PROFILE_KINDS = ("fwdz_level0", "fwdz_level1", "plane_level0", "plane_level1", "epilogue", "hidden_level1")
 
     def profile(self, on: bool = True):
         _lib.check(self.lib, self.lib.dlpd_profile_enable(self._h, 1 if on else 0))

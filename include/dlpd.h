@@ -85,8 +85,9 @@ int dlpd_search_host(dlpd_plan* plan, const float* R_host, int n, float tau, flo
 #define DLPD_PROFILE_FWDZ1 1     /* same, level 1 */
 #define DLPD_PROFILE_PLANE0 2    /* y/x transforms, receptor multiply, inverse x/y, level 0 */
 #define DLPD_PROFILE_PLANE1 3    /* same, level 1 */
-#define DLPD_PROFILE_EPILOGUE 4  /* inverse z + filter + mask + argmin */
-#define DLPD_PROFILE_KINDS 5
+#define DLPD_PROFILE_EPILOGUE 4  /* inverse z (level 0) + filter + mask + argmin */
+#define DLPD_PROFILE_HIDDEN1 5   /* inverse z (level 1) + level-1 part of the filter's hidden layer */
+#define DLPD_PROFILE_KINDS 6
 int dlpd_profile_enable(dlpd_plan* plan, int on);
 /* Synchronises `stream`, returns accumulated milliseconds and launch counts per kind, and resets them. */
 int dlpd_profile_read(dlpd_plan* plan, double* ms, int* launches, void* stream);

@@ -22,6 +22,8 @@ for s in $STAGES; do
       timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:dlpd_kernel -c 60 --csv \
         --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --cpu-rotations 0 --rot-batch 16 --max-rot 16 \
         > $OUT/launches_run.log 2>&1 ;;
+    ubench)
+      ./build/fp32x2_rate > $OUT/ubench.log 2>&1 ;;
     ncu)
       timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
         -k "regex:Epilogue|Plane|FwdZC" -s 2 -c 5 -o $OUT/prof -f \
@@ -36,4 +38,4 @@ for s in $STAGES; do
         bench.py --gpus 2 --steps 10 --warmup 3 > $OUT/bench_2gpu.log 2>&1 ;;
   esac
 done
-tail -5 $OUT/*.log
+tail -n 5 $OUT/*.log
