@@ -343,7 +343,7 @@ static int real_spectra(int L, const float* vols, int C, cpx* s1, cpx* spec, con
     f.C = C; f.Ctot = C; f.c_out0 = 0; f.c_ext = -1; f.n_rot = 1; f.center = 0.f;
     TRY(launch_fwdz(L, f, 1, st));
     PlaneParams q;
-    q.in = s1; q.out = spec; q.spec = nullptr; q.spec_pair_stride = 0; q.tw = tw; q.C = C; q.P = 1; q.tiled = 0;
+    q.in = s1; q.out = spec; q.spec = nullptr; q.spec_pair_stride = 0; q.tw = tw; q.C = C; q.P = 1; q.tiled = 0; q.wave = 1 << 30;
     q.scale = (float)(1.0 / ((double)N * N * N));
     TRY(launch_plane(L, q, st));
     return 0;
@@ -461,9 +461,9 @@ static int search_chunk(dlpd_plan* p, const float* R, const float* clash_rot, in
     }
     PlaneParams q;
     q.in = p->s1_0; q.out = p->s2_0; q.spec = p->rspec0; q.spec_pair_stride = 0; q.tw = p->tw0; q.C = p->C0 + 1; q.P = P;
-    q.scale = 1.f; q.tiled = 1;
+    q.scale = 1.f; q.tiled = 1; q.wave = p->sm_count;
     { ProfScope ps(p, DLPD_PROFILE_PLANE0, st); TRY(launch_plane(L, q, st)); }
-    q.in = p->s1_1; q.out = p->s2_1; q.spec = p->rspec1; q.tw = p->tw1; q.C = p->C1; q.tiled = 0;
+    q.in = p->s1_1; q.out = p->s2_1; q.spec = p->rspec1; q.tw = p->tw1; q.C = p->C1; q.tiled = 0; q.wave = 2 * p->sm_count;
     { ProfScope ps(p, DLPD_PROFILE_PLANE1, st); TRY(launch_plane(L1, q, st)); }
     int rc = DLPD_EINVAL;
     {
@@ -598,7 +598,7 @@ extern "C" int dlpd_volume_correlate(const float* v1, const float* v2, float* ou
         f.C = 1; f.Ctot = 1; f.c_out0 = 0; f.c_ext = -1; f.n_rot = 1; f.center = 0.f;
         TRY(launch_fwdz(L, f, q, st));
         PlaneParams pl;
-        pl.in = w.s1; pl.out = w.spec; pl.spec = nullptr; pl.spec_pair_stride = 0; pl.tw = w.tw; pl.C = 1; pl.P = q; pl.tiled = 0;
+        pl.in = w.s1; pl.out = w.spec; pl.spec = nullptr; pl.spec_pair_stride = 0; pl.tw = w.tw; pl.C = 1; pl.P = q; pl.tiled = 0; pl.wave = 1 << 30;
         pl.scale = (float)(1.0 / ((double)N * N * N));
         TRY(launch_plane(L, pl, st));
         f.src = v2 + n3(L) * i0;

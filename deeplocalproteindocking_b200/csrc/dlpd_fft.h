@@ -30,6 +30,23 @@ DLPD_DEV cpx cmul(cpx a, cpx w) {                                       // a.x *
 }
 DLPD_DEV cpx caxpy(float s, cpx x, cpx y) { return ffma2_(make_float2(s, s), x, y); }   // s * x + y
 
+// a * e^{+2 pi i m / 16} for an index that is a compile-time constant once the butterfly loops are unrolled: the
+// trivial rotations cost nothing, the others multiply by literal constants (no table load)
+DLPD_DEV float w16_cos(int m) {
+    return m == 0 ? 1.0f : m == 1 ? 0.92387953251128674f : m == 2 ? 0.70710678118654752f : m == 3 ? 0.38268343236508977f
+         : m == 4 ? 0.0f : m == 5 ? -0.38268343236508977f : m == 6 ? -0.70710678118654752f : m == 7 ? -0.92387953251128674f
+         : m == 8 ? -1.0f : m == 9 ? -0.92387953251128674f : m == 10 ? -0.70710678118654752f : m == 11 ? -0.38268343236508977f
+         : m == 12 ? 0.0f : m == 13 ? 0.38268343236508977f : m == 14 ? 0.70710678118654752f : 0.92387953251128674f;
+}
+DLPD_DEV cpx mul_w16(cpx a, int m) {
+    m &= 15;
+    if (m == 0) return a;
+    if (m == 4) return cmul_i(a);
+    if (m == 8) return make_float2(-a.x, -a.y);
+    if (m == 12) return make_float2(a.y, -a.x);
+    return cmul(a, make_float2(w16_cos(m), w16_cos((m + 12) & 15)));       // sin(t) = cos(t - pi/2)
+}
+
 // ---- small DFTs, sign + ------------------------------------------------------------------------
 template <int R> struct Dft;
 
@@ -139,6 +156,8 @@ template <int KIND, int RA, int RB, int LEN, int NB, int TWN, int ES> struct Fft
     static constexpr bool FWD = KIND == PASS_DIF || KIND == PASS_DIF_PRUNED || KIND == PASS_MID;
     static constexpr bool INV = KIND == PASS_DIT || KIND == PASS_MID;
     static_assert(KIND != PASS_DIF_PRUNED || RA == 2, "pruned pass is the outermost radix-2 step");
+    // innermost pass (one butterfly per block, j == 0): every twiddle is a compile-time power of w_NB, NB | 16
+    static constexpr bool CONST_TW = (M2 == 1) && (16 % NB == 0);
 
     // load the RA x RB values of the task whose first element is e0 = blk*NB + j (line l at `p`) and transform them
     template <class In, class Mul>
@@ -168,14 +187,19 @@ template <int KIND, int RA, int RB, int LEN, int NB, int TWN, int ES> struct Fft
                 }
                 a[0][k] = c[0];
                 DLPD_UNROLL
-                for (int i = 1; i < RA; ++i) a[i][k] = cmul(c[i], tw[TWO * (j + k * M2) * i]);
+                for (int i = 1; i < RA; ++i) {
+                    if constexpr (CONST_TW) a[i][k] = mul_w16(c[i], (16 / NB) * k * i);
+                    else a[i][k] = cmul(c[i], tw[TWO * (j + k * M2) * i]);
+                }
             }
-            // inner DFT over k for each pa, then twiddle w_M^{j * s}
+            // inner DFT over k for each pa, then twiddle w_M^{j * s}  (j == 0 when M2 == 1: no twiddle)
             DLPD_UNROLL
             for (int i = 0; i < RA; ++i) {
                 Dft<RB>::run(a[i]);
-                DLPD_UNROLL
-                for (int k = 1; k < RB; ++k) a[i][k] = cmul(a[i][k], tw[TWI * j * k]);
+                if constexpr (M2 > 1) {
+                    DLPD_UNROLL
+                    for (int k = 1; k < RB; ++k) a[i][k] = cmul(a[i][k], tw[TWI * j * k]);
+                }
             }
         }
         if constexpr (!std::is_same<Mul, NoHook>::value) {
@@ -189,8 +213,10 @@ template <int KIND, int RA, int RB, int LEN, int NB, int TWN, int ES> struct Fft
             // inner: twiddle w_M^{j * s}, DFT over s for each pa
             DLPD_UNROLL
             for (int i = 0; i < RA; ++i) {
-                DLPD_UNROLL
-                for (int k = 1; k < RB; ++k) a[i][k] = cmul(a[i][k], tw[TWI * j * k]);
+                if constexpr (M2 > 1) {
+                    DLPD_UNROLL
+                    for (int k = 1; k < RB; ++k) a[i][k] = cmul(a[i][k], tw[TWI * j * k]);
+                }
                 Dft<RB>::run(a[i]);
             }
             // outer: twiddle w_NB^{(j + k*M2) * pa}, DFT over pa for each k
@@ -199,7 +225,10 @@ template <int KIND, int RA, int RB, int LEN, int NB, int TWN, int ES> struct Fft
                 cpx c[RA];
                 c[0] = a[0][k];
                 DLPD_UNROLL
-                for (int i = 1; i < RA; ++i) c[i] = cmul(a[i][k], tw[TWO * (j + k * M2) * i]);
+                for (int i = 1; i < RA; ++i) {
+                    if constexpr (CONST_TW) c[i] = mul_w16(a[i][k], (16 / NB) * k * i);
+                    else c[i] = cmul(a[i][k], tw[TWO * (j + k * M2) * i]);
+                }
                 Dft<RA>::run(c);
                 DLPD_UNROLL
                 for (int i = 0; i < RA; ++i) a[i][k] = c[i];

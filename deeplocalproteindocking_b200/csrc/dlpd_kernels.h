@@ -24,11 +24,14 @@
 #ifndef DLPD_EPI_NT
 #define DLPD_EPI_NT 768
 #endif
+#ifndef DLPD_EPI_NPROD
+#define DLPD_EPI_NPROD 64
+#endif
 #ifndef DLPD_HID_NT
 #define DLPD_HID_NT 512
 #endif
 #ifndef DLPD_PLANE_PREFETCH
-#define DLPD_PLANE_PREFETCH 1
+#define DLPD_PLANE_PREFETCH 2
 #endif
 #ifndef DLPD_FWDZC_NT
 #define DLPD_FWDZC_NT 256
@@ -323,6 +326,7 @@ struct PlaneParams {
     long spec_pair_stride;   // 0: all pairs share the receptor (search); C*N^3: one spectrum per "pair"
     const cpx* tw;           // [N]
     int C, P;
+    int wave;                // CTAs per wave (SM count x resident CTAs): distance of the S1 look-ahead prefetch
     int tiled;               // S2 rows in natural [x][y] order (0) or in 2x2 tiles [x/2][y/2][x&1][y&1] (1, fused search)
     float scale;
 };
@@ -364,12 +368,20 @@ template <int L_> struct Plane {
         DLPD_SYNC();
         const long plane = ((long)pair * p.C + c) * N + kz;
         const cpx* spec = p.spec ? p.spec + (long)pair * p.spec_pair_stride + ((long)c * N + kz) * N * N : nullptr;
-#if DLPD_PLANE_PREFETCH
-        // pull the receptor plane towards L2 now; it is consumed three passes later
-        if (spec) DLPD_FOR_TASKS(t, N * N / 16, NT) prefetch_l2(reinterpret_cast<const char*>(spec) + 128 * t);
-#endif
         GlobalIn<LoadS1> in{LoadS1{p.in + plane * L * L}};
         fft_fwd_head<N, L, NP, NT>(pl, tw, LineMul<1>(), in);                   // along x, columns y < L
+#if DLPD_PLANE_PREFETCH
+        // pull the receptor plane towards L2 now (behind this CTA's own S1 loads); it is consumed two passes later
+        if (spec) DLPD_FOR_TASKS(t, N * N / 16, NT) prefetch_l2(reinterpret_cast<const char*>(spec) + 128 * t);
+#endif
+#if DLPD_PLANE_PREFETCH >= 2
+        // ... and the S1 plane of the CTA that will follow this one on the SM (about one grid wave ahead)
+        if (bx + p.wave < p.P * N * p.C) {
+            const int b2 = bx + p.wave;
+            const long plane2 = ((long)(b2 % p.P) * p.C + b2 / (p.P * N)) * N + (b2 / p.P) % N;
+            DLPD_FOR_TASKS(t, L * L / 16, NT) prefetch_l2(reinterpret_cast<const char*>(p.in + plane2 * L * L) + 128 * t);
+        }
+#endif
         fft_fwd_tail<N, L, NP, NT>(pl, tw, LineMul<1>());
         fft_fwd_head<N, N, 1, NT>(pl, tw, LineMul<NP>());                       // along y, all rows kx'
         if (p.spec == nullptr) {
@@ -592,18 +604,32 @@ template <int L_, int C0, int C1, int H> struct Epilogue {
     static constexpr int L = L_, N = 2 * L_, N1 = L_, T = L_;      // T tiles per axis
     static constexpr int NL0 = 4 * (C0 + 1);       // level-0 lines of a 2x2 tile: line = c*4 + (y&1)*2 + (x&1)
     static constexpr int NT = (N >= 128) ? DLPD_EPI_NT : 128;
+    // warp specialisation: the last NPROD threads only issue the cp.async copies of the NEXT tile (each copy touches
+    // its own cache line, so issuing them is slow -- but it now overlaps the transform of the current tile instead of
+    // stalling every warp); the first NC threads transform and score
+    static constexpr int NPROD = (N >= 128) ? DLPD_EPI_NPROD : 32, NC = NT - NPROD;
     static constexpr int BUF = N * NL0, HB = N1 * H;
     static constexpr int SMEM = (2 * BUF + 2 * HB + N) * (int)sizeof(cpx) + 64 * 8;
+    static constexpr int QPT = NPROD / 2;          // (c, kz) rows covered per sweep of the producer threads
+    static_assert(HB % 2 == 0 && NPROD % 32 == 0 && NC % 32 == 0, "team shapes");
 
     static DLPD_DEV void issue_loads(const Params& p, int tile, cpx* b0, cpx* hb) {
         const int pair = tile / (T * T), r = tile % (T * T);            // r = (x/2) * T + (y/2)
         const cpx* s = p.s2_0 + ((long)pair * (C0 + 1) * N * T * T + r) * 4;
-        DLPD_FOR_TASKS(t, (C0 + 1) * N * 2, NT) {
-            const int h = t & 1, q = t >> 1, kz = q % N, c = q / N;     // q = c*N + kz: 32 contiguous bytes per (c, kz)
-            cp_async16(b0 + kz * NL0 + c * 4 + 2 * h, s + (long)q * (T * T * 4) + 2 * h);
+        DLPD_FOR_TASKS_SUB(t, NPROD, NPROD, NC) {
+            const int h = t & 1;
+            int c = (t >> 1) / N, kz = (t >> 1) % N;
+            const cpx* src = s + ((long)(t >> 1) * (T * T) * 4 + 2 * h);           // q = c*N + kz: 32 contiguous bytes per row
+            for (int q = t >> 1; q < (C0 + 1) * N; q += QPT) {
+                cp_async16(b0 + kz * NL0 + c * 4 + 2 * h, src);
+                src += (long)QPT * T * T * 4;
+                kz += QPT % N;
+                c += QPT / N;
+                if (kz >= N) { kz -= N; ++c; }
+            }
         }
         const cpx* hs = p.h1 + ((long)pair * T * T + r) * HB;           // level-1 column (x/2, y/2): N1*H contiguous
-        DLPD_FOR_TASKS(t, HB / 2, NT) cp_async16(hb + 2 * t, hs + 2 * t);
+        DLPD_FOR_TASKS_SUB(t, HB / 2, NPROD, NC) cp_async16(hb + 2 * t, hs + 2 * t);
     }
 
     static DLPD_DEV void flush_best(const Params& p, int pair, unsigned long long bestA, unsigned long long bestB,
@@ -624,9 +650,47 @@ template <int L_, int C0, int C1, int H> struct Epilogue {
 #endif
     }
 
+    // transform + score one tile (consumer team)
+    template <class TM>
+    static DLPD_DEV void score_tile(const Params& p, const TM& tm, cpx* b0, const cpx* h1, const cpx* tw0, int pair, int x0, int y0,
+                                    unsigned long long& bestA, unsigned long long& bestB) {
+        const int rotA = 2 * pair, rotB = 2 * pair + 1;
+        const bool hasB = rotB < p.n_rot;
+        team_inv_tail<N, NL0, NL0>(tm, b0, tw0, LineMul<1>());
+        team_inv_head<N, NL0, NL0>(tm, b0, tw0, LineMul<1>());
+        DLPD_TEAM_TASKS(tm, t, 4 * N) {
+            const int xy = t & 3, z = t >> 2;
+            const cpx* v0 = b0 + z * NL0 + xy;
+            const cpx* hz = h1 + (z >> 1) * H;
+            float2 h[H];                                        // (rotA, rotB) per hidden unit
+            DLPD_UNROLL
+            for (int j = 0; j < H; ++j) h[j] = hz[j];
+            DLPD_UNROLL
+            for (int c = 0; c < C0; ++c) {
+                const float2 v = v0[c * 4];
+                DLPD_UNROLL
+                for (int j = 0; j < H; ++j) h[j] = ffma2_(dup2(p.filt.W1t[c * H + j]), v, h[j]);
+            }
+            float2 sc = dup2(p.filt.b2);
+            DLPD_UNROLL
+            for (int j = 0; j < H; ++j) sc = ffma2_(dup2(p.filt.W2[j]), make_float2(fmaxf(h[j].x, 0.0f), fmaxf(h[j].y, 0.0f)), sc);
+            const cpx clash = v0[C0 * 4];
+            const float Va = clash.x < p.tau ? sc.x : 0.0f;     // (clash < tau).float() * score   (Docker.py:226,232)
+            const float Vb = clash.y < p.tau ? sc.y : 0.0f;
+            const unsigned int lin = (unsigned int)(((x0 + (xy & 1)) * N + (y0 + (xy >> 1))) * N + z);
+            const unsigned long long ka = ((unsigned long long)score_key(Va) << 32) | lin;
+            const unsigned long long kb = ((unsigned long long)score_key(Vb) << 32) | lin;
+            bestA = ka < bestA ? ka : bestA;
+            bestB = kb < bestB ? kb : bestB;
+            if (p.score_out != nullptr) {
+                p.score_out[(long)rotA * N * N * N + lin] = Va;
+                if (hasB) p.score_out[(long)rotB * N * N * N + lin] = Vb;
+            }
+        }
+    }
+
     // grid: x = p.grid persistent CTAs
     static DLPD_DEV void body(const Params& p, int bx, int, int, char* smem) {
-        static_assert(HB % 2 == 0, "h1 column copied in 16-byte pieces");
         cpx* bufs = reinterpret_cast<cpx*>(smem);      // [2][kz][NL0]
         cpx* hbufs = bufs + 2 * BUF;                   // [2][z'][H]  (rotA, rotB): b1 + level-1 part of the hidden layer
         cpx* tw0 = hbufs + 2 * HB;
@@ -634,55 +698,31 @@ template <int L_, int C0, int C1, int H> struct Epilogue {
         DLPD_FOR_TASKS(t, N, NT) tw0[t] = p.tw0[t];
         if (bx < p.n_tiles) issue_loads(p, bx, bufs, hbufs);
         cp_async_commit();
+        cp_async_wait_pending();
         unsigned long long bestA = ~0ull, bestB = ~0ull;
         int cur_pair = -1, slot = 0;
+#if defined(DLPD_EMU)
+        const CtaTeam<NC> tm;
+        const bool producer = true, consumer = true;   // one emulated thread plays both roles, copies complete at once
+#else
+        const SubTeam<NC> tm{(int)threadIdx.x, 1};
+        const bool producer = threadIdx.x >= NC, consumer = !producer;
+#endif
         for (int tile = bx; tile < p.n_tiles; tile += p.grid, slot ^= 1) {
-            cp_async_wait_pending();
             DLPD_SYNC();                               // this tile has landed; everyone is done with the other buffer
-            if (tile + p.grid < p.n_tiles) issue_loads(p, tile + p.grid, bufs + (slot ^ 1) * BUF, hbufs + (slot ^ 1) * HB);
-            cp_async_commit();
-            cpx* b0 = bufs + slot * BUF;
-            const cpx* h1 = hbufs + slot * HB;
             const int pair = tile / (T * T), r = tile % (T * T);
-            const int x0 = 2 * (r / T), y0 = 2 * (r % T);
             if (pair != cur_pair) {
                 if (cur_pair >= 0) flush_best(p, cur_pair, bestA, bestB, red);
                 cur_pair = pair;
                 bestA = bestB = ~0ull;
             }
-            const int rotA = 2 * pair, rotB = 2 * pair + 1;
-            const bool hasB = rotB < p.n_rot;
-            fft_inv_tail<N, NL0, NL0, NT>(b0, tw0, LineMul<1>());
-            fft_inv_head<N, NL0, NL0, NT>(b0, tw0, LineMul<1>());
-            DLPD_FOR_TASKS(t, 4 * N, NT) {
-                const int xy = t & 3, z = t >> 2;
-                const cpx* v0 = b0 + z * NL0 + xy;
-                const cpx* hz = h1 + (z >> 1) * H;
-                float2 h[H];                                        // (rotA, rotB) per hidden unit
-                DLPD_UNROLL
-                for (int j = 0; j < H; ++j) h[j] = hz[j];
-                DLPD_UNROLL
-                for (int c = 0; c < C0; ++c) {
-                    const float2 v = v0[c * 4];
-                    DLPD_UNROLL
-                    for (int j = 0; j < H; ++j) h[j] = ffma2_(dup2(p.filt.W1t[c * H + j]), v, h[j]);
-                }
-                float2 sc = dup2(p.filt.b2);
-                DLPD_UNROLL
-                for (int j = 0; j < H; ++j) sc = ffma2_(dup2(p.filt.W2[j]), make_float2(fmaxf(h[j].x, 0.0f), fmaxf(h[j].y, 0.0f)), sc);
-                const cpx clash = v0[C0 * 4];
-                const float Va = clash.x < p.tau ? sc.x : 0.0f;     // (clash < tau).float() * score   (Docker.py:226,232)
-                const float Vb = clash.y < p.tau ? sc.y : 0.0f;
-                const unsigned int lin = (unsigned int)(((x0 + (xy & 1)) * N + (y0 + (xy >> 1))) * N + z);
-                const unsigned long long ka = ((unsigned long long)score_key(Va) << 32) | lin;
-                const unsigned long long kb = ((unsigned long long)score_key(Vb) << 32) | lin;
-                bestA = ka < bestA ? ka : bestA;
-                bestB = kb < bestB ? kb : bestB;
-                if (p.score_out != nullptr) {
-                    p.score_out[(long)rotA * N * N * N + lin] = Va;
-                    if (hasB) p.score_out[(long)rotB * N * N * N + lin] = Vb;
-                }
+            if (producer) {
+                if (tile + p.grid < p.n_tiles) issue_loads(p, tile + p.grid, bufs + (slot ^ 1) * BUF, hbufs + (slot ^ 1) * HB);
+                cp_async_commit();
+                cp_async_wait_pending();
             }
+            if (consumer)
+                score_tile(p, tm, bufs + slot * BUF, hbufs + slot * HB, tw0, pair, 2 * (r / T), 2 * (r % T), bestA, bestB);
         }
         if (cur_pair >= 0) flush_best(p, cur_pair, bestA, bestB, red);
     }

@@ -27,6 +27,8 @@
   static inline float2 fmul2_(float2 a, float2 b) { return make_float2(a.x * b.x, a.y * b.y); }
   // one emulated "thread": tasks run in order
   #define DLPD_FOR_TASKS(t, n, NT) for (int t = 0; t < (n); ++t)
+  // tasks for the SUB threads [off, off + SUB) of the CTA only
+  #define DLPD_FOR_TASKS_SUB(t, n, SUB, off) for (int t = 0; t < (n); ++t)
   #define DLPD_SYNC() do {} while (0)
   // asynchronous global->shared copies (cp.async on the device)
   static inline void cp_async16(void* dst, const void* src) { memcpy(dst, src, 16); }
@@ -49,6 +51,7 @@
   #define DLPD_DEV __device__ __forceinline__
   #define DLPD_CE __host__ __device__ constexpr
   #define DLPD_FOR_TASKS(t, n, NT) for (int t = threadIdx.x; t < (n); t += (NT))
+  #define DLPD_FOR_TASKS_SUB(t, n, SUB, off) for (int t = (int)threadIdx.x - (off); t >= 0 && t < (n); t += (SUB))
   #define DLPD_SYNC() __syncthreads()
   #define DLPD_UNROLL _Pragma("unroll")
   #define DLPD_RESTRICT __restrict__
