@@ -30,6 +30,9 @@
 #ifndef DLPD_HID_NT
 #define DLPD_HID_NT 512
 #endif
+#ifndef DLPD_PLANE_TEAMS
+#define DLPD_PLANE_TEAMS 5
+#endif
 #ifndef DLPD_PLANE_PREFETCH
 #define DLPD_PLANE_PREFETCH 2
 #endif
@@ -336,6 +339,11 @@ template <int L_> struct Plane {
     static constexpr int L = L_, N = 2 * L_, NP = N + 1;     // odd pitch: conflict-free along both axes
     static constexpr int NT = (N >= 128) ? DLPD_PLANE_NT : ((N >= 64) ? 512 : 256);   // 800 = 5 x 160 lanes: whole passes per round, <= 80 registers
     static constexpr int SMEM = (N * NP + N) * (int)sizeof(cpx);
+    // teams (see body): only for the big plane, and only when rows, columns and threads split evenly
+    static constexpr int G = (N >= 128 && N % DLPD_PLANE_TEAMS == 0 && L_ % DLPD_PLANE_TEAMS == 0 && NT % (32 * DLPD_PLANE_TEAMS) == 0)
+                                 ? DLPD_PLANE_TEAMS : 1;
+    static constexpr int TNT = NT / G;
+    static constexpr int PFT = (G > 1) ? TNT : NT;           // threads that issue the prefetches
     struct LoadS1 {          // element e = x of column l = y
         const cpx* in;
         DLPD_DEV cpx operator()(int l, int e) const { return in[e * L + l]; }
@@ -368,20 +376,47 @@ template <int L_> struct Plane {
         DLPD_SYNC();
         const long plane = ((long)pair * p.C + c) * N + kz;
         const cpx* spec = p.spec ? p.spec + (long)pair * p.spec_pair_stride + ((long)c * N + kz) * N * N : nullptr;
+        if constexpr (G > 1) {
+            // G teams of TNT threads: each owns L/G columns (x passes) or N/G rows (y passes) and synchronises on its own
+            // named barrier between the passes of one direction, so the teams drift apart and their shared-memory and
+            // arithmetic phases overlap; only the two transpositions (x -> y -> x) need the whole CTA
+            if (spec != nullptr) {
+                DLPD_FOR_TEAMS(g, G, TNT) {
+                    const SubTeam<TNT> tm{DLPD_TEAM_TID(TNT), g + 1};
+                    GlobalIn<LoadS1> in{LoadS1{p.in + plane * L * L + g * (L / G)}};
+                    team_fwd_head<N, L / G, NP>(tm, pl + g * (L / G), tw, LineMul<1>(), in);        // along x, columns y < L
+                    if (g == 0) prefetch(p, bx, spec);
+                    team_fwd_tail<N, L / G, NP>(tm, pl + g * (L / G), tw, LineMul<1>());
+                }
+                DLPD_SYNC();
+                DLPD_FOR_TEAMS(g, G, TNT) {
+                    const SubTeam<TNT> tm{DLPD_TEAM_TID(TNT), g + 1};
+                    cpx* rows = pl + g * (N / G) * NP;
+                    PointMul<MulSpec> mul{MulSpec{spec + g * (N / G)}};
+                    team_fwd_head<N, N / G, 1>(tm, rows, tw, LineMul<NP>());                        // along y, rows kx'
+                    team_mid<N, N / G, 1>(tm, rows, tw, LineMul<NP>(), mul);                        // y tail . multiply . inverse y tail
+                    team_inv_head<N, N / G, 1>(tm, rows, tw, LineMul<NP>());                        // inverse y
+                }
+                DLPD_SYNC();
+                DLPD_FOR_TEAMS(g, G, TNT) {
+                    const SubTeam<TNT> tm{DLPD_TEAM_TID(TNT), g + 1};
+                    cpx* cols = pl + g * (N / G);
+                    team_inv_tail<N, N / G, NP>(tm, cols, tw, LineMul<1>());                        // inverse x
+                    if (p.tiled) {
+                        static_assert((N / G) % 2 == 0 && (N / 2 / LinePlan<N>::R0) % 2 == 0, "tiled pair stores");
+                        GlobalOutPair<StoreS2TiledPair> out{StoreS2TiledPair{p.out + plane * N * N + g * (N / G / 2) * 4}};
+                        team_inv_head<N, N / G, NP>(tm, cols, tw, LineMul<1>(), out);
+                    } else {
+                        GlobalOut<StoreS2> out{StoreS2{p.out + plane * N * N + g * (N / G)}};
+                        team_inv_head<N, N / G, NP>(tm, cols, tw, LineMul<1>(), out);
+                    }
+                }
+                return;
+            }
+        }
         GlobalIn<LoadS1> in{LoadS1{p.in + plane * L * L}};
         fft_fwd_head<N, L, NP, NT>(pl, tw, LineMul<1>(), in);                   // along x, columns y < L
-#if DLPD_PLANE_PREFETCH
-        // pull the receptor plane towards L2 now (behind this CTA's own S1 loads); it is consumed two passes later
-        if (spec) DLPD_FOR_TASKS(t, N * N / 16, NT) prefetch_l2(reinterpret_cast<const char*>(spec) + 128 * t);
-#endif
-#if DLPD_PLANE_PREFETCH >= 2
-        // ... and the S1 plane of the CTA that will follow this one on the SM (about one grid wave ahead)
-        if (bx + p.wave < p.P * N * p.C) {
-            const int b2 = bx + p.wave;
-            const long plane2 = ((long)(b2 % p.P) * p.C + b2 / (p.P * N)) * N + (b2 / p.P) % N;
-            DLPD_FOR_TASKS(t, L * L / 16, NT) prefetch_l2(reinterpret_cast<const char*>(p.in + plane2 * L * L) + 128 * t);
-        }
-#endif
+        prefetch(p, bx, spec);
         fft_fwd_tail<N, L, NP, NT>(pl, tw, LineMul<1>());
         fft_fwd_head<N, N, 1, NT>(pl, tw, LineMul<NP>());                       // along y, all rows kx'
         if (p.spec == nullptr) {
@@ -410,6 +445,22 @@ template <int L_> struct Plane {
             GlobalOut<StoreS2> out{StoreS2{p.out + plane * N * N}};
             fft_inv_head<N, N, NP, NT>(pl, tw, LineMul<1>(), out);
         }
+    }
+
+    // L2 look-ahead: the receptor plane (consumed two passes later) and the S1 plane of the CTA that will follow this
+    // one on the SM (about one grid wave ahead)
+    static DLPD_DEV void prefetch(const Params& p, int bx, const cpx* spec) {
+        (void)p; (void)bx; (void)spec;
+#if DLPD_PLANE_PREFETCH
+        if (spec) DLPD_FOR_TASKS_SUB(t, N * N / 16, PFT, 0) prefetch_l2(reinterpret_cast<const char*>(spec) + 128 * t);
+#endif
+#if DLPD_PLANE_PREFETCH >= 2
+        if (bx + p.wave < p.P * N * p.C) {
+            const int b2 = bx + p.wave;
+            const long plane2 = ((long)(b2 % p.P) * p.C + b2 / (p.P * N)) * N + (b2 / p.P) % N;
+            DLPD_FOR_TASKS_SUB(t, L * L / 16, PFT, 0) prefetch_l2(reinterpret_cast<const char*>(p.in + plane2 * L * L) + 128 * t);
+        }
+#endif
     }
 };
 

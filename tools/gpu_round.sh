@@ -23,10 +23,10 @@ for s in $STAGES; do
         --log-file $OUT/launches.csv python bench.py --steps 1 --warmup 1 --cpu-rotations 0 --rot-batch 16 --max-rot 16 \
         > $OUT/launches_run.log 2>&1 ;;
     ubench)
-      ./build/fp32x2_rate > $OUT/ubench.log 2>&1 ;;
+      for b in fp32x2_rate mma_tf32_rate; do ./build/$b; done > $OUT/ubench.log 2>&1 ;;
     ncu)
       timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
-        -k "regex:Epilogue|Plane|FwdZC" -s 2 -c 5 -o $OUT/prof -f \
+        -k "regex:Epilogue|Plane|FwdZC|HiddenL1" -s 2 -c 6 -o $OUT/prof -f \
         python bench.py --steps 1 --warmup 0 --cpu-rotations 0 --rot-batch 8 --max-rot 8 > $OUT/ncu_run.log 2>&1 ;;
     sanitize)
       timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -q -x -k "small or ties" \
