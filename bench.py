@@ -202,6 +202,8 @@ def main():
     ap.add_argument("--max-rot", type=int, default=32, help="rotations per internal chunk (workspace size)")
     ap.add_argument("--cpu-rotations", type=int, default=8, help="rotations of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--ref-rot-per-step", type=int, default=2)
+    ap.add_argument("--plane-mode", default="auto", choices=["auto", "single", "cluster"], help="plane-stage kernel (tuning)")
+    ap.add_argument("--epilogue-tile", type=int, default=0, choices=[0, 1, 2], help="epilogue tile shape (tuning)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -214,8 +216,10 @@ def main():
         return
 
     import torch.distributed as dist
-    from deeplocalproteindocking_b200 import DockingSearch, rotations
+    from deeplocalproteindocking_b200 import DockingSearch, rotations, set_option
     from deeplocalproteindocking_b200 import distributed as D
+    set_option("plane_mode", args.plane_mode)
+    set_option("epilogue_tile", args.epilogue_tile)
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)

@@ -26,15 +26,21 @@ SIGNATURES = {
     "dlpd_set_ligand": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p]),
     "dlpd_set_filter": (c_int, [c_void_p, POINTER(c_float), POINTER(c_float), POINTER(c_float), POINTER(c_float)]),
     "dlpd_search": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "dlpd_search_candidates": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_int,
+                                       c_void_p, c_void_p]),
+    "dlpd_search_prerotated": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "dlpd_search_host": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
     "dlpd_profile_enable": (c_int, [c_void_p, c_int]),
     "dlpd_profile_read": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_int), c_void_p]),
     "dlpd_launch_count": (c_longlong, []),
+    "dlpd_set_option": (c_int, [c_int, c_int]),
     "dlpd_volume_rotate": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dlpd_volume_correlate": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),
 }
 
 CENTER_MODES = {"box": 0, "grid": 1}
+OPTIONS = {"plane_mode": 1, "epilogue_tile": 2}                  # DLPD_OPT_* of include/dlpd.h
+PLANE_MODES = {"auto": 0, "single": 1, "cluster": 2}
 
 
 class DlpdError(RuntimeError):
@@ -69,3 +75,12 @@ def get_lib() -> ctypes.CDLL:
                 "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
         _lib = bind_signatures(ctypes.CDLL(LIB_PATH))
     return _lib
+
+
+def set_option(name: str, value) -> None:
+    """Process-wide kernel selection switches (`dlpd_set_option`): plane_mode = auto | single | cluster,
+    epilogue_tile = 0 (auto) | 1 | 2.  Tuning and tests only; the defaults are what ships."""
+    lib = get_lib()
+    if name == "plane_mode" and isinstance(value, str):
+        value = PLANE_MODES[value]
+    check(lib, lib.dlpd_set_option(OPTIONS[name], int(value)))

@@ -1,8 +1,11 @@
 // Host side of libdlpd.so: the C ABI declared in include/dlpd.h, kernel launchers and workspace management.
 // Built by nvcc for sm_100a (product).  The same file compiles with `g++ -x c++ -DDLPD_EMU` into the
 // host emulation used by tests/emu (TEST INFRASTRUCTURE: never loaded by the package).
-#include "dlpd_kernels.h"
 #include "../../include/dlpd.h"
+#if !defined(DLPD_EMU)
+#include <cooperative_groups.h>
+#endif
+#include "dlpd_kernels.h"
 
 #include <stdio.h>
 #include <stdlib.h>
@@ -40,6 +43,20 @@ template <class K> static int launch(dim3 g, const typename K::Params& p, dlpd_s
     for (unsigned z = 0; z < g.z; ++z)
         for (unsigned y = 0; y < g.y; ++y)
             for (unsigned x = 0; x < g.x; ++x) K::body(p, (int)x, (int)y, (int)z, smem.data());
+    ++g_launches;
+    return 0;
+}
+// thread-block clusters: the CL CTAs of a cluster run phase A one after the other, then phase B with every CTA's
+// shared memory visible (distributed shared memory on the device)
+template <class K> static int launch_cluster(unsigned clusters, const typename K::Params& p, dlpd_stream_t) {
+    std::vector<std::vector<char> > smem(K::CL, std::vector<char>((size_t)K::SMEM + 16));
+    cpx* slabs[K::CL];
+    for (int r = 0; r < K::CL; ++r) slabs[r] = reinterpret_cast<cpx*>(smem[r].data());
+    for (unsigned cid = 0; cid < clusters; ++cid) {
+        for (int r = 0; r < K::CL; ++r) K::phase_a(p, (int)cid, r, smem[r].data());
+        if (K::exchanges(p))
+            for (int r = 0; r < K::CL; ++r) K::phase_b(p, (int)cid, r, slabs, smem[r].data());
+    }
     ++g_launches;
     return 0;
 }
@@ -87,6 +104,49 @@ template <class K> static int launch(dim3 g, const typename K::Params& p, dlpd_s
     ++g_launches;
     return 0;
 }
+
+// kernels that span a thread-block cluster of K::CL CTAs (distributed shared memory)
+template <class K>
+__global__ void __launch_bounds__(K::NT) dlpd_cluster_kernel(const __grid_constant__ typename K::Params p) {
+    extern __shared__ __align__(16) char smem[];
+    namespace cg = cooperative_groups;
+    cg::cluster_group cl = cg::this_cluster();
+    const int rank = (int)cl.block_rank(), cid = (int)(blockIdx.x / K::CL);
+    K::phase_a(p, cid, rank, smem);
+    if (K::exchanges(p)) {                 // uniform over the cluster
+        cl.sync();
+        cpx* slabs[K::CL];
+#pragma unroll
+        for (int r = 0; r < K::CL; ++r) slabs[r] = cl.map_shared_rank(reinterpret_cast<cpx*>(smem), r);
+        K::phase_b(p, cid, rank, slabs, smem);
+        cl.sync();                         // nobody leaves while its shared memory is still being read
+    }
+}
+template <class K> static int launch_cluster(unsigned clusters, const typename K::Params& p, dlpd_stream_t st) {
+    static bool configured[64] = {};
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (dev < 64 && !configured[dev]) {
+        if (K::SMEM > 48 * 1024)
+            CU(cudaFuncSetAttribute(dlpd_cluster_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+        configured[dev] = true;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(clusters * K::CL);
+    cfg.blockDim = dim3(K::NT);
+    cfg.dynamicSmemBytes = K::SMEM;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = K::CL;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    CU(cudaLaunchKernelEx(&cfg, dlpd_cluster_kernel<K>, p));
+    ++g_launches;
+    return 0;
+}
 #endif
 
 #define TRY(call)                  \
@@ -99,17 +159,18 @@ template <class K> static int launch(dim3 g, const typename K::Params& p, dlpd_s
 // compiled sizes
 // ------------------------------------------------------------------------------------------------------
 template <int L> struct Tile {
-    static constexpr int FWD_YT = (L > 40) ? 40 : L;      // y lines per FwdZ CTA
+    static constexpr int FWD_YT = (L <= 40) ? L : ((L % 40 == 0) ? 40 : 32);      // y lines per FwdZ CTA
     static constexpr int INV_YT = ((2 * L) % 8 == 0) ? 8 : (((2 * L) % 4 == 0) ? 4 : 2);
     static constexpr int CL_YT = (L % 8 == 0) ? 8 : ((L % 4 == 0) ? 4 : 2);   // y lines per FwdZC CTA
     static constexpr int CL_CG = 8;                                           // channels per FwdZC CTA
 };
 
 // box sizes the single-level kernels are compiled for
-#define DLPD_OP_SIZES(X) X(4) X(8) X(10) X(16) X(20) X(40) X(80)
+#define DLPD_OP_SIZES(X) X(4) X(8) X(10) X(16) X(20) X(40) X(64) X(80) X(128)
 // (L, C0, C1, H) the fused search is compiled for
 #define DLPD_SEARCH_CONFIGS(X) \
-    X(8, 4, 6, 5) X(16, 4, 6, 5) X(20, 4, 6, 5) X(8, 16, 32, 24) X(16, 16, 32, 24) X(20, 16, 32, 24) X(80, 16, 32, 24)
+    X(8, 4, 6, 5) X(16, 4, 6, 5) X(20, 4, 6, 5) X(8, 16, 32, 24) X(16, 16, 32, 24) X(20, 16, 32, 24) X(80, 16, 32, 24) \
+    X(128, 16, 32, 24)
 
 static bool op_size_ok(int L) {
     switch (L) {
@@ -145,8 +206,23 @@ template <int L> static int launch_fwdzc_t(const FwdZCParams& p, int P, dlpd_str
     typedef FwdZC<L, Tile<L>::CL_CG, Tile<L>::CL_YT> K;
     return launch<K>(dim3(L * K::YTILES, p.C / K::CG, P), p, st);
 }
+// Plane<L> needs the whole N x N plane in one SM's shared memory; PlaneX<L, 4> spreads it over a cluster of 4 CTAs.
+static constexpr int SMEM_MAX = 227 * 1024;
+static int g_plane_mode = DLPD_PLANE_AUTO;
+static int g_epi_tile = 0;               // 0 = automatic, 1 / 2 = force 2x1 / 2x2 tiles in the epilogue
+template <int L> struct HasPlaneX { static constexpr bool value = (L == 8 || L == 16 || L == 20 || L == 40 || L == 64 || L == 80 || L == 128); };
+template <int L> struct HasPlane { static constexpr bool value = ((2 * L) * (2 * L + 1) + 2 * L) * 8 <= SMEM_MAX; };
 template <int L> static int launch_plane_t(const PlaneParams& p, dlpd_stream_t st) {
-    return launch<Plane<L> >(dim3((unsigned)(p.P * 2 * L * p.C)), p, st);
+    bool cluster = !HasPlane<L>::value;
+    if (g_plane_mode == DLPD_PLANE_CLUSTER && HasPlaneX<L>::value) cluster = true;
+    if (g_plane_mode == DLPD_PLANE_SINGLE) cluster = false;
+    if (cluster) {
+        if constexpr (HasPlaneX<L>::value) return launch_cluster<PlaneX<L, 4> >((unsigned)(p.P * 2 * L * p.C), p, st);
+        else return fail(DLPD_EINVAL, "the cluster plane kernel is not compiled for this box size");
+    } else {
+        if constexpr (HasPlane<L>::value) return launch<Plane<L> >(dim3((unsigned)(p.P * 2 * L * p.C)), p, st);
+        else return fail(DLPD_EINVAL, "the plane of this box size does not fit one SM: use the cluster plane kernel");
+    }
 }
 template <int L> static int launch_invz_t(const InvZParams& p, int Q, dlpd_stream_t st) {
     typedef InvZStore<L, Tile<L>::INV_YT> K;
@@ -340,7 +416,7 @@ static int real_spectra(int L, const float* vols, int C, cpx* s1, cpx* spec, con
     const int N = 2 * L;
     FwdZParams f;
     f.src = vols; f.src_pair_stride = 0; f.src_rot = nullptr; f.R = nullptr; f.out = s1; f.tw = tw;
-    f.C = C; f.Ctot = C; f.c_out0 = 0; f.c_ext = -1; f.n_rot = 1; f.center = 0.f;
+    f.C = C; f.Ctot = C; f.c_out0 = 0; f.c_ext = -1; f.ext_all = 0; f.n_rot = 1; f.center = 0.f;
     TRY(launch_fwdz(L, f, 1, st));
     PlaneParams q;
     q.in = s1; q.out = spec; q.spec = nullptr; q.spec_pair_stride = 0; q.tw = tw; q.C = C; q.P = 1; q.tiled = 0; q.wave = 1 << 30;
@@ -410,30 +486,53 @@ template <int L, int C0, int C1, int H> static int launch_hidden(dlpd_plan* p, i
     return launch<K>(dim3(K::N1 / K::YT, K::N1, P), e, st);
 }
 
+struct CandArgs {
+    int* cand = nullptr;
+    unsigned int* count = nullptr;
+    unsigned int cap = 0, key = 0;
+    int rot_base = 0;
+};
+template <int L, int C0, int C1, int H, int TY>
+static int launch_epilogue_t(dlpd_plan* p, int n, int P, float tau, float* out_scores, const CandArgs& ca, dlpd_stream_t st) {
+    typedef Epilogue<L, C0, C1, H, TY> K;
+    if constexpr (K::SMEM <= SMEM_MAX) {
+        typename K::Params e;
+        e.s2_0 = p->s2_0; e.h1 = p->h1; e.best = p->best; e.score_out = out_scores;
+        e.tw0 = p->tw0; e.n_rot = n; e.tau = tau;
+        e.cand = ca.cand; e.cand_count = ca.count; e.cand_cap = ca.cap; e.cand_key = ca.key; e.rot_base = ca.rot_base;
+        e.n_tiles = P * K::TILES;
+        e.grid = e.n_tiles < p->sm_count ? e.n_tiles : p->sm_count;
+        fill_filter(p, e.filt);
+        return launch<K>(dim3(e.grid), e, st);
+    } else {
+        return fail(DLPD_EINVAL, "epilogue tile does not fit shared memory");
+    }
+}
 template <int L, int C0, int C1, int H>
-static int launch_epilogue(dlpd_plan* p, int n, int P, float tau, float* out_scores, dlpd_stream_t st) {
-    typedef Epilogue<L, C0, C1, H> K;
-    typename K::Params e;
-    e.s2_0 = p->s2_0; e.h1 = p->h1; e.best = p->best; e.score_out = out_scores;
-    e.tw0 = p->tw0; e.n_rot = n; e.tau = tau;
-    e.n_tiles = P * L * L;
-    e.grid = e.n_tiles < p->sm_count ? e.n_tiles : p->sm_count;
-    fill_filter(p, e.filt);
-    return launch<K>(dim3(e.grid), e, st);
+static int launch_epilogue(dlpd_plan* p, int n, int P, float tau, float* out_scores, const CandArgs& ca, dlpd_stream_t st) {
+    const bool fits2 = Epilogue<L, C0, C1, H, 2>::SMEM <= SMEM_MAX;
+    const int ty = g_epi_tile ? g_epi_tile : (fits2 ? 2 : 1);
+    return ty == 2 ? launch_epilogue_t<L, C0, C1, H, 2>(p, n, P, tau, out_scores, ca, st)
+                   : launch_epilogue_t<L, C0, C1, H, 1>(p, n, P, tau, out_scores, ca, st);
 }
 
 // one chunk of n <= max_rot rotations
-static int search_chunk(dlpd_plan* p, const float* R, const float* clash_rot, int n, float tau, float* out_best,
-                        float* out_scores, dlpd_stream_t st) {
+// lig0_rot / lig1_rot != nullptr: every ligand volume arrives already rotated, one set per rotation (dockE3)
+static int search_chunk(dlpd_plan* p, const float* R, const float* clash_rot, const float* lig0_rot, const float* lig1_rot,
+                        int n, float tau, float* out_best, float* out_scores, const CandArgs& ca, dlpd_stream_t st) {
     const int L = p->L, L1 = L / 2, N = 2 * L;
     const int P = (n + 1) / 2;
     TRY(rt_memset(p->best, 0xff, sizeof(unsigned long long) * n, st));
     {   // level 0: C0 rotated feature channels + the clash channel (rotated here, or supplied already rotated)
         ProfScope ps(p, DLPD_PROFILE_FWDZ0, st);
         FwdZParams f;
-        f.src_pair_stride = 0; f.R = R; f.out = p->s1_0; f.tw = p->tw0; f.Ctot = p->C0 + 1; f.n_rot = n;
+        f.src_pair_stride = 0; f.R = R; f.out = p->s1_0; f.tw = p->tw0; f.Ctot = p->C0 + 1; f.n_rot = n; f.ext_all = 0;
         f.center = center_of(L, p->center_mode);
-        if (channel_last_ok(p->C0)) {
+        if (lig0_rot) {
+            f.src = p->lig0; f.src_rot = lig0_rot; f.C = p->C0; f.c_out0 = 0; f.c_ext = -1; f.ext_all = 1;
+            TRY(launch_fwdz(L, f, P, st));
+            f.ext_all = 0;
+        } else if (channel_last_ok(p->C0)) {
             FwdZCParams g;
             g.src = p->lig0_cl; g.R = R; g.out = p->s1_0; g.tw = p->tw0; g.C = p->C0; g.Ctot = p->C0 + 1; g.n_rot = n;
             g.center = f.center;
@@ -447,7 +546,12 @@ static int search_chunk(dlpd_plan* p, const float* R, const float* clash_rot, in
     }
     {   // level 1
         ProfScope ps(p, DLPD_PROFILE_FWDZ1, st);
-        if (channel_last_ok(p->C1)) {
+        if (lig1_rot) {
+            FwdZParams f;
+            f.src = p->lig1; f.src_pair_stride = 0; f.src_rot = lig1_rot; f.R = R; f.out = p->s1_1; f.tw = p->tw1;
+            f.C = p->C1; f.Ctot = p->C1; f.c_out0 = 0; f.c_ext = -1; f.ext_all = 1; f.n_rot = n; f.center = center_of(L1, p->center_mode);
+            TRY(launch_fwdz(L1, f, P, st));
+        } else if (channel_last_ok(p->C1)) {
             FwdZCParams g;
             g.src = p->lig1_cl; g.R = R; g.out = p->s1_1; g.tw = p->tw1; g.C = p->C1; g.Ctot = p->C1; g.n_rot = n;
             g.center = center_of(L1, p->center_mode);
@@ -455,7 +559,7 @@ static int search_chunk(dlpd_plan* p, const float* R, const float* clash_rot, in
         } else {
             FwdZParams f;
             f.src = p->lig1; f.src_pair_stride = 0; f.src_rot = nullptr; f.R = R; f.out = p->s1_1; f.tw = p->tw1;
-            f.C = p->C1; f.Ctot = p->C1; f.c_out0 = 0; f.c_ext = -1; f.n_rot = n; f.center = center_of(L1, p->center_mode);
+            f.C = p->C1; f.Ctot = p->C1; f.c_out0 = 0; f.c_ext = -1; f.ext_all = 0; f.n_rot = n; f.center = center_of(L1, p->center_mode);
             TRY(launch_fwdz(L1, f, P, st));
         }
     }
@@ -476,7 +580,7 @@ static int search_chunk(dlpd_plan* p, const float* R, const float* clash_rot, in
     rc = DLPD_EINVAL;
     {
         ProfScope ps(p, DLPD_PROFILE_EPILOGUE, st);
-#define X(L_, A, B, C) if (p->L == L_ && p->C0 == A && p->C1 == B && p->H == C) rc = launch_epilogue<L_, A, B, C>(p, n, P, tau, out_scores, st);
+#define X(L_, A, B, C) if (p->L == L_ && p->C0 == A && p->C1 == B && p->H == C) rc = launch_epilogue<L_, A, B, C>(p, n, P, tau, out_scores, ca, st);
         DLPD_SEARCH_CONFIGS(X)
 #undef X
     }
@@ -487,10 +591,11 @@ static int search_chunk(dlpd_plan* p, const float* R, const float* clash_rot, in
     return 0;
 }
 
-extern "C" int dlpd_search(dlpd_plan* p, const float* R, const float* lig_clash_rot, int n, float tau, float* out_best,
-                           float* out_scores, void* stream) {
-    if (!p || !R || !out_best || n < 1) return fail(DLPD_EINVAL, "dlpd_search: bad argument");
-    if (!p->has_receptor || !p->has_ligand || !p->has_filter)
+static int search_all(dlpd_plan* p, const float* R, const float* lig_clash_rot, const float* lig0_rot, const float* lig1_rot,
+                      int n, float tau, float* out_best, float* out_scores, CandArgs ca, void* stream) {
+    const bool prerot = lig0_rot != nullptr;
+    if (!p || !out_best || n < 1 || (!prerot && !R)) return fail(DLPD_EINVAL, "dlpd_search: bad argument");
+    if (!p->has_receptor || !p->has_filter || (!prerot && !p->has_ligand))
         return fail(DLPD_ESTATE, "dlpd_search: set_receptor, set_ligand and set_filter must be called first");
     if (!lig_clash_rot && !p->lig_has_clash)
         return fail(DLPD_ESTATE, "dlpd_search: no ligand clash volume (pass one to set_ligand or per rotation)");
@@ -499,10 +604,35 @@ extern "C" int dlpd_search(dlpd_plan* p, const float* R, const float* lig_clash_
     const size_t L3 = n3(p->L), N3 = n3(2 * p->L);
     for (int i0 = 0; i0 < n; i0 += p->max_rot) {
         const int m = n - i0 < p->max_rot ? n - i0 : p->max_rot;
-        TRY(search_chunk(p, R + 9 * (size_t)i0, lig_clash_rot ? lig_clash_rot + L3 * i0 : nullptr, m, tau,
-                         out_best + 4 * (size_t)i0, out_scores ? out_scores + N3 * i0 : nullptr, st));
+        ca.rot_base = i0;
+        const size_t L13 = n3(p->L / 2);
+        TRY(search_chunk(p, R ? R + 9 * (size_t)i0 : nullptr, lig_clash_rot ? lig_clash_rot + L3 * i0 : nullptr,
+                         prerot ? lig0_rot + L3 * p->C0 * i0 : nullptr, prerot ? lig1_rot + L13 * p->C1 * i0 : nullptr, m, tau,
+                         out_best + 4 * (size_t)i0, out_scores ? out_scores + N3 * i0 : nullptr, ca, st));
     }
     return 0;
+}
+
+extern "C" int dlpd_search(dlpd_plan* p, const float* R, const float* lig_clash_rot, int n, float tau, float* out_best,
+                           float* out_scores, void* stream) {
+    return search_all(p, R, lig_clash_rot, nullptr, nullptr, n, tau, out_best, out_scores, CandArgs(), stream);
+}
+
+extern "C" int dlpd_search_prerotated(dlpd_plan* p, const float* lig0_rot, const float* lig1_rot, const float* lig_clash_rot,
+                                      int n, float tau, float* out_best, float* out_scores, void* stream) {
+    if (!lig0_rot || !lig1_rot || !lig_clash_rot) return fail(DLPD_EINVAL, "dlpd_search_prerotated: NULL volume pointer");
+    return search_all(p, nullptr, lig_clash_rot, lig0_rot, lig1_rot, n, tau, out_best, out_scores, CandArgs(), stream);
+}
+
+extern "C" int dlpd_search_candidates(dlpd_plan* p, const float* R, const float* lig_clash_rot, int n, float tau,
+                                      float score_max, float* out_best, int* cand, int cand_cap, unsigned int* cand_count,
+                                      void* stream) {
+    if (!cand || !cand_count || cand_cap < 1) return fail(DLPD_EINVAL, "dlpd_search_candidates: bad candidate buffer");
+    if (score_max != score_max) return fail(DLPD_EINVAL, "dlpd_search_candidates: score_max is NaN");
+    TRY(rt_memset(cand_count, 0, sizeof(unsigned int), (dlpd_stream_t)stream));
+    CandArgs ca;
+    ca.cand = cand; ca.count = cand_count; ca.cap = (unsigned int)cand_cap; ca.key = score_key(score_max);
+    return search_all(p, R, lig_clash_rot, nullptr, nullptr, n, tau, out_best, nullptr, ca, stream);
 }
 
 extern "C" int dlpd_search_host(dlpd_plan* p, const float* R_host, int n, float tau, float* best_host, void* stream) {
@@ -529,6 +659,20 @@ extern "C" int dlpd_search_host(dlpd_plan* p, const float* R_host, int n, float 
 }
 
 extern "C" long long dlpd_launch_count(void) { return g_launches; }
+
+extern "C" int dlpd_set_option(int key, int value) {
+    switch (key) {
+        case DLPD_OPT_PLANE_MODE:
+            if (value < DLPD_PLANE_AUTO || value > DLPD_PLANE_CLUSTER) return fail(DLPD_EINVAL, "bad plane mode");
+            g_plane_mode = value;
+            return 0;
+        case DLPD_OPT_EPILOGUE_TILE:
+            if (value < 0 || value > 2) return fail(DLPD_EINVAL, "epilogue tile must be 0 (auto), 1 (2x1) or 2 (2x2)");
+            g_epi_tile = value;
+            return 0;
+    }
+    return fail(DLPD_EINVAL, "unknown option");
+}
 
 extern "C" int dlpd_profile_enable(dlpd_plan* p, int on) {
     if (!p) return fail(DLPD_EINVAL, "dlpd_profile_enable: NULL plan");
@@ -595,7 +739,7 @@ extern "C" int dlpd_volume_correlate(const float* v1, const float* v2, float* ou
         const int q = items - i0 < w.Q ? items - i0 : w.Q;
         FwdZParams f;
         f.src = v1 + n3(L) * i0; f.src_pair_stride = (long)n3(L); f.src_rot = nullptr; f.R = nullptr; f.out = w.s1; f.tw = w.tw;
-        f.C = 1; f.Ctot = 1; f.c_out0 = 0; f.c_ext = -1; f.n_rot = 1; f.center = 0.f;
+        f.C = 1; f.Ctot = 1; f.c_out0 = 0; f.c_ext = -1; f.ext_all = 0; f.n_rot = 1; f.center = 0.f;
         TRY(launch_fwdz(L, f, q, st));
         PlaneParams pl;
         pl.in = w.s1; pl.out = w.spec; pl.spec = nullptr; pl.spec_pair_stride = 0; pl.tw = w.tw; pl.C = 1; pl.P = q; pl.tiled = 0; pl.wave = 1 << 30;

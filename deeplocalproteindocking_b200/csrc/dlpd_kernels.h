@@ -134,13 +134,16 @@ struct RotateVolume {
 struct FwdZParams {
     const float* src;        // [.. pair_stride ..][C][L^3] source volumes
     long src_pair_stride;    // 0: every pair reads the same volumes (search); C*L^3: one real volume per "pair"
-    const float* src_rot;    // optional [n_rot][L^3]: volumes that are ALREADY rotated, used for channel c_ext
+    const float* src_rot;    // optional [n_rot][C_ext][L^3]: volumes that are ALREADY rotated -- for channel c_ext only
+                             // (C_ext = 1: re-projected clash volume, Docker.py:221-224) or, with ext_all, for every
+                             // channel of the launch (C_ext = C: dockE3 re-runs the representation per rotation, Docker.py:165-169)
     const float* R;          // [n_rot][9] rotation matrices, or nullptr: identity, imaginary part = 0
     cpx* out;                // S1 [P][Ctot][N][L][L]
     const cpx* tw;           // [N] e^{+2 pi i k/N}
     int C;                   // channels of this launch (grid.y)
     int Ctot, c_out0;        // channel count of S1 and index of this launch's first channel in it
     int c_ext, n_rot;
+    int ext_all;
     float center;
 };
 
@@ -157,7 +160,8 @@ template <int L_, int YT_> struct FwdZ {
         const int x = bx / YTILES, y0 = (bx % YTILES) * YT, c = by, pair = bz;
         const int rotA = 2 * pair, rotB = 2 * pair + 1;
         const bool hasB = rotB < p.n_rot;
-        const bool ext = (p.src_rot != nullptr) && (c == p.c_ext);
+        const bool ext = (p.src_rot != nullptr) && (p.ext_all || c == p.c_ext);
+        const long ext_c = p.ext_all ? p.C : 1, ext_i = p.ext_all ? c : 0;
         const bool rotate = (p.R != nullptr) && !ext;
         constexpr int L3 = L * L * L;
         float ra[9], rb[9];
@@ -180,8 +184,8 @@ template <int L_, int YT_> struct FwdZ {
                     b = trilinear_zero(src, L, sx, sy, sz);
                 }
             } else if (ext) {
-                a = __ldg(p.src_rot + (long)rotA * L3 + idx);
-                if (hasB) b = __ldg(p.src_rot + (long)rotB * L3 + idx);
+                a = __ldg(p.src_rot + ((long)rotA * ext_c + ext_i) * L3 + idx);
+                if (hasB) b = __ldg(p.src_rot + ((long)rotB * ext_c + ext_i) * L3 + idx);
             } else {
                 a = __ldg(src + idx);                          // plain real volume (receptor / standalone operator)
             }
@@ -465,6 +469,136 @@ template <int L_> struct Plane {
 };
 
 // ------------------------------------------------------------------------------------------------------
+// PlaneX: the same (c, kz') plane pipeline spread over a thread-block CLUSTER of CL CTAs, for planes that do not fit
+// one SM's shared memory (N = 256: 526 KB) or that should leave room for several resident CTAs per SM (N = 160).
+//
+// The x transform is split by its outermost radix-CL step.  With kx = q + CL k2 (q < CL, k2 < M = N / CL):
+//     forward:  X[q + CL k2] = FFT_M( y_q )[k2],   y_q[j] = w_N^{q j} sum_{m < CL/2} x[j + m M] e^{2 pi i q m / CL}
+//               (the zero-padded upper half drops out of the sum) -- every slab q needs only the INPUT column, so the
+//               forward direction has no exchange at all: CTA q folds the S1 plane into its own M rows;
+//     inverse:  A_q = IFFT_M(slab q) is local as well; only the last step
+//               out[j + m M] = sum_q e^{2 pi i q m / CL} (w_N^{q j} A_q[j])
+//               mixes the slabs.  Each CTA gathers its share of rows j from all CL slabs through distributed shared
+//               memory (one coalesced read per value), applies the radix-CL butterfly and stores S2 straight to global.
+// Between the two, the y transforms, the receptor multiply and the inverse y transform work on rows, i.e. inside a slab.
+// The frequency order along kx' differs from Plane<L>'s; it is private to this kernel (the receptor spectrum is
+// produced by the same code in spectrum mode).
+// ------------------------------------------------------------------------------------------------------
+template <int M> struct XPlan;            // M = XA * XB: two single-radix shared-memory passes
+#define DLPD_XPLAN(M_, A_, B_)                                            \
+    template <> struct XPlan<M_> {                                        \
+        static constexpr int XA = A_, XB = B_;                            \
+        static_assert(A_ * B_ == M_, "bad x factorisation");              \
+    };
+DLPD_XPLAN(4, 4, 1)
+DLPD_XPLAN(8, 8, 1)
+DLPD_XPLAN(10, 5, 2)
+DLPD_XPLAN(20, 5, 4)
+DLPD_XPLAN(32, 8, 4)
+DLPD_XPLAN(40, 5, 8)
+DLPD_XPLAN(64, 8, 8)
+
+#ifndef DLPD_PLANEX_NT
+#define DLPD_PLANEX_NT 256
+#endif
+#ifndef DLPD_PLANEX_NT_BIG
+#define DLPD_PLANEX_NT_BIG 512
+#endif
+
+template <int L_, int CL_> struct PlaneX {
+    typedef PlaneParams Params;
+    static constexpr int L = L_, N = 2 * L_, CL = CL_, M = N / CL_, NP = N + 1;
+    static constexpr int XA = XPlan<M>::XA, XB = XPlan<M>::XB;
+    static constexpr int NT = (N > 160) ? DLPD_PLANEX_NT_BIG : ((N >= 128) ? DLPD_PLANEX_NT : 128);
+    static constexpr int SMEM = (M * NP + N) * (int)sizeof(cpx);
+    static_assert(CL_ == 4 && N % CL_ == 0 && M % 2 == 0 && N % XB == 0, "cluster shape");
+
+    struct FoldS1 {          // element e = j of column l = y of slab q: w_N^{q j} (x[j] + i^q x[j + M])
+        const cpx* in;       // S1 plane [x < L][y < L]
+        const cpx* tw;
+        int q;
+        DLPD_DEV cpx operator()(int l, int e) const {
+            const cpx a = in[e * L + l], b = in[(e + M) * L + l];
+            const cpx ib = q == 0 ? b : q == 1 ? cmul_i(b) : q == 2 ? make_float2(-b.x, -b.y) : make_float2(b.y, -b.x);
+            const cpx v = cadd(a, ib);
+            return q == 0 ? v : cmul(v, tw[e * q]);
+        }
+    };
+    struct MulSpec {         // element e = ky' of local row l (global row kx' = q M + l); spectrum stored [ky'][kx']
+        const cpx* spec;
+        DLPD_DEV cpx operator()(int l, int e) const { return __ldg(spec + e * N + l); }
+    };
+
+    static DLPD_DEV bool exchanges(const Params& p) { return p.spec != nullptr; }
+
+    // everything up to the partial inverse along x: local to the slab
+    static DLPD_DEV void phase_a(const Params& p, int cid, int q, char* smem) {
+        cpx* pl = reinterpret_cast<cpx*>(smem);        // [M local rows kx'][y], pitch NP
+        cpx* tw = pl + M * NP;
+        const int pair = cid % p.P, kz = (cid / p.P) % N, c = cid / (p.P * N);
+        DLPD_FOR_TASKS(t, N, NT) tw[t] = p.tw[t];
+        DLPD_SYNC();
+        const long plane = ((long)pair * p.C + c) * N + kz;
+        // forward x on the columns y < L: fold from global, then the M-point transform
+        GlobalIn<FoldS1> in{FoldS1{p.in + plane * L * L, tw, q}};
+        fft_pass<PASS_DIF, XA, 1, L, M, M, N, NP, NT>(pl, tw, LineMul<1>(), in);
+        if constexpr (XB > 1) fft_pass<PASS_DIF, XB, 1, L, M, XB, N, NP, NT>(pl, tw, LineMul<1>());
+        fft_fwd_head<N, M, 1, NT>(pl, tw, LineMul<NP>());                       // along y, my rows
+        if (p.spec == nullptr) {
+            fft_fwd_tail<N, M, 1, NT>(pl, tw, LineMul<NP>());
+            cpx* out = p.out + plane * N * N + q * M;
+            DLPD_FOR_TASKS(t, M * N, NT) {
+                const int l = t % M, ky = t / M;                                // transposed store [ky'][kx']
+                const cpx v = pl[l * NP + ky];
+                out[ky * N + l] = make_float2(v.x * p.scale, -v.y * p.scale);
+            }
+            return;
+        }
+        const cpx* spec = p.spec + (long)pair * p.spec_pair_stride + ((long)c * N + kz) * N * N + q * M;
+        PointMul<MulSpec> mul{MulSpec{spec}};
+        fft_mid<N, M, 1, NT>(pl, tw, LineMul<NP>(), mul);                       // y tail . multiply . inverse y tail
+        fft_inv_head<N, M, 1, NT>(pl, tw, LineMul<NP>());                       // inverse y
+        if constexpr (XB > 1) fft_pass<PASS_DIT, XB, 1, N, M, XB, N, NP, NT>(pl, tw, LineMul<1>());
+        fft_pass<PASS_DIT, XA, 1, N, M, M, N, NP, NT>(pl, tw, LineMul<1>());    // A_q = IFFT_M along x, all columns
+    }
+
+    // last inverse-x step across the slabs of the cluster (slabs[r] = CTA r's plane buffer) for the row pairs
+    // jp = rank, rank + CL, ...: lanes run along y, so slab reads and S2 stores are contiguous
+    static DLPD_DEV void phase_b(const Params& p, int cid, int rank, cpx* const* slabs, char* smem) {
+        const cpx* tw = reinterpret_cast<const cpx*>(smem) + M * NP;
+        const int pair = cid % p.P, kz = (cid / p.P) % N, c = cid / (p.P * N);
+        cpx* out = p.out + (((long)pair * p.C + c) * N + kz) * N * N;
+        const int npairs = (M / 2 - rank + CL - 1) / CL;
+        DLPD_FOR_TASKS(t, npairs * N, NT) {
+            const int y = t % N, j = 2 * (rank + CL * (t / N));
+            cpx a0[CL], a1[CL];
+            DLPD_UNROLL
+            for (int r = 0; r < CL; ++r) {
+                a0[r] = slabs[r][j * NP + y];
+                a1[r] = slabs[r][(j + 1) * NP + y];
+            }
+            DLPD_UNROLL
+            for (int r = 1; r < CL; ++r) {
+                a0[r] = cmul(a0[r], tw[r * j]);
+                a1[r] = cmul(a1[r], tw[r * (j + 1)]);
+            }
+            Dft<CL>::run(a0);
+            Dft<CL>::run(a1);
+            DLPD_UNROLL
+            for (int m = 0; m < CL; ++m) {
+                const int x = j + m * M;                                        // even
+                if (p.tiled) {
+                    store_cpx2(out + ((((x >> 1) * L) + (y >> 1)) << 2) + ((y & 1) << 1), a0[m], a1[m]);
+                } else {
+                    out[x * N + y] = a0[m];
+                    out[(x + 1) * N + y] = a1[m];
+                }
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------
 // InvZStore: inverse FFT along z, real part -> real volume (standalone VolumeConvolution operator only).
 // ------------------------------------------------------------------------------------------------------
 struct InvZParams {
@@ -644,16 +778,25 @@ template <int C0, int C1, int H> struct EpiParams {
     const cpx* h1;                // [P][N1][N1][N1][H]
     unsigned long long* best;     // [n_rot] packed (score_key << 32 | linear index), pre-set to ~0
     float* score_out;             // optional [n_rot][N^3] masked score volume (module-level drop-in / tests)
+    // optional candidate list for the global top-K (Docker.update_top, Docker.py:86-105): every translation whose masked
+    // score is <= the caller's current K-th best is appended as (score bits, rotation, linear index, 0)
+    int* cand;                    // [cand_cap][4] or nullptr
+    unsigned int* cand_count;     // total number of qualifying translations (may exceed cand_cap: caller re-runs exactly)
+    unsigned int cand_cap, cand_key;
+    int rot_base;                 // index of this chunk's first rotation within the caller's batch
     const cpx* tw0;               // [N]
     int n_rot, n_tiles, grid;     // tiles = P * (N/2)^2; grid = number of CTAs walking over them
     float tau;
     FilterW<C0, C1, H> filt;
 };
 
-template <int L_, int C0, int C1, int H> struct Epilogue {
+template <int L_, int C0, int C1, int H, int TY_ = 2> struct Epilogue {
     typedef EpiParams<C0, C1, H> Params;
-    static constexpr int L = L_, N = 2 * L_, N1 = L_, T = L_;      // T tiles per axis
-    static constexpr int NL0 = 4 * (C0 + 1);       // level-0 lines of a 2x2 tile: line = c*4 + (y&1)*2 + (x&1)
+    static constexpr int L = L_, N = 2 * L_, N1 = L_, T = L_;      // T = N/2 tile rows along x
+    // tile = 2 x TY (x,y) columns: 2x2 normally; 2x1 when two 2x2 buffers do not fit shared memory (N = 256) -- the
+    // level-1 column (x/2, y/2) is then fetched by both y-halves
+    static constexpr int TY = TY_, XY = 2 * TY_, TPR = (TY_ == 2) ? T : N;     // TPR tiles per x-pair row
+    static constexpr int NL0 = XY * (C0 + 1);      // level-0 lines of a tile: line = c*XY + (y&1)*2 + (x&1)
     static constexpr int NT = (N >= 128) ? DLPD_EPI_NT : 128;
     // warp specialisation: the last NPROD threads only issue the cp.async copies of the NEXT tile (each copy touches
     // its own cache line, so issuing them is slow -- but it now overlaps the transform of the current tile instead of
@@ -661,25 +804,31 @@ template <int L_, int C0, int C1, int H> struct Epilogue {
     static constexpr int NPROD = (N >= 128) ? DLPD_EPI_NPROD : 32, NC = NT - NPROD;
     static constexpr int BUF = N * NL0, HB = N1 * H;
     static constexpr int SMEM = (2 * BUF + 2 * HB + N) * (int)sizeof(cpx) + 64 * 8;
-    static constexpr int QPT = NPROD / 2;          // (c, kz) rows covered per sweep of the producer threads
-    static_assert(HB % 2 == 0 && NPROD % 32 == 0 && NC % 32 == 0, "team shapes");
+    static constexpr int QPT = NPROD / TY;         // (c, kz) rows covered per sweep of the producer threads
+    static constexpr int TILES = T * TPR;          // tiles per pair
+    static_assert(HB % 2 == 0 && NPROD % 32 == 0 && NC % 32 == 0 && (TY_ == 1 || TY_ == 2), "team shapes");
+
+    // tile r of a pair -> x/2, first y
+    static DLPD_DEV int tile_xh(int r) { return r / TPR; }
+    static DLPD_DEV int tile_y0(int r) { return (TY == 2) ? 2 * (r % TPR) : r % TPR; }
 
     static DLPD_DEV void issue_loads(const Params& p, int tile, cpx* b0, cpx* hb) {
-        const int pair = tile / (T * T), r = tile % (T * T);            // r = (x/2) * T + (y/2)
-        const cpx* s = p.s2_0 + ((long)pair * (C0 + 1) * N * T * T + r) * 4;
+        const int pair = tile / TILES, r = tile % TILES;
+        const int r4 = tile_xh(r) * T + (tile_y0(r) >> 1);              // 2x2 group (x/2) * T + (y/2) of the tiled S2
+        const cpx* s = p.s2_0 + ((long)pair * (C0 + 1) * N * T * T + r4) * 4 + ((TY == 1) ? 2 * (tile_y0(r) & 1) : 0);
         DLPD_FOR_TASKS_SUB(t, NPROD, NPROD, NC) {
-            const int h = t & 1;
-            int c = (t >> 1) / N, kz = (t >> 1) % N;
-            const cpx* src = s + ((long)(t >> 1) * (T * T) * 4 + 2 * h);           // q = c*N + kz: 32 contiguous bytes per row
-            for (int q = t >> 1; q < (C0 + 1) * N; q += QPT) {
-                cp_async16(b0 + kz * NL0 + c * 4 + 2 * h, src);
+            const int h = (TY == 2) ? (t & 1) : 0, q0 = t / TY;
+            int c = q0 / N, kz = q0 % N;
+            const cpx* src = s + ((long)q0 * (T * T) * 4 + 2 * h);      // q = c*N + kz: 16 TY contiguous bytes per row
+            for (int q = q0; q < (C0 + 1) * N; q += QPT) {
+                cp_async16(b0 + kz * NL0 + c * XY + 2 * h, src);
                 src += (long)QPT * T * T * 4;
                 kz += QPT % N;
                 c += QPT / N;
                 if (kz >= N) { kz -= N; ++c; }
             }
         }
-        const cpx* hs = p.h1 + ((long)pair * T * T + r) * HB;           // level-1 column (x/2, y/2): N1*H contiguous
+        const cpx* hs = p.h1 + ((long)pair * T * T + r4) * HB;          // level-1 column (x/2, y/2): N1*H contiguous
         DLPD_FOR_TASKS_SUB(t, HB / 2, NPROD, NC) cp_async16(hb + 2 * t, hs + 2 * t);
     }
 
@@ -701,6 +850,16 @@ template <int L_, int C0, int C1, int H> struct Epilogue {
 #endif
     }
 
+    static DLPD_DEV void emit_candidate(const Params& p, float v, int rot, unsigned int lin) {
+        const unsigned int slot = atomic_inc_u32(p.cand_count);
+        if (slot < p.cand_cap) {
+            int bits;
+            memcpy(&bits, &v, 4);
+            int* d = p.cand + 4 * (long)slot;
+            d[0] = bits; d[1] = p.rot_base + rot; d[2] = (int)lin; d[3] = 0;
+        }
+    }
+
     // transform + score one tile (consumer team)
     template <class TM>
     static DLPD_DEV void score_tile(const Params& p, const TM& tm, cpx* b0, const cpx* h1, const cpx* tw0, int pair, int x0, int y0,
@@ -709,8 +868,8 @@ template <int L_, int C0, int C1, int H> struct Epilogue {
         const bool hasB = rotB < p.n_rot;
         team_inv_tail<N, NL0, NL0>(tm, b0, tw0, LineMul<1>());
         team_inv_head<N, NL0, NL0>(tm, b0, tw0, LineMul<1>());
-        DLPD_TEAM_TASKS(tm, t, 4 * N) {
-            const int xy = t & 3, z = t >> 2;
+        DLPD_TEAM_TASKS(tm, t, XY * N) {
+            const int xy = t % XY, z = t / XY;
             const cpx* v0 = b0 + z * NL0 + xy;
             const cpx* hz = h1 + (z >> 1) * H;
             float2 h[H];                                        // (rotA, rotB) per hidden unit
@@ -718,14 +877,14 @@ template <int L_, int C0, int C1, int H> struct Epilogue {
             for (int j = 0; j < H; ++j) h[j] = hz[j];
             DLPD_UNROLL
             for (int c = 0; c < C0; ++c) {
-                const float2 v = v0[c * 4];
+                const float2 v = v0[c * XY];
                 DLPD_UNROLL
                 for (int j = 0; j < H; ++j) h[j] = ffma2_(dup2(p.filt.W1t[c * H + j]), v, h[j]);
             }
             float2 sc = dup2(p.filt.b2);
             DLPD_UNROLL
             for (int j = 0; j < H; ++j) sc = ffma2_(dup2(p.filt.W2[j]), make_float2(fmaxf(h[j].x, 0.0f), fmaxf(h[j].y, 0.0f)), sc);
-            const cpx clash = v0[C0 * 4];
+            const cpx clash = v0[C0 * XY];
             const float Va = clash.x < p.tau ? sc.x : 0.0f;     // (clash < tau).float() * score   (Docker.py:226,232)
             const float Vb = clash.y < p.tau ? sc.y : 0.0f;
             const unsigned int lin = (unsigned int)(((x0 + (xy & 1)) * N + (y0 + (xy >> 1))) * N + z);
@@ -736,6 +895,10 @@ template <int L_, int C0, int C1, int H> struct Epilogue {
             if (p.score_out != nullptr) {
                 p.score_out[(long)rotA * N * N * N + lin] = Va;
                 if (hasB) p.score_out[(long)rotB * N * N * N + lin] = Vb;
+            }
+            if (p.cand != nullptr) {
+                if ((unsigned int)(ka >> 32) <= p.cand_key) emit_candidate(p, Va, rotA, lin);
+                if (hasB && (unsigned int)(kb >> 32) <= p.cand_key) emit_candidate(p, Vb, rotB, lin);
             }
         }
     }
@@ -761,7 +924,7 @@ template <int L_, int C0, int C1, int H> struct Epilogue {
 #endif
         for (int tile = bx; tile < p.n_tiles; tile += p.grid, slot ^= 1) {
             DLPD_SYNC();                               // this tile has landed; everyone is done with the other buffer
-            const int pair = tile / (T * T), r = tile % (T * T);
+            const int pair = tile / TILES, r = tile % TILES;
             if (pair != cur_pair) {
                 if (cur_pair >= 0) flush_best(p, cur_pair, bestA, bestB, red);
                 cur_pair = pair;
@@ -773,7 +936,7 @@ template <int L_, int C0, int C1, int H> struct Epilogue {
                 cp_async_wait_pending();
             }
             if (consumer)
-                score_tile(p, tm, bufs + slot * BUF, hbufs + slot * HB, tw0, pair, 2 * (r / T), 2 * (r % T), bestA, bestB);
+                score_tile(p, tm, bufs + slot * BUF, hbufs + slot * HB, tw0, pair, 2 * tile_xh(r), tile_y0(r), bestA, bestB);
         }
         if (cur_pair >= 0) flush_best(p, cur_pair, bestA, bestB, red);
     }

@@ -42,6 +42,7 @@
   #define DLPD_TEAM_TID(TNT) 0
   static inline void named_barrier_sync(int, int) {}
   static inline void store_cpx2(float2* dst, float2 a, float2 b) { dst[0] = a; dst[1] = b; }
+  static inline unsigned int atomic_inc_u32(unsigned int* p) { return (*p)++; }
   #define DLPD_UNROLL
   #define DLPD_RESTRICT
   typedef void* dlpd_stream_t;
@@ -83,6 +84,7 @@
   DLPD_DEV void store_cpx2(float2* dst, float2 a, float2 b) {       // 16-byte aligned destination
       *reinterpret_cast<float4*>(dst) = make_float4(a.x, a.y, b.x, b.y);
   }
+  DLPD_DEV unsigned int atomic_inc_u32(unsigned int* p) { return atomicAdd(p, 1u); }
   typedef cudaStream_t dlpd_stream_t;
 #endif
 

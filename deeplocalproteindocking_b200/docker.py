@@ -160,8 +160,14 @@ class Docker:
     def _volumes(self, atoms: Atoms):
         coords, nat, off = typed_layout(Atoms(atoms.coords.to(torch.float32), atoms.types), self.device)
         density = self.project(coords, nat, off)                         # [1,11,L,L,L]
-        vols = self.docking_model.representation(density)
+        vols = self._represent(density)
         return [v[0] for v in vols], density.sum(dim=1)[0]
+
+    def _represent(self, density):
+        """The representation network in true fp32 (the reference predates TF32 convolutions; cuDNN's default TF32
+        path would perturb the volumes at the 1e-3 level)."""
+        with torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            return self.docking_model.representation(density)
 
     def _engine_for(self, vols) -> DockingSearch:
         key = (self.box_size, vols[0].shape[0], vols[1].shape[0])
@@ -196,7 +202,9 @@ class Docker:
             rot_idx = torch.arange(len(self.rot)) if rotation_subset is None else torch.as_tensor(rotation_subset)
             lig_dev = lig.coords.to(self.device)
             best_all = torch.empty(rot_idx.numel(), 4, device=self.device)
-            exact_topk = self.max_conf > 1
+            want_topk = self.max_conf > 1
+            N = 2 * self.box_size
+            self.exact_batches = self.candidate_batches = 0              # how the top-K list was maintained (diagnostics)
             for i0 in range(0, rot_idx.numel(), self.rot_batch):
                 sel = rot_idx[i0:i0 + self.rot_batch]
                 Rb = self.rot.R[sel].to(self.device)                     # float64, like r_batch_cpu (Docker.py:214)
@@ -204,13 +212,86 @@ class Docker:
                 if self.clash_source == "project":
                     moved = torch.einsum("nij,aj->nai", Rb, lig_dev) + self.box_length / 2.0
                     clash_rot = project_density_batched(moved.to(torch.float32), self.box_size, self.resolution)
-                best, scores = eng.search(Rb.to(torch.float32), tau, clash_rot, return_scores=exact_topk)
+                best = None
+                # Top-K maintenance (Docker.py:86-105).  Once the list is full and its K-th score is negative, only
+                # translations scoring <= that value can enter it: the fused epilogue lists exactly those and the score
+                # volume is never written.  Until then (and if a batch overflows the candidate buffer) the batch is
+                # scored into a volume and the reference's extraction loop is replayed on it.
+                kth = self.top_list[-1][4] if (want_topk and len(self.top_list) == self.max_conf) else None
+                if want_topk and kth is not None and kth < 0.0:
+                    best, cand, total = eng.search_candidates(Rb.to(torch.float32), kth, tau, clash_rot,
+                                                              capacity=max(4 * self.max_conf, 1 << 14))
+                    if total <= cand.shape[0]:
+                        self._merge_candidates(cand.cpu(), sel, N)
+                        self.candidate_batches += 1
+                    else:
+                        best = None
+                if best is None:
+                    best, scores = eng.search(Rb.to(torch.float32), tau, clash_rot, return_scores=want_topk)
+                    if want_topk:
+                        self.exact_batches += 1
+                        for j, r in enumerate(sel.tolist()):
+                            self.update_top(scores[j], r)
                 best_all[i0:i0 + sel.numel()] = best
-                if exact_topk:
+            self.best_per_rotation = best_all.cpu()
+            if not want_topk:
+                b = self.best_per_rotation
+                items = [(int(r), int(b[j, 1]), int(b[j, 2]), int(b[j, 3]), float(b[j, 0])) for j, r in enumerate(rot_idx.tolist())]
+                items.sort(key=lambda t: t[4])
+                self.top_list = items[:self.max_conf]
+        self.write_conformations()
+
+    def _merge_candidates(self, cand: torch.Tensor, sel: torch.Tensor, N: int):
+        """Merge (score, position in `sel`, linear index) candidates into the global list: same order as appending each
+        rotation's extraction list and stable-sorting by score (Docker.py:100-105) -- ties keep rotation order, then
+        row-major voxel order (Docker.py:91-96)."""
+        rows = sorted(((float(s), int(j), int(lin)) for s, j, lin in cand.tolist()), key=lambda t: (t[0], t[1], t[2]))
+        sel_l = sel.tolist()
+        for s, j, lin in rows:
+            self.top_list.append((sel_l[j], lin // (N * N), (lin // N) % N, lin % N, s))
+        self.top_list.sort(key=lambda t: t[4])
+        self.top_list = self.top_list[:self.max_conf]
+
+    def dockE3(self, ureceptor, uligand, batch_size=None, rotation_subset: Optional[torch.Tensor] = None):
+        """`Docker.dockE3` (Docker.py:135-182): the ligand ATOMS are rotated, re-projected and pushed through the
+        representation network for every rotation (plain PyTorch; not rotation-equivariant networks need this), then
+        the same fused correlation / filter / mask / argmin path scores all translations."""
+        self.top_list = []
+        self.docking_model.eval()
+        with torch.no_grad():
+            rec = self._atoms(ureceptor).centred()
+            lig = self._atoms(uligand).centred()
+            rcoords = rec.coords
+            if self.randomize_rot:
+                rcoords = rcoords @ self.randR[0].t()
+            rec_vols, rec_forbidden = self._volumes(Atoms(rcoords + self.box_center, rec.types))
+            eng = self._engine_for(rec_vols)
+            eng.set_receptor(rec_vols, rec_forbidden)
+            eng.set_filter(self.docking_model.filter)
+            tau = float(self.docking_model.threshold_clash)
+            rot_idx = torch.arange(len(self.rot)) if rotation_subset is None else torch.as_tensor(rotation_subset)
+            order = torch.argsort(lig.types, stable=True)
+            counts = torch.bincount(lig.types, minlength=NUM_ATOM_TYPES)[:NUM_ATOM_TYPES]
+            lig_sorted = lig.coords[order]
+            best_all = torch.empty(rot_idx.numel(), 4, device=self.device)
+            nb = self.rot_batch if batch_size is None else max(int(batch_size), 1)
+            for i0 in range(0, rot_idx.numel(), nb):
+                sel = rot_idx[i0:i0 + nb]
+                Rb = self.rot.R[sel]                                                    # CPU float64 (Docker.py:159,162)
+                moved = torch.einsum("nij,aj->nai", Rb, lig_sorted) + self.box_center   # rotate, then translate (:162-163)
+                n = sel.numel()
+                coords = moved.reshape(n, -1).to(self.device, torch.float32)
+                nat = counts.reshape(1, -1).repeat(n, 1).to(self.device, torch.int32)
+                off = (torch.cumsum(counts, 0) - counts).reshape(1, -1).repeat(n, 1).to(self.device, torch.int32)
+                ligand = self.project(coords, nat, off)                                 # [n,11,L,L,L]          (:164)
+                vols = self._represent(ligand)                                          #                       (:165)
+                best, scores = eng.search_prerotated(vols[0], vols[1], ligand.sum(dim=1), tau, return_scores=self.max_conf > 1)
+                best_all[i0:i0 + n] = best
+                if self.max_conf > 1:
                     for j, r in enumerate(sel.tolist()):
                         self.update_top(scores[j], r)
             self.best_per_rotation = best_all.cpu()
-            if not exact_topk:
+            if self.max_conf <= 1:
                 b = self.best_per_rotation
                 items = [(int(r), int(b[j, 1]), int(b[j, 2]), int(b[j, 3]), float(b[j, 0])) for j, r in enumerate(rot_idx.tolist())]
                 items.sort(key=lambda t: t[4])

@@ -140,6 +140,47 @@ class DockingSearch:
                                                      _stream_ptr(self.device)))
         return best, scores
 
+    def search_candidates(self, R: torch.Tensor, score_max: float, threshold_clash: Optional[float] = None,
+                          ligand_forbidden_rotated: Optional[torch.Tensor] = None, capacity: int = 1 << 16
+                          ) -> Tuple[torch.Tensor, torch.Tensor, int]:
+        """`search` that also lists every translation with masked score <= `score_max` (the caller's current K-th best,
+        Docker.py:100-105).  Returns (best [n,4], candidates [m,3] float64 = (score, rotation index in R, linear index),
+        total) -- if total > m == capacity the list is truncated and the caller must redo this batch exactly."""
+        tau = self.threshold_clash if threshold_clash is None else float(threshold_clash)
+        Rd = _dev_f32(R, self.device, "R").reshape(-1, 9)
+        n = Rd.shape[0]
+        best = torch.empty(n, 4, device=self.device, dtype=torch.float32)
+        cand = torch.empty(int(capacity), 4, device=self.device, dtype=torch.int32)
+        count = torch.zeros(1, device=self.device, dtype=torch.int32)
+        cr = None
+        if ligand_forbidden_rotated is not None:
+            cr = _dev_f32(ligand_forbidden_rotated, self.device, "ligand_forbidden_rotated").reshape(n, self.L, self.L, self.L)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib, self.lib.dlpd_search_candidates(self._h, _ptr(Rd), _ptr(cr), n, tau, float(score_max), _ptr(best),
+                                                                _ptr(cand), int(capacity), _ptr(count), _stream_ptr(self.device)))
+        total = int(count.item())
+        c = cand[:min(total, int(capacity))]
+        out = torch.stack([c[:, 0].contiguous().view(torch.float32).double(), c[:, 1].double(), c[:, 2].double()], dim=1)
+        return best, out, total
+
+    def search_prerotated(self, lig0_rot: torch.Tensor, lig1_rot: torch.Tensor, ligand_forbidden_rotated: torch.Tensor,
+                          threshold_clash: Optional[float] = None, return_scores: bool = False
+                          ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """The loop body of `Docker.dockE3` (Docker.py:159-180): ligand volumes [n,C0,L^3], [n,C1,(L/2)^3] and clash
+        volumes [n,L^3] computed per rotation by the caller; returns what `search` returns."""
+        tau = self.threshold_clash if threshold_clash is None else float(threshold_clash)
+        L, L1 = self.L, self.L // 2
+        n, N = lig0_rot.shape[0], 2 * self.L
+        v0 = _dev_f32(lig0_rot, self.device, "lig0_rot").reshape(n, self.C0, L, L, L)
+        v1 = _dev_f32(lig1_rot, self.device, "lig1_rot").reshape(n, self.C1, L1, L1, L1)
+        cr = _dev_f32(ligand_forbidden_rotated, self.device, "ligand_forbidden_rotated").reshape(n, L, L, L)
+        best = torch.empty(n, 4, device=self.device, dtype=torch.float32)
+        scores = torch.empty(n, N, N, N, device=self.device, dtype=torch.float32) if return_scores else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib, self.lib.dlpd_search_prerotated(self._h, _ptr(v0), _ptr(v1), _ptr(cr), n, tau, _ptr(best),
+                                                                _ptr(scores), _stream_ptr(self.device)))
+        return best, scores
+
     def search_host(self, R_host: torch.Tensor, threshold_clash: Optional[float] = None) -> torch.Tensor:
         """End-to-end call with HOST buffers: R [n,3,3] CPU float32 in, best [n,4] CPU out (copies inside, synchronous)."""
         tau = self.threshold_clash if threshold_clash is None else float(threshold_clash)

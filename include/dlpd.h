@@ -75,6 +75,23 @@ int dlpd_set_filter(dlpd_plan* plan, const float* W1, const float* b1, const flo
 int dlpd_search(dlpd_plan* plan, const float* R, const float* lig_clash_rot, int n, float tau, float* out_best,
                 float* out_scores, void* stream);
 
+/* dlpd_search that ALSO lists every translation whose masked score is <= score_max: the candidates of the global
+ * top-K list kept by Docker.update_top (Docker.py:86-105) once the caller knows its current K-th best score, so the
+ * K-iteration extraction loop never needs the score volume.
+ *   cand        device [cand_cap][4] int32: (score as float bits, rotation index in [0,n), linear index (x*2L+y)*2L+z, 0),
+ *               in no particular order
+ *   cand_count  device [1]: number of qualifying translations; if it exceeds cand_cap the list is truncated and the
+ *               caller must fall back to dlpd_search with out_scores for this batch */
+int dlpd_search_candidates(dlpd_plan* plan, const float* R, const float* lig_clash_rot, int n, float tau, float score_max,
+                           float* out_best, int* cand, int cand_cap, unsigned int* cand_count, void* stream);
+
+/* The loop body of Docker.dockE3 (Docker.py:159-180): the ligand is re-projected and pushed through the representation
+ * network for EVERY rotation (plain PyTorch, outside this library), so all its volumes arrive already rotated:
+ *   lig0_rot [n][C0][L^3], lig1_rot [n][C1][(L/2)^3], lig_clash_rot [n][L^3]   (device)
+ * Everything downstream (correlation, filter, mask, argmin) is the same fused path; dlpd_set_ligand is not needed. */
+int dlpd_search_prerotated(dlpd_plan* plan, const float* lig0_rot, const float* lig1_rot, const float* lig_clash_rot, int n,
+                           float tau, float* out_best, float* out_scores, void* stream);
+
 /* Same with HOST buffers (R_host [n][9] in, best_host [n][4] out): stages through pinned memory, copies inside,
  * and synchronises the stream before returning.  This is the end-to-end call bench.py times. */
 int dlpd_search_host(dlpd_plan* plan, const float* R_host, int n, float tau, float* best_host, void* stream);
@@ -93,6 +110,21 @@ int dlpd_profile_enable(dlpd_plan* plan, int on);
 int dlpd_profile_read(dlpd_plan* plan, double* ms, int* launches, void* stream);
 /* Number of kernels this library has launched in the calling process so far. */
 long long dlpd_launch_count(void);
+
+/* ---- tuning / test switches (process-wide) -------------------------------------------------------------
+ * DLPD_OPT_PLANE_MODE     which kernel runs the per-(channel, kz) plane stage: AUTO = one CTA per plane when the plane
+ *                         fits an SM's shared memory (N <= 160), else a 4-CTA cluster with distributed shared memory;
+ *                         SINGLE forces the former (fails if the plane does not fit), CLUSTER prefers the latter wherever it is
+ *                         compiled (box sizes 8, 16, 20, 40, 64, 80, 128).  The receptor spectra of
+ *                         a plan are laid out for the mode in force at dlpd_set_receptor time: do not switch between
+ *                         dlpd_set_receptor and dlpd_search.
+ * DLPD_OPT_EPILOGUE_TILE  0 = automatic, 1 = 2x1, 2 = 2x2 (x,y) columns per epilogue tile */
+#define DLPD_OPT_PLANE_MODE 1
+#define DLPD_OPT_EPILOGUE_TILE 2
+#define DLPD_PLANE_AUTO 0
+#define DLPD_PLANE_SINGLE 1
+#define DLPD_PLANE_CLUSTER 2
+int dlpd_set_option(int key, int value);
 
 /* ---- standalone operators (module-level drop-ins) --------------------------------------------------------
  * TorchProteinLibrary.Volume.VolumeRotation.forward(volume, R)   (Docker.py:40,218)

@@ -78,11 +78,39 @@ class EmuPlan:
         _lib.check(lib(), lib().dlpd_search(self.h, ptr(R), ptr(clash_rot), n, float(tau), ptr(best), ptr(scores), None))
         return best, scores
 
+    def search_candidates(self, R, tau, score_max, cap, clash_rot=None):
+        R = R.contiguous().float().reshape(-1, 9)
+        best = torch.zeros(R.shape[0], 4)
+        cand = torch.zeros(cap, 4, dtype=torch.int32)
+        count = torch.zeros(1, dtype=torch.int32)
+        clash_rot = clash_rot.contiguous().float() if clash_rot is not None else None
+        _lib.check(lib(), lib().dlpd_search_candidates(self.h, ptr(R), ptr(clash_rot), R.shape[0], float(tau), float(score_max),
+                                                       ptr(best), ptr(cand), cap, ptr(count), None))
+        total = int(count)
+        c = cand[:min(total, cap)]
+        return best, c[:, 0].contiguous().view(torch.float32), c[:, 1], c[:, 2], total
+
+    def search_prerotated(self, v0, v1, clash, tau, want_scores=False):
+        v0, v1, clash = (t.contiguous().float() for t in (v0, v1, clash))
+        n, N = v0.shape[0], 2 * self.L
+        best = torch.zeros(n, 4)
+        scores = torch.zeros(n, N, N, N) if want_scores else None
+        _lib.check(lib(), lib().dlpd_search_prerotated(self.h, ptr(v0), ptr(v1), ptr(clash), n, float(tau), ptr(best), ptr(scores), None))
+        return best, scores
+
     def search_host(self, R, tau):
         R = R.contiguous().float().reshape(-1, 9)
         best = torch.zeros(R.shape[0], 4)
         _lib.check(lib(), lib().dlpd_search_host(self.h, ptr(R), R.shape[0], float(tau), ptr(best), None))
         return best
+
+
+OPT_PLANE_MODE, OPT_EPILOGUE_TILE = 1, 2
+PLANE_AUTO, PLANE_SINGLE, PLANE_CLUSTER = 0, 1, 2
+
+
+def set_option(key, value):
+    _lib.check(lib(), lib().dlpd_set_option(key, value))
 
 
 def volume_rotate(vol, R, center="box"):

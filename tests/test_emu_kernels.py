@@ -121,3 +121,87 @@ def test_emu_unsupported_configuration_fails_loudly():
         emu.EmuPlan(12, 4, 6, 5)
     with pytest.raises(Exception):
         emu.volume_correlate(torch.zeros(1, 1, 12, 12, 12), torch.zeros(1, 1, 12, 12, 12))
+
+
+@pytest.fixture
+def cluster_mode():
+    """Force the 4-CTA cluster plane kernel (PlaneX) and the 2x1 epilogue tile -- the kernels the 128^3 configuration uses."""
+    emu.set_option(emu.OPT_PLANE_MODE, emu.PLANE_CLUSTER)
+    emu.set_option(emu.OPT_EPILOGUE_TILE, 1)
+    yield
+    emu.set_option(emu.OPT_PLANE_MODE, emu.PLANE_AUTO)
+    emu.set_option(emu.OPT_EPILOGUE_TILE, 0)
+
+
+@pytest.mark.parametrize("L", [8, 16, 20])
+def test_emu_cluster_plane_correlate_matches_oracle(L, cluster_mode):
+    g = torch.Generator().manual_seed(L)
+    v1 = torch.randn(1, 3, L, L, L, generator=g)
+    v2 = torch.randn(1, 3, L, L, L, generator=g)
+    got = emu.volume_correlate(v1, v2)
+    want = O.correlate(v1.double(), v2.double())
+    assert (got.double() - want).abs().max() <= 2e-5 * want.abs().max()
+
+
+@pytest.mark.parametrize("L,C0,C1,H,n", [(8, 4, 6, 5, 3), (16, 4, 6, 5, 2), (20, 16, 32, 24, 3)])
+def test_emu_cluster_plane_search_matches_oracle(L, C0, C1, H, n, cluster_mode):
+    test_emu_search_matches_oracle(L, C0, C1, H, n)
+
+
+def test_emu_candidates_are_exactly_the_translations_below_the_threshold():
+    """dlpd_search_candidates vs the masked score volume of the same call (Docker.update_top feed, Docker.py:86-105)."""
+    L, C0, C1, H = 8, 4, 6, 5
+    rec, lig, rf, lf = _case(L, C0, C1, seed=31)
+    filt = O.FilterWeights.random(C0 + C1, H, seed=2)
+    Rs = R20[[11, 500, 1400]]
+    tau = float(torch.quantile(O.correlate(rf, lf[None, None]).flatten(), 0.7))
+    plan = emu.EmuPlan(L, C0, C1, H, max_rot=2)
+    try:
+        plan.set_receptor(rec[0][0], rec[1][0], rf[0, 0])
+        plan.set_ligand(lig[0][0], lig[1][0], lf)
+        plan.set_filter(filt.W1, filt.b1, filt.W2, filt.b2)
+        best, scores = plan.search(Rs, tau, want_scores=True)
+        thr = float(torch.kthvalue(scores.flatten(), 40).values)
+        best2, cs, crot, clin, total = plan.search_candidates(Rs, tau, thr, cap=4096)
+        _, _, _, _, total_small = plan.search_candidates(Rs, tau, thr, cap=8)
+    finally:
+        plan.close()
+    assert torch.equal(best, best2)
+    flat = scores.reshape(3, -1)
+    want = torch.nonzero(flat <= thr)
+    assert total == want.shape[0] == total_small and total >= 40
+    got = sorted(zip(crot.tolist(), clin.tolist(), cs.tolist()))
+    assert [(r, l) for r, l, _ in got] == [tuple(w) for w in want.tolist()]
+    assert all(s == float(flat[r, l]) for r, l, s in got)
+
+
+def test_emu_search_prerotated_equals_search_of_rotated_volumes():
+    """dockE3 entry point: volumes rotated by the caller (here: with the oracle's VolumeRotation) must score exactly
+    like the fused gather of the same volumes, up to the interpolation rounding of the two rotation codes."""
+    L, C0, C1, H = 8, 4, 6, 5
+    rec, lig, rf, lf = _case(L, C0, C1, seed=41)
+    filt = O.FilterWeights.random(C0 + C1, H, seed=7)
+    Rs = R20[[21, 900, 1700]]
+    rot = lambda v: torch.stack([O.rotate_volume(v.double(), Rs[i][None])[0] for i in range(3)]).float()
+    v0, v1, cl = rot(lig[0]), rot(lig[1]), rot(lf[None, None])[:, 0]
+    tau = 4.0
+    plan = emu.EmuPlan(L, C0, C1, H, max_rot=2)
+    try:
+        plan.set_receptor(rec[0][0], rec[1][0], rf[0, 0])
+        plan.set_filter(filt.W1, filt.b1, filt.W2, filt.b2)
+        best_pre, sc_pre = plan.search_prerotated(v0, v1, cl, tau, want_scores=True)
+        plan.set_ligand(lig[0][0], lig[1][0], lf)
+        best, sc = plan.search(Rs, tau, want_scores=True)
+    finally:
+        plan.close()
+    ok = (sc_pre != 0) == (sc != 0)                         # threshold-straddling voxels may flip
+    assert ok.float().mean() > 0.999
+    assert (sc_pre - sc)[ok].abs().max() <= 1e-4 * sc.abs().max()
+    d = lambda t: t.double()
+    spectra = O.ReceptorSpectra([d(r) for r in rec], d(rf))
+    for i in range(3):
+        V = O.score_rotation(spectra, [d(v0[i])[None], d(v1[i])[None]], d(cl[i]), torch.eye(3, dtype=torch.float64),
+                             filt.to(torch.float64), tau, ligand_forbidden_is_rotated=True)
+        s, x, y, z = O.best_pose(V)
+        assert [int(v) for v in best_pre[i, 1:]] == [x, y, z]
+        assert abs(float(best_pre[i, 0]) - s) <= 1e-4 * max(abs(s), 1e-3 * float(V.abs().max()))

@@ -50,3 +50,72 @@ def test_docksE3_matches_oracle_loop(clash_source, max_conf, tmp_path):
     assert [t[:4] for t in docker.top_list] == [t[:4] for t in want_top]
     lines = open(tmp_path / "t.dat").read().splitlines()
     assert len(lines) == len(docker.top_list) and all(len(l.split("\t")) == 13 for l in lines)
+
+
+def test_dockSE3_topk_candidates_path_matches_oracle_loop(tmp_path):
+    """max_conf = 300 over 12 rotations in batches of 4: the first batch fills the list through score volumes, the later
+    ones through the epilogue's candidate lists (no score volume) -- same top list as the reference's extraction loop."""
+    L, res, K = 20, 1.25, 300
+    model = _model(1)
+    rec, lig = synthetic.config_pair(L, seed=5)
+    docker = Docker(model, angle_inc=20, box_size=L, resolution=res, max_conf=K, rot_batch=4, clash_source="rotate", device=DEV)
+    subset = torch.arange(0, 1854, 160)
+    docker.dockSE3(rec, lig, batch_size=2, rotation_subset=subset)
+    assert docker.candidate_batches >= 1 and docker.exact_batches >= 1
+    with torch.no_grad():
+        rc, lc = rec.centred(), lig.centred()
+        rv, rf = docker._volumes(Atoms(rc.coords + docker.box_center, rc.types))
+        lv, lf = docker._volumes(Atoms(lc.coords + docker.box_center, lc.types))
+    cpu = lambda t: t.detach().cpu().double()
+    filt = O.FilterWeights(cpu(model.filter.fc[0].weight), cpu(model.filter.fc[0].bias), cpu(model.filter.fc[2].weight),
+                           cpu(model.filter.fc[2].bias))
+    _, want_top = O.dock([cpu(v)[None] for v in rv], cpu(rf)[None, None], [cpu(v)[None] for v in lv], cpu(lf), docker.rot.R[subset],
+                         filt, 5.0, K=K + 50)
+    want_top = [(int(subset[i]), x, y, z, s) for i, x, y, z, s in want_top]
+    assert len(docker.top_list) == K
+    got_s = torch.tensor([t[4] for t in docker.top_list], dtype=torch.float64)
+    want_s = torch.tensor([t[4] for t in want_top[:K]], dtype=torch.float64)
+    tol = 1e-4 * float(want_s.abs().max())
+    assert (got_s - want_s).abs().max() <= tol
+    # membership: every pose the oracle ranks clearly above the K-th score must be present, and nothing may come from
+    # outside the oracle's list extended by 50 -- poses within the fp32 tolerance of the K-th score may swap
+    got = set(t[:4] for t in docker.top_list)
+    kth = float(want_s[-1])
+    assert {t[:4] for t in want_top if t[4] < kth - tol} <= got
+    assert got <= {t[:4] for t in want_top if t[4] <= kth + tol}
+    order = [t[:4] for t in docker.top_list]
+    ref_rank = {t[:4]: i for i, t in enumerate(want_top)}
+    assert all(abs(ref_rank[p] - i) <= 3 or abs(want_top[ref_rank[p]][4] - want_top[min(i, K + 49)][4]) <= tol for i, p in enumerate(order))
+
+
+def test_dockE3_matches_oracle(tmp_path):
+    """dockE3 (Docker.py:135-182): re-projected + re-represented ligand per rotation, fused scoring downstream."""
+    L, res = 20, 1.25
+    model = _model(2)
+    rec, lig = synthetic.config_pair(L, seed=7)
+    docker = Docker(model, angle_inc=20, box_size=L, resolution=res, max_conf=1, rot_batch=3, device=DEV)
+    subset = torch.tensor([3, 400, 800, 1200, 1600])
+    assert docker.new_log(str(tmp_path / "e3.dat"))
+    docker.dockE3(rec, lig, batch_size=3, rotation_subset=subset)
+    docker.cleanup()
+    cpu = lambda t: t.detach().cpu().double()
+    filt = O.FilterWeights(cpu(model.filter.fc[0].weight), cpu(model.filter.fc[0].bias), cpu(model.filter.fc[2].weight),
+                           cpu(model.filter.fc[2].bias))
+    with torch.no_grad():
+        rc, lc = rec.centred(), lig.centred()
+        rv, rf = docker._volumes(Atoms(rc.coords + docker.box_center, rc.types))
+        spectra = O.ReceptorSpectra([cpu(v)[None] for v in rv], cpu(rf)[None, None])
+        for j, r in enumerate(subset.tolist()):
+            moved = lc.coords @ docker.rot.R[r].t() + docker.box_center
+            lv, lf = docker._volumes(Atoms(moved, lc.types))
+            V = O.score_rotation(spectra, [cpu(v)[None] for v in lv], cpu(lf), torch.eye(3, dtype=torch.float64), filt, 5.0,
+                                 ligand_forbidden_is_rotated=True)
+            s, x, y, z = O.best_pose(V)
+            got = docker.best_per_rotation[j]
+            tol = 1e-4 * max(abs(s), 1e-3 * float(V.abs().max()))
+            gx, gy, gz = (int(v) for v in got[1:])
+            # the network runs on a different batch here than inside dockE3 (cuDNN may pick another algorithm), so the
+            # volumes agree to rounding only: poses must match unless the oracle's scores are tied within tolerance
+            assert [gx, gy, gz] == [x, y, z] or abs(float(V[gx, gy, gz]) - s) <= tol
+            assert abs(float(got[0]) - float(V[gx, gy, gz])) <= tol
+    assert len(open(tmp_path / "e3.dat").read().splitlines()) == 1

@@ -191,3 +191,72 @@ def test_errors_are_loud():
     out = VolumeConvolution()(v, v.detach())
     with pytest.raises(NotImplementedError):
         out.sum().backward()
+
+
+# ---- the kernels of the 128^3 configuration: 4-CTA cluster plane (distributed shared memory) + 2x1 epilogue tile ----
+@pytest.fixture
+def cluster_mode():
+    _lib.set_option("plane_mode", "cluster")
+    _lib.set_option("epilogue_tile", 1)
+    yield
+    _lib.set_option("plane_mode", "auto")
+    _lib.set_option("epilogue_tile", 0)
+
+
+@pytest.mark.parametrize("L", [8, 16, 20, 40, 80])
+def test_cluster_plane_convolution_matches_oracle(L, cluster_mode):
+    test_volume_convolution_matches_oracle(L)
+
+
+@pytest.mark.parametrize("L,C0,C1,H,n", [(16, 4, 6, 5, 4), (20, 16, 32, 24, 5)])
+def test_cluster_plane_search_small_matches_oracle(L, C0, C1, H, n, cluster_mode):
+    test_search_small_matches_oracle(L, C0, C1, H, n)
+
+
+def test_cluster_plane_search_80_identical_poses(cluster_mode):
+    """Same L=80 problem through both plane kernels: identical best poses, scores equal to rounding."""
+    L, C0, C1 = 80, 16, 32
+    rec, rec_clash = synthetic.learned_volumes(L, (C0, C1), seed=11)
+    lig, lig_clash = synthetic.learned_volumes(L, (C0, C1), seed=12)
+    filt = O.FilterWeights.random(C0 + C1, seed=13)
+    Rs = R20[[7, 777, 1777, 42, 1000]]
+    out = []
+    for mode, tile in (("cluster", 1), ("cluster", 2), ("single", 2)):
+        _lib.set_option("plane_mode", mode)
+        _lib.set_option("epilogue_tile", tile)
+        eng = DockingSearch(L, (C0, C1), max_rot=4, device=DEV)
+        eng.set_receptor(rec, rec_clash); eng.set_ligand(lig, lig_clash); eng.set_filter((filt.W1, filt.b1, filt.W2, filt.b2))
+        out.append(eng.search(Rs, 30.0)[0].cpu())
+        eng.close()
+    for b in out[:2]:
+        assert torch.equal(b[:, 1:], out[2][:, 1:])
+        assert torch.allclose(b[:, 0], out[2][:, 0], rtol=2e-5, atol=1e-6)
+
+
+def test_volume_convolution_128_matches_oracle():
+    L = 128
+    g = torch.Generator().manual_seed(128)
+    v1 = torch.randn(1, 1, L, L, L, generator=g)
+    v2 = torch.randn(1, 1, L, L, L, generator=g)
+    got = VolumeConvolution()(v1.to(DEV), v2.to(DEV)).cpu()
+    want = O.correlate(_d(v1), _d(v2))
+    assert (got.double() - want).abs().max() <= 2e-5 * want.abs().max()
+    vol = torch.randn(1, 2, L, L, L, generator=g)
+    R = R20[[321]]
+    rot = VolumeRotation()(vol.to(DEV), R.float().to(DEV)).cpu()
+    assert (rot.double() - O.rotate_volume(_d(vol), R)).abs().max() < 2e-4      # fp32 source coordinates: error grows with L
+
+
+def test_search_full_size_128_matches_oracle():
+    """BASELINE config 5 shape: L=128, 16@128^3 + 32@64^3 + clash; 2 rotations (one packed pair) vs the fp64 oracle."""
+    L, C0, C1 = 128, 16, 32
+    rec, rec_clash = synthetic.learned_volumes(L, (C0, C1), seed=21)
+    lig, lig_clash = synthetic.learned_volumes(L, (C0, C1), seed=22)
+    filt = O.FilterWeights.random(C0 + C1, seed=23)
+    Rs = R20[[9, 1234]]
+    tau = 30.0
+    eng = DockingSearch(L, (C0, C1), max_rot=2, device=DEV)
+    eng.set_receptor(rec, rec_clash); eng.set_ligand(lig, lig_clash); eng.set_filter((filt.W1, filt.b1, filt.W2, filt.b2))
+    best, _ = eng.search(Rs, tau)
+    eng.close()
+    _check_against_oracle(best.cpu(), None, rec, lig, rec_clash, lig_clash, Rs, filt, tau)
