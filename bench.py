@@ -36,11 +36,28 @@ L, C0, C1, HID = 80, 16, 32, 24
 ANGLE_INC = 10
 TAU = 300.0
 
+# BASELINE.json configs (index = position in BASELINE.json "configs", 1-based).  The bench line the driver reads is
+# config 2; 3-5 are the multi-GPU / batch / large-box cases, runnable with --config for measurement.
+CONFIGS = {
+    2: dict(box=80, angle_inc=10, pairs=1, source="atoms",
+            text="single pair, 80^3 grid, oim10 rotation set (14868 rotations, file order)"),
+    3: dict(box=80, angle_inc=4, pairs=1, source="atoms",
+            text="single pair, 80^3 grid, oim04 rotation set (232020 rotations, deterministic surrogate: the table is a "
+                 "missing blob in the reference snapshot)"),
+    4: dict(box=80, angle_inc=6, pairs=64, source="learned",
+            text="batch of 64 synthetic receptor-ligand pairs (multi-channel learned volumes), oim06 rotation set (68760 "
+                 "rotations), pairs dealt round-robin to the GPUs, one pair switch (receptor spectra + ligand upload) per step"),
+    5: dict(box=128, angle_inc=4, pairs=1, source="learned",
+            text="large-complex 128^3 grid, multi-channel learned volumes, oim04 rotation set (232020 rotations, surrogate)"),
+}
 
-def algorithmic_bytes_per_rotation(L=L, C0=C0, C1=C1):
+
+def algorithmic_bytes_per_rotation(L=None, C0=C0, C1=C1):
     """per channel of edge l (n = 2l, h = n*n*(n/2+1)): 4 l^3 + 24 h bytes; split by kernel as
     FwdZ = 4 l^3 (read ligand), Plane = 16 h (receptor spectrum read + spectrum write), Epilogue (level 0) and
     HiddenL1 (level 1) = 8 h (read back)."""
+    L = globals()["L"] if L is None else L
+
     def h(l):
         n = 2 * l
         return n * n * (n // 2 + 1)
@@ -52,6 +69,16 @@ def algorithmic_bytes_per_rotation(L=L, C0=C0, C1=C1):
     }
     parts["total"] = sum(parts.values())
     return parts
+
+
+def measured_traffic():
+    """DRAM bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum of one `ncu --set full` capture at the bench's
+    launch shape), committed under profiles/ by tools/ncu_traffic.py; None if no capture matches."""
+    path = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f)
+    return None
 
 
 def measured_peaks():
@@ -87,9 +114,8 @@ def build_problem(device):
 
 
 def clash_volumes(lig_coords_dev, Rb64, device):
-    from deeplocalproteindocking_b200.docker import project_density_batched
-    moved = torch.einsum("nij,aj->nai", Rb64, lig_coords_dev) + L * 1.25 / 2.0
-    return project_density_batched(moved.to(torch.float32), L, 1.25)
+    from deeplocalproteindocking_b200.volume import project_clash_rotated
+    return project_clash_rotated(lig_coords_dev, Rb64, L, 1.25)
 
 
 class ClockSampler:
@@ -184,12 +210,24 @@ def run_reference(args, rank, world):
     print(json.dumps(line), flush=True)
 
 
-def workload_config(rot_batch, world):
-    return {"workload": "single pair, 80^3 grid, oim10 rotation set (14868 rotations, file order), 16@80^3+32@40^3 channels "
-                        "+ clash channel, 48->24->1 filter, all 160^3 translations scored per rotation, fp32",
-            "box_size": L, "channels": [C0, C1], "rotation_set": "oim10", "rotations_per_step_per_gpu": rot_batch,
-            "parallelism": "rotations sharded i mod %d" % world,
-            "l2_policy": "working set per step >> L2 (receptor spectra 0.69 GB + 0.86 GB workspace per rotation pair); no explicit flush"}
+def workload_config(rot_batch, world, config=2):
+    c = CONFIGS[config]
+    return {"workload": "%s, %d@%d^3+%d@%d^3 channels + clash channel, 48->24->1 filter, all %d^3 translations scored per "
+                        "rotation, fp32" % (c["text"], C0, c["box"], C1, c["box"] // 2, 2 * c["box"]),
+            "baseline_config": config,
+            "box_size": c["box"], "channels": [C0, C1], "rotation_set": "oim%02d" % c["angle_inc"],
+            "rotations_per_step_per_gpu": rot_batch,
+            "parallelism": ("rotations sharded i mod %d" % world) if c["pairs"] == 1 else
+                           ("pairs sharded p mod %d, all rotations of a pair on one GPU" % world),
+            "l2_policy": "working set per step >> L2 (receptor spectra + per-pair workspace, GBs); no explicit flush"}
+
+
+def build_learned_pair(box, seed, device):
+    """Configs 4/5: "multi-channel learned volumes" generated directly; the clash volume is rotated with the features."""
+    from deeplocalproteindocking_b200 import synthetic
+    rec, rec_clash = synthetic.learned_volumes(box, (C0, C1), seed=2 * seed, device=device)
+    lig, lig_clash = synthetic.learned_volumes(box, (C0, C1), seed=2 * seed + 1, device=device)
+    return rec, rec_clash, lig, lig_clash
 
 
 def main():
@@ -202,6 +240,7 @@ def main():
     ap.add_argument("--max-rot", type=int, default=32, help="rotations per internal chunk (workspace size)")
     ap.add_argument("--cpu-rotations", type=int, default=8, help="rotations of the cpu_baseline sample (0 = skip)")
     ap.add_argument("--ref-rot-per-step", type=int, default=2)
+    ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config (1-based); 2 is the bench line")
     ap.add_argument("--plane-mode", default="auto", choices=["auto", "single", "cluster"], help="plane-stage kernel (tuning)")
     ap.add_argument("--epilogue-tile", type=int, default=0, choices=[0, 1, 2], help="epilogue tile shape (tuning)")
     args = ap.parse_args()
@@ -228,20 +267,41 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=device)
 
-    rec_vols, rec_clash, lig_vols, lig_coords, filt = build_problem(device)
-    Rall = rotations.Rotations(ANGLE_INC).R                                  # [14868,3,3] float64 CPU
-    shard = D.shard_indices(Rall.shape[0], rank, world)
+    cfg = CONFIGS[args.config]
+    box = cfg["box"]
+    global L
+    L = box                                                                   # clash_volumes / cpu_baseline read the module constant
+    Rall = rotations.Rotations(cfg["angle_inc"]).R                           # [N_rot,3,3] float64 CPU
     nb = args.rot_batch
     n_steps_total = args.warmup + args.steps
+    if cfg["source"] == "atoms":
+        rec_vols, rec_clash, lig_vols, lig_coords, filt = build_problem(device)
+        pairs = [(rec_vols, rec_clash, lig_vols, None)]
+        lig_dev = lig_coords.to(device)
+    else:
+        from deeplocalproteindocking_b200 import SimpleFilter
+        torch.manual_seed(1234 + args.config)
+        filt = SimpleFilter([C0, C1])
+        my_pairs = [p for p in range(cfg["pairs"]) if p % world == rank] or [rank % cfg["pairs"]]
+        my_pairs = my_pairs[:max(1, min(len(my_pairs), n_steps_total))]
+        pairs = [build_learned_pair(box, 1000 * args.config + p, device) for p in my_pairs]
+        lig_dev = lig_coords = None
+    multi_pair = cfg["pairs"] > 1
+    shard = D.shard_indices(Rall.shape[0], rank, world) if not multi_pair else torch.arange(Rall.shape[0])
 
     def step_indices(s):
         return shard[(torch.arange(nb) + s * nb) % shard.numel()]
 
-    eng = DockingSearch(L, (C0, C1), HID, max_rot=args.max_rot, device=device)
-    eng.set_receptor(rec_vols, rec_clash)
-    eng.set_ligand(lig_vols, None)
+    eng = DockingSearch(box, (C0, C1), HID, max_rot=args.max_rot, device=device)
     eng.set_filter(filt)
-    lig_dev = lig_coords.to(device)
+    tau = TAU if cfg["source"] == "atoms" else 30.0
+
+    def load_pair(k):
+        rv, rc, lv, lc = pairs[k % len(pairs)]
+        eng.set_receptor(rv, rc)
+        eng.set_ligand(lv, lc)
+
+    load_pair(0)
     R_dev = [Rall[step_indices(s)].to(device) for s in range(n_steps_total)]             # resident inputs (float64 like r_batch_cpu)
     R_pin = [Rall[step_indices(s)].float().pin_memory() for s in range(n_steps_total)]   # host inputs for the e2e leg
 
@@ -251,16 +311,20 @@ def main():
         torch.cuda.synchronize()
 
     def device_step(s):
-        clash = clash_volumes(lig_dev, R_dev[s], device)
-        best, _ = eng.search(R_dev[s].to(torch.float32), TAU, clash)
+        if multi_pair:
+            load_pair(s)
+        clash = clash_volumes(lig_dev, R_dev[s], device) if lig_dev is not None else None
+        best, _ = eng.search(R_dev[s].to(torch.float32), tau, clash)
         return best
 
     def host_step(s):
         """End to end through the public API with HOST buffers: H2D of the step's rotation matrices from pinned
         memory, clash re-projection + fused search, D2H of the step's best poses."""
+        if multi_pair:
+            load_pair(s)
         Rd = R_pin[s].to(device, non_blocking=True)
-        clash = clash_volumes(lig_dev, Rd.double(), device)
-        best, _ = eng.search(Rd, TAU, clash)
+        clash = clash_volumes(lig_dev, Rd.double(), device) if lig_dev is not None else None
+        best, _ = eng.search(Rd, tau, clash)
         return best.cpu()
 
     # ---------------- device-resident leg (value, roofline) -------------------------------------------------
@@ -309,7 +373,8 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        alg = algorithmic_bytes_per_rotation()
+        alg = algorithmic_bytes_per_rotation(box)
+        traffic = measured_traffic()
         per_kernel = {}
         for k, (tms, n) in prof.items():
             if n == 0:
@@ -321,15 +386,22 @@ def main():
         dom = max(per_kernel, key=lambda k: per_kernel[k]["ms_per_launch"] * per_kernel[k]["launches"]) if per_kernel else None
         roofline = None
         if dom:
+            rot_per_launch = nb * args.steps / per_kernel[dom]["launches"]
+            tr = None
+            if traffic and traffic.get("box") == box and dom in traffic.get("kernels", {}) and \
+                    traffic.get("rotations_per_launch") == rot_per_launch:
+                tr = traffic["kernels"][dom]["dram_bytes_per_launch"]
             roofline = {"bound": "hbm", "kernel": dom, "achieved": per_kernel[dom]["algorithmic_GBps"], "peak": peak,
-                        "unit": "GB/s", "frac": per_kernel[dom]["frac_of_hbm_peak"], "traffic": None, "peak_source": peak_src,
-                        "algorithmic_bytes_per_rotation": alg[dom]}
+                        "unit": "GB/s", "frac": per_kernel[dom]["frac_of_hbm_peak"], "traffic": tr, "peak_source": peak_src,
+                        "algorithmic_bytes_per_rotation": alg[dom], "rotations_per_launch": rot_per_launch,
+                        "algorithmic_bytes_per_launch": alg[dom] * rot_per_launch,
+                        "traffic_source": (traffic or {}).get("source") if tr else None}
         step_gbs = (value / world) * alg["total"] / 1e9
         line = {
             "metric": "rotations/sec (all translations scored)", "value": value, "unit": "rotations/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": workload_config(nb, world),
+            "config": workload_config(nb, world, args.config),
             "e2e": {"value": e2e_value, "unit": "rotations/s", "h2d_bytes_per_step": nb * 36, "d2h_bytes_per_step": nb * 16},
             "gpu_launches": launches,
             "roofline": roofline,
@@ -338,7 +410,7 @@ def main():
             "kernels": per_kernel,
             "clocks": clocks,
         }
-        if world == 1 and args.cpu_rotations > 0:
+        if world == 1 and args.cpu_rotations > 0 and cfg["source"] == "atoms":
             t, n = cpu_baseline(rec_vols, rec_clash, lig_vols, lig_coords, filt, Rall, args.cpu_rotations)
             line["cpu_baseline"] = {"value": n / t, "unit": "rotations/s", "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": "%d rotations of oim10 (after 1 warm-up), CPU PyTorch torch.fft oracle, "

@@ -33,6 +33,7 @@ SIGNATURES = {
     "dlpd_profile_enable": (c_int, [c_void_p, c_int]),
     "dlpd_profile_read": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_int), c_void_p]),
     "dlpd_launch_count": (c_longlong, []),
+    "dlpd_project_clash": (c_int, [c_void_p, c_void_p, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
     "dlpd_set_option": (c_int, [c_int, c_int]),
     "dlpd_volume_rotate": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_void_p]),
     "dlpd_volume_correlate": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_void_p]),

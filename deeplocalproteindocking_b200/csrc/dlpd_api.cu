@@ -704,6 +704,18 @@ extern "C" int dlpd_volume_rotate(const float* vol, const float* R, float* out, 
     return launch<RotateVolume>(dim3(gx, C, B), p, (dlpd_stream_t)stream);
 }
 
+extern "C" int dlpd_project_clash(const double* coords, const double* R, int nat, int n, int L, float resolution, float* out,
+                                  void* stream) {
+    if (!coords || !R || !out || nat < 1 || n < 1 || L < 1 || !(resolution > 0.f))
+        return fail(DLPD_EINVAL, "dlpd_project_clash: bad argument");
+    dlpd_stream_t st = (dlpd_stream_t)stream;
+    TRY(rt_memset(out, 0, sizeof(float) * n3(L) * (size_t)n, st));
+    ProjectParams p;
+    p.coords = coords; p.R = R; p.out = out; p.nat = nat; p.n = n; p.L = L; p.res = resolution;
+    p.centre = 0.5 * (double)L * (double)resolution;
+    return launch<ProjectClash>(dim3((nat + ProjectClash::NT - 1) / ProjectClash::NT, n), p, st);
+}
+
 struct OpWorkspace {
     cpx *tw = nullptr, *s1 = nullptr, *spec = nullptr, *s2 = nullptr;
     int L = 0, Q = 0;

@@ -127,6 +127,65 @@ struct RotateVolume {
 };
 
 // ------------------------------------------------------------------------------------------------------
+// ProjectClash: the in-loop ligand re-projection of dockSE3 (Docker.py:221-224) for a batch of rotations:
+//   x = (float)(R_i r + box_centre)   -- rotation and translation in float64 like the reference's CPU CoordsRotate /
+//                                        CoordsTranslate, then the cast of `.to(dtype=torch.float)`
+//   out[i][v] += exp(-|x - v res|^2 / 2) for the 5^3 voxels v within +-2 cells of floor(x / res) inside the box
+// i.e. `TypedCoords2Volume(...)(...).sum(dim=1)` (atom types do not matter once summed).  One thread per
+// (atom, rotation); the Gaussian is evaluated per axis (15 exponentials) and scattered with atomic adds.
+// ------------------------------------------------------------------------------------------------------
+struct ProjectParams {
+    const double* coords;    // [nat][3] ligand atoms, bbox-centred (Angstrom)
+    const double* R;         // [n][9] row-major
+    float* out;              // [n][L^3], zeroed by the launcher
+    int nat, n, L;
+    float res;
+    double centre;           // box_length / 2
+};
+struct ProjectClash {
+    typedef ProjectParams Params;
+    static constexpr int NT = 128;
+    static constexpr int SMEM = 0;
+    // grid: x = ceil(nat / NT), y = n
+    static DLPD_DEV void body(const Params& p, int bx, int by, int, char*) {
+        const double* R = p.R + 9 * by;
+        float* out = p.out + (long)by * p.L * p.L * p.L;
+        DLPD_FOR_TASKS(t, NT, NT) {
+            const int a = bx * NT + t;
+            if (a < p.nat) {
+                const double rx = p.coords[3 * a], ry = p.coords[3 * a + 1], rz = p.coords[3 * a + 2];
+                const float x[3] = {(float)(R[0] * rx + R[1] * ry + R[2] * rz + p.centre),
+                                    (float)(R[3] * rx + R[4] * ry + R[5] * rz + p.centre),
+                                    (float)(R[6] * rx + R[7] * ry + R[8] * rz + p.centre)};
+                int base[3];
+                float g[3][5];
+                DLPD_UNROLL
+                for (int d = 0; d < 3; ++d) {
+                    base[d] = (int)floorf(x[d] / p.res) - 2;
+                    DLPD_UNROLL
+                    for (int k = 0; k < 5; ++k) {
+                        const int i = base[d] + k;
+                        const float dx = x[d] - (float)i * p.res;
+                        g[d][k] = (i >= 0 && i < p.L) ? expf(-0.5f * dx * dx) : 0.0f;
+                    }
+                }
+                for (int i = 0; i < 5; ++i) {
+                    if (g[0][i] == 0.0f) continue;
+                    for (int j = 0; j < 5; ++j) {
+                        const float gxy = g[0][i] * g[1][j];
+                        if (gxy == 0.0f) continue;
+                        float* row = out + ((long)(base[0] + i) * p.L + (base[1] + j)) * p.L;
+                        DLPD_UNROLL
+                        for (int k = 0; k < 5; ++k)
+                            if (g[2][k] != 0.0f) atomic_add_f32(row + base[2] + k, gxy * g[2][k]);
+                    }
+                }
+            }
+        }
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------
 // FwdZ: gather (rotate) + pruned forward FFT along z, one channel per CTA.
 // Used for the clash channel, the receptor / standalone operators and channel counts the channel-last kernel
 // (FwdZC below) does not take.

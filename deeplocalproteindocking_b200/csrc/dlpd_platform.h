@@ -43,6 +43,7 @@
   static inline void named_barrier_sync(int, int) {}
   static inline void store_cpx2(float2* dst, float2 a, float2 b) { dst[0] = a; dst[1] = b; }
   static inline unsigned int atomic_inc_u32(unsigned int* p) { return (*p)++; }
+  static inline void atomic_add_f32(float* p, float v) { *p += v; }
   #define DLPD_UNROLL
   #define DLPD_RESTRICT
   typedef void* dlpd_stream_t;
@@ -85,6 +86,7 @@
       *reinterpret_cast<float4*>(dst) = make_float4(a.x, a.y, b.x, b.y);
   }
   DLPD_DEV unsigned int atomic_inc_u32(unsigned int* p) { return atomicAdd(p, 1u); }
+  DLPD_DEV void atomic_add_f32(float* p, float v) { atomicAdd(p, v); }
   typedef cudaStream_t dlpd_stream_t;
 #endif
 

@@ -19,7 +19,7 @@ import torch
 
 from .rotations import Rotations
 from .search import DockingSearch
-from .volume import TypedCoords2Volume
+from .volume import TypedCoords2Volume, project_clash_rotated
 
 NUM_ATOM_TYPES = 11
 
@@ -210,8 +210,7 @@ class Docker:
                 Rb = self.rot.R[sel].to(self.device)                     # float64, like r_batch_cpu (Docker.py:214)
                 clash_rot = None
                 if self.clash_source == "project":
-                    moved = torch.einsum("nij,aj->nai", Rb, lig_dev) + self.box_length / 2.0
-                    clash_rot = project_density_batched(moved.to(torch.float32), self.box_size, self.resolution)
+                    clash_rot = project_clash_rotated(lig_dev, Rb, self.box_size, self.resolution)
                 best = None
                 # Top-K maintenance (Docker.py:86-105).  Once the list is full and its K-th score is negative, only
                 # translations scoring <= that value can enter it: the fused epilogue lists exactly those and the score

@@ -126,3 +126,20 @@ class TypedCoords2Volume(nn.Module):
             lin = (c[..., 0] * L + c[..., 1]) * L + c[..., 2]
             out[b].index_put_((types[:, None].expand_as(lin).reshape(-1), lin.reshape(-1)), val.reshape(-1), accumulate=True)
         return out.reshape(B, T, L, L, L)
+
+
+def project_clash_rotated(lig_coords: torch.Tensor, R: torch.Tensor, box_size: int, resolution: float) -> torch.Tensor:
+    """The in-loop ligand re-projection of `dockSE3` (Docker.py:221-224) for a batch of rotations, one CUDA launch:
+    lig_coords [Nat,3] float64 (bbox-centred), R [n,3,3] float64, both on the GPU -> [n,L,L,L] float32 summed density
+    of the rotated, box-centred atoms (`project(...).sum(dim=1)`)."""
+    if not (lig_coords.is_cuda and R.is_cuda):
+        raise _lib.DlpdError("project_clash_rotated needs CUDA tensors: libdlpd has no CPU path")
+    c = lig_coords.to(torch.float64).contiguous()
+    Rd = R.to(torch.float64).contiguous().reshape(-1, 9)
+    n, L = Rd.shape[0], int(box_size)
+    out = torch.empty(n, L, L, L, device=c.device, dtype=torch.float32)
+    lib = _lib.get_lib()
+    with torch.cuda.device(c.device):
+        _lib.check(lib, lib.dlpd_project_clash(_ptr(c), _ptr(Rd), c.shape[0], n, L, float(resolution), _ptr(out),
+                                              _stream_ptr(c.device)))
+    return out

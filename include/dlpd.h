@@ -111,6 +111,13 @@ int dlpd_profile_read(dlpd_plan* plan, double* ms, int* launches, void* stream);
 /* Number of kernels this library has launched in the calling process so far. */
 long long dlpd_launch_count(void);
 
+/* The in-loop ligand clash re-projection of dockSE3 (Docker.py:221-224) for n rotations in one launch:
+ * CoordsRotate + CoordsTranslate in float64, cast to float32, TypedCoords2Volume, sum over atom types.
+ *   coords device [nat][3] float64 bbox-centred ligand atoms (Angstrom); R device [n][9] float64;
+ *   out device [n][L^3] fp32 (overwritten) -- feed it to dlpd_search as lig_clash_rot. */
+int dlpd_project_clash(const double* coords, const double* R, int nat, int n, int L, float resolution, float* out,
+                       void* stream);
+
 /* ---- tuning / test switches (process-wide) -------------------------------------------------------------
  * DLPD_OPT_PLANE_MODE     which kernel runs the per-(channel, kz) plane stage: AUTO = one CTA per plane when the plane
  *                         fits an SM's shared memory (N <= 160), else a 4-CTA cluster with distributed shared memory;

@@ -127,3 +127,10 @@ def volume_correlate(v1, v2):
     out = torch.empty(B, C, 2 * L, 2 * L, 2 * L)
     _lib.check(lib(), lib().dlpd_volume_correlate(ptr(v1), ptr(v2), ptr(out), B, C, L, None))
     return out
+
+
+def project_clash(coords, R, L, res):
+    coords, R = coords.contiguous().double(), R.contiguous().double().reshape(-1, 9)
+    out = torch.empty(R.shape[0], L, L, L)
+    _lib.check(lib(), lib().dlpd_project_clash(ptr(coords), ptr(R), coords.shape[0], R.shape[0], L, float(res), ptr(out), None))
+    return out

@@ -205,3 +205,15 @@ def test_emu_search_prerotated_equals_search_of_rotated_volumes():
         s, x, y, z = O.best_pose(V)
         assert [int(v) for v in best_pre[i, 1:]] == [x, y, z]
         assert abs(float(best_pre[i, 0]) - s) <= 1e-4 * max(abs(s), 1e-3 * float(V.abs().max()))
+
+
+def test_emu_project_clash_matches_oracle():
+    """dlpd_project_clash vs the oracle's restatement of Docker.py:221-224 (atoms partly outside the box included)."""
+    g = torch.Generator().manual_seed(4)
+    L, res = 16, 1.25
+    coords = (torch.rand(200, 3, generator=g, dtype=torch.float64) - 0.5) * 22.0       # box is 20 A: some atoms poke out
+    Rs = R20[[0, 77, 1500]]
+    got = emu.project_clash(coords, Rs, L, res)
+    for i in range(3):
+        want = O.ligand_clash_volume(coords, Rs[i], L, res)
+        assert (got[i] - want).abs().max() <= 2e-6 * max(1.0, float(want.abs().max()))

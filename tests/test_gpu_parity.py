@@ -260,3 +260,18 @@ def test_search_full_size_128_matches_oracle():
     best, _ = eng.search(Rs, tau)
     eng.close()
     _check_against_oracle(best.cpu(), None, rec, lig, rec_clash, lig_clash, Rs, filt, tau)
+
+
+def test_project_clash_matches_oracle():
+    """CUDA re-projection of the rotated ligand atoms (Docker.py:221-224) vs the oracle, atoms partly outside the box."""
+    from deeplocalproteindocking_b200.volume import project_clash_rotated
+    g = torch.Generator().manual_seed(4)
+    L, res = 20, 1.25
+    coords = (torch.rand(400, 3, generator=g, dtype=torch.float64) - 0.5) * 27.0
+    Rs = R20[[0, 77, 1500, 1853]]
+    got = project_clash_rotated(coords.to(DEV), Rs.to(DEV), L, res).cpu()
+    for i in range(4):
+        want = O.ligand_clash_volume(coords, Rs[i], L, res)
+        assert (got[i] - want).abs().max() <= 2e-6 * max(1.0, float(want.abs().max()))
+    with pytest.raises(_lib.DlpdError):
+        project_clash_rotated(coords, Rs, L, res)                      # CPU tensors: no CPU path

@@ -27,12 +27,18 @@ for s in $STAGES; do
     ncu)
       timeout 900 ncu --set full --clock-control none --import-source on --kernel-name-base demangled \
         -k "regex:Epilogue|Plane|FwdZC|HiddenL1" -s 2 -c 6 -o $OUT/prof -f \
-        python bench.py --steps 1 --warmup 0 --cpu-rotations 0 --rot-batch 8 --max-rot 8 > $OUT/ncu_run.log 2>&1 ;;
+        python bench.py --steps 1 --warmup 0 --cpu-rotations 0 --rot-batch 32 --max-rot 32 > $OUT/ncu_run.log 2>&1 ;;
     sanitize)
       timeout 600 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -q -x -k "small or ties" \
         > $OUT/memcheck.log 2>&1
       timeout 600 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -q -x -k "small_matches_oracle and 8-4" \
         > $OUT/racecheck.log 2>&1 ;;
+    cfg5)
+      timeout 600 python bench.py --config 5 --steps 4 --warmup 3 --cpu-rotations 0 --rot-batch 32 --max-rot 32 > $OUT/bench_cfg5.log 2>&1; echo "rc=$?" >> $OUT/bench_cfg5.log ;;
+    cfg4)
+      timeout 600 python bench.py --config 4 --steps 8 --warmup 3 --cpu-rotations 0 > $OUT/bench_cfg4.log 2>&1; echo "rc=$?" >> $OUT/bench_cfg4.log ;;
+    cfg3)
+      timeout 600 python bench.py --config 3 --steps 8 --warmup 3 --cpu-rotations 0 > $OUT/bench_cfg3.log 2>&1; echo "rc=$?" >> $OUT/bench_cfg3.log ;;
     scale2)
       timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 \
         bench.py --gpus 2 --steps 10 --warmup 3 > $OUT/bench_2gpu.log 2>&1 ;;
