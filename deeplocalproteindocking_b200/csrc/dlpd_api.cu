@@ -107,7 +107,7 @@ template <class K> static int launch(dim3 g, const typename K::Params& p, dlpd_s
 
 // kernels that span a thread-block cluster of K::CL CTAs (distributed shared memory)
 template <class K>
-__global__ void __launch_bounds__(K::NT) dlpd_cluster_kernel(const __grid_constant__ typename K::Params p) {
+__global__ void __launch_bounds__(K::NT, K::MINB) dlpd_cluster_kernel(const __grid_constant__ typename K::Params p) {
     extern __shared__ __align__(16) char smem[];
     namespace cg = cooperative_groups;
     cg::cluster_group cl = cg::this_cluster();
@@ -129,6 +129,7 @@ template <class K> static int launch_cluster(unsigned clusters, const typename K
     if (dev < 64 && !configured[dev]) {
         if (K::SMEM > 48 * 1024)
             CU(cudaFuncSetAttribute(dlpd_cluster_kernel<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+        CU(cudaFuncSetAttribute(dlpd_cluster_kernel<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured[dev] = true;
     }
     cudaLaunchConfig_t cfg = {};
@@ -161,7 +162,8 @@ template <class K> static int launch_cluster(unsigned clusters, const typename K
 template <int L> struct Tile {
     static constexpr int FWD_YT = (L <= 40) ? L : ((L % 40 == 0) ? 40 : 32);      // y lines per FwdZ CTA
     static constexpr int INV_YT = ((2 * L) % 8 == 0) ? 8 : (((2 * L) % 4 == 0) ? 4 : 2);
-    static constexpr int CL_YT = (L % 8 == 0) ? 8 : ((L % 4 == 0) ? 4 : 2);   // y lines per FwdZC CTA
+    // y lines per FwdZC CTA (4 at L = 128: 68 KB of shared memory, three resident CTAs instead of one)
+    static constexpr int CL_YT = (L >= 128) ? 4 : ((L % 8 == 0) ? 8 : ((L % 4 == 0) ? 4 : 2));
     static constexpr int CL_CG = 8;                                           // channels per FwdZC CTA
 };
 

@@ -572,15 +572,16 @@ template <int L_, int CL_> struct PlaneX {
     static constexpr int SMEM = (M * NP + N) * (int)sizeof(cpx);
     static_assert(CL_ == 4 && N % CL_ == 0 && M % 2 == 0 && N % XB == 0, "cluster shape");
 
+    static constexpr int MINB = (SMEM <= 56 * 1024) ? 4 : 1;   // resident CTAs per SM the register budget is cut for
     struct FoldS1 {          // element e = j of column l = y of slab q: w_N^{q j} (x[j] + i^q x[j + M])
-        const cpx* in;       // S1 plane [x < L][y < L]
+        const cpx* pl;       // staged S1 plane: pl[j][y] = x[j][y], pl[j][L + y] = x[j + M][y]   (j < M, y < L)
         const cpx* tw;
         int q;
+        cpx iq;              // i^q
         DLPD_DEV cpx operator()(int l, int e) const {
-            const cpx a = in[e * L + l], b = in[(e + M) * L + l];
-            const cpx ib = q == 0 ? b : q == 1 ? cmul_i(b) : q == 2 ? make_float2(-b.x, -b.y) : make_float2(b.y, -b.x);
-            const cpx v = cadd(a, ib);
-            return q == 0 ? v : cmul(v, tw[e * q]);
+            const cpx a = pl[e * NP + l], b = pl[e * NP + L + l];
+            const cpx w = tw[e * q];                                   // q = 0: tw[0] = 1
+            return cadd(cmul(a, w), cmul(b, cmul(w, iq)));
         }
     };
     struct MulSpec {         // element e = ky' of local row l (global row kx' = q M + l); spectrum stored [ky'][kx']
@@ -595,11 +596,30 @@ template <int L_, int CL_> struct PlaneX {
         cpx* pl = reinterpret_cast<cpx*>(smem);        // [M local rows kx'][y], pitch NP
         cpx* tw = pl + M * NP;
         const int pair = cid % p.P, kz = (cid / p.P) % N, c = cid / (p.P * N);
-        DLPD_FOR_TASKS(t, N, NT) tw[t] = p.tw[t];
-        DLPD_SYNC();
         const long plane = ((long)pair * p.C + c) * N + kz;
-        // forward x on the columns y < L: fold from global, then the M-point transform
-        GlobalIn<FoldS1> in{FoldS1{p.in + plane * L * L, tw, q}};
+        // stage the whole S1 plane (L x L, read by all CL CTAs of the cluster) in the still empty slab with asynchronous
+        // copies -- every load is in flight at once instead of one dependent round trip per butterfly task: row j < M
+        // holds x = j in its left half (columns y < L) and x = j + M in its right half, which the y transform only
+        // fills later
+        {
+            const cpx* s1 = p.in + plane * L * L;
+            DLPD_FOR_TASKS(t, L * L, NT) {
+                const int x = t / L, y = t - x * L;
+                cp_async8(pl + (x % M) * NP + (x / M) * L + y, s1 + t);
+            }
+        }
+        const cpx* spec = p.spec ? p.spec + (long)pair * p.spec_pair_stride + ((long)c * N + kz) * N * N + q * M : nullptr;
+        if (spec != nullptr) {           // my quarter of the receptor plane (M x 8 bytes per ky' row) -> L2, used 3 passes later
+            constexpr int LPR = (M * (int)sizeof(cpx) + 127) / 128 + 1;
+            DLPD_FOR_TASKS(t, N * LPR, NT)
+                prefetch_l2(reinterpret_cast<const char*>(spec + (long)(t / LPR) * N) + 128 * (t % LPR));
+        }
+        DLPD_FOR_TASKS(t, N, NT) tw[t] = p.tw[t];
+        cp_async_wait_all();
+        DLPD_SYNC();
+        // forward x on the columns y < L: radix-CL fold in place, then the M-point transform
+        const cpx iq = q == 0 ? make_float2(1.f, 0.f) : q == 1 ? make_float2(0.f, 1.f) : q == 2 ? make_float2(-1.f, 0.f) : make_float2(0.f, -1.f);
+        GlobalIn<FoldS1> in{FoldS1{pl, tw, q, iq}};
         fft_pass<PASS_DIF, XA, 1, L, M, M, N, NP, NT>(pl, tw, LineMul<1>(), in);
         if constexpr (XB > 1) fft_pass<PASS_DIF, XB, 1, L, M, XB, N, NP, NT>(pl, tw, LineMul<1>());
         fft_fwd_head<N, M, 1, NT>(pl, tw, LineMul<NP>());                       // along y, my rows
@@ -613,7 +633,6 @@ template <int L_, int CL_> struct PlaneX {
             }
             return;
         }
-        const cpx* spec = p.spec + (long)pair * p.spec_pair_stride + ((long)c * N + kz) * N * N + q * M;
         PointMul<MulSpec> mul{MulSpec{spec}};
         fft_mid<N, M, 1, NT>(pl, tw, LineMul<NP>(), mul);                       // y tail . multiply . inverse y tail
         fft_inv_head<N, M, 1, NT>(pl, tw, LineMul<NP>());                       // inverse y
