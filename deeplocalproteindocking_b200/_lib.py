@@ -40,7 +40,8 @@ SIGNATURES = {
 }
 
 CENTER_MODES = {"box": 0, "grid": 1}
-OPTIONS = {"plane_mode": 1, "epilogue_tile": 2}                  # DLPD_OPT_* of include/dlpd.h
+OPTIONS = {"plane_mode": 1, "epilogue_tile": 2, "epilogue_kind": 3}      # DLPD_OPT_* of include/dlpd.h
+EPILOGUE_KINDS = {"auto": 0, "classic": 1, "pipelined": 2}
 PLANE_MODES = {"auto": 0, "single": 1, "cluster": 2}
 
 
@@ -84,4 +85,6 @@ def set_option(name: str, value) -> None:
     lib = get_lib()
     if name == "plane_mode" and isinstance(value, str):
         value = PLANE_MODES[value]
+    if name == "epilogue_kind" and isinstance(value, str):
+        value = EPILOGUE_KINDS[value]
     check(lib, lib.dlpd_set_option(OPTIONS[name], int(value)))

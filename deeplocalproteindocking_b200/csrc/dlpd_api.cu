@@ -212,6 +212,10 @@ template <int L> static int launch_fwdzc_t(const FwdZCParams& p, int P, dlpd_str
 static constexpr int SMEM_MAX = 227 * 1024;
 static int g_plane_mode = DLPD_PLANE_AUTO;
 static int g_epi_tile = 0;               // 0 = automatic, 1 / 2 = force 2x1 / 2x2 tiles in the epilogue
+static int g_epi_kind = DLPD_EPILOGUE_AUTO;
+#ifndef DLPD_EPILOGUE_DEFAULT_PIPELINED
+#define DLPD_EPILOGUE_DEFAULT_PIPELINED 0
+#endif
 template <int L> struct HasPlaneX { static constexpr bool value = (L == 8 || L == 16 || L == 20 || L == 40 || L == 64 || L == 80 || L == 128); };
 template <int L> struct HasPlane { static constexpr bool value = ((2 * L) * (2 * L + 1) + 2 * L) * 8 <= SMEM_MAX; };
 template <int L> static int launch_plane_t(const PlaneParams& p, dlpd_stream_t st) {
@@ -511,7 +515,26 @@ static int launch_epilogue_t(dlpd_plan* p, int n, int P, float tau, float* out_s
     }
 }
 template <int L, int C0, int C1, int H>
+static int launch_epilogue_pipe(dlpd_plan* p, int n, int P, float tau, float* out_scores, const CandArgs& ca, dlpd_stream_t st) {
+    typedef EpiloguePipe<L, C0, C1, H> K;
+    if constexpr (K::SMEM <= SMEM_MAX) {
+        typename K::Params e;
+        e.s2_0 = p->s2_0; e.h1 = p->h1; e.best = p->best; e.score_out = out_scores;
+        e.tw0 = p->tw0; e.n_rot = n; e.tau = tau;
+        e.cand = ca.cand; e.cand_count = ca.count; e.cand_cap = ca.cap; e.cand_key = ca.key; e.rot_base = ca.rot_base;
+        e.n_tiles = P * L * L;                      // 2x2 groups
+        e.grid = e.n_tiles < p->sm_count ? e.n_tiles : p->sm_count;
+        fill_filter(p, e.filt);
+        return launch<K>(dim3(e.grid), e, st);
+    } else {
+        return fail(DLPD_EINVAL, "the pipelined epilogue does not fit shared memory at this box size");
+    }
+}
+template <int L, int C0, int C1, int H>
 static int launch_epilogue(dlpd_plan* p, int n, int P, float tau, float* out_scores, const CandArgs& ca, dlpd_stream_t st) {
+    const bool pipe_fits = EpiloguePipe<L, C0, C1, H>::SMEM <= SMEM_MAX;
+    if (g_epi_kind == DLPD_EPILOGUE_PIPELINED || (g_epi_kind == DLPD_EPILOGUE_AUTO && DLPD_EPILOGUE_DEFAULT_PIPELINED && pipe_fits && !g_epi_tile))
+        return launch_epilogue_pipe<L, C0, C1, H>(p, n, P, tau, out_scores, ca, st);
     const bool fits2 = Epilogue<L, C0, C1, H, 2>::SMEM <= SMEM_MAX;
     const int ty = g_epi_tile ? g_epi_tile : (fits2 ? 2 : 1);
     return ty == 2 ? launch_epilogue_t<L, C0, C1, H, 2>(p, n, P, tau, out_scores, ca, st)
@@ -667,6 +690,10 @@ extern "C" int dlpd_set_option(int key, int value) {
         case DLPD_OPT_PLANE_MODE:
             if (value < DLPD_PLANE_AUTO || value > DLPD_PLANE_CLUSTER) return fail(DLPD_EINVAL, "bad plane mode");
             g_plane_mode = value;
+            return 0;
+        case DLPD_OPT_EPILOGUE_KIND:
+            if (value < DLPD_EPILOGUE_AUTO || value > DLPD_EPILOGUE_PIPELINED) return fail(DLPD_EINVAL, "bad epilogue kind");
+            g_epi_kind = value;
             return 0;
         case DLPD_OPT_EPILOGUE_TILE:
             if (value < 0 || value > 2) return fail(DLPD_EINVAL, "epilogue tile must be 0 (auto), 1 (2x1) or 2 (2x2)");

@@ -407,13 +407,22 @@ template <int L_> struct Plane {
                                  ? DLPD_PLANE_TEAMS : 1;
     static constexpr int TNT = NT / G;
     static constexpr int PFT = (G > 1) ? TNT : NT;           // threads that issue the prefetches
+    // DLPD_ABLATE_* (never defined in the shipped build): timing experiments that remove one memory stream at a time
     struct LoadS1 {          // element e = x of column l = y
         const cpx* in;
+#if defined(DLPD_ABLATE_PLANE_LOAD)
+        DLPD_DEV cpx operator()(int l, int e) const { return make_float2((float)l, (float)e); }
+#else
         DLPD_DEV cpx operator()(int l, int e) const { return in[e * L + l]; }
+#endif
     };
     struct MulSpec {         // element e = ky' of row l = kx'
         const cpx* spec;
+#if defined(DLPD_ABLATE_PLANE_MUL)
+        DLPD_DEV cpx operator()(int l, int e) const { return make_float2(1.0f + (float)l, (float)e); }
+#else
         DLPD_DEV cpx operator()(int l, int e) const { return __ldg(spec + e * N + l); }
+#endif
     };
     struct StoreS2 {         // element e = x of column l = y, natural [x][y] rows
         cpx* out;
@@ -427,7 +436,11 @@ template <int L_> struct Plane {
     struct StoreS2TiledPair {   // elements x = e (even) and e + 1 of column y = l: one 16-byte store, 512 contiguous bytes per warp
         cpx* out;
         DLPD_DEV void operator()(int l, int e, cpx v0, cpx v1) const {
+#if defined(DLPD_ABLATE_PLANE_STORE)
+            if (v0.x == 1.2345e30f) out[0] = v1;
+#else
             store_cpx2(out + ((((e >> 1) * L) + (l >> 1)) << 2) + ((l & 1) << 1), v0, v1);
+#endif
         }
     };
     // grid: x = P * N * C  with the pair index fastest (CTAs that share a receptor plane run together -> L2 reuse)
@@ -942,10 +955,24 @@ template <int L_, int C0, int C1, int H, int TY_ = 2> struct Epilogue {
     template <class TM>
     static DLPD_DEV void score_tile(const Params& p, const TM& tm, cpx* b0, const cpx* h1, const cpx* tw0, int pair, int x0, int y0,
                                     unsigned long long& bestA, unsigned long long& bestB) {
-        const int rotA = 2 * pair, rotB = 2 * pair + 1;
-        const bool hasB = rotB < p.n_rot;
+        transform_tile(tm, b0, tw0);
+        score_voxels(p, tm, b0, h1, pair, x0, y0, bestA, bestB);
+    }
+
+    // inverse z transform of the NL0 lines of a tile, in place
+    template <class TM> static DLPD_DEV void transform_tile(const TM& tm, cpx* b0, const cpx* tw0) {
+#if !defined(DLPD_ABLATE_EPI_FFT)
         team_inv_tail<N, NL0, NL0>(tm, b0, tw0, LineMul<1>());
         team_inv_head<N, NL0, NL0>(tm, b0, tw0, LineMul<1>());
+#endif
+    }
+
+    // filter, clash mask and running argmin over the XY * N voxels of a transformed tile
+    template <class TM>
+    static DLPD_DEV void score_voxels(const Params& p, const TM& tm, const cpx* b0, const cpx* h1, int pair, int x0, int y0,
+                                      unsigned long long& bestA, unsigned long long& bestB) {
+        const int rotA = 2 * pair, rotB = 2 * pair + 1;
+        const bool hasB = rotB < p.n_rot;
         DLPD_TEAM_TASKS(tm, t, XY * N) {
             const int xy = t % XY, z = t / XY;
             const cpx* v0 = b0 + z * NL0 + xy;
@@ -953,12 +980,16 @@ template <int L_, int C0, int C1, int H, int TY_ = 2> struct Epilogue {
             float2 h[H];                                        // (rotA, rotB) per hidden unit
             DLPD_UNROLL
             for (int j = 0; j < H; ++j) h[j] = hz[j];
+#if defined(DLPD_ABLATE_EPI_MLP)
+            h[0] = v0[0];
+#else
             DLPD_UNROLL
             for (int c = 0; c < C0; ++c) {
                 const float2 v = v0[c * XY];
                 DLPD_UNROLL
                 for (int j = 0; j < H; ++j) h[j] = ffma2_(dup2(p.filt.W1t[c * H + j]), v, h[j]);
             }
+#endif
             float2 sc = dup2(p.filt.b2);
             DLPD_UNROLL
             for (int j = 0; j < H; ++j) sc = ffma2_(dup2(p.filt.W2[j]), make_float2(fmaxf(h[j].x, 0.0f), fmaxf(h[j].y, 0.0f)), sc);
@@ -1009,7 +1040,9 @@ template <int L_, int C0, int C1, int H, int TY_ = 2> struct Epilogue {
                 bestA = bestB = ~0ull;
             }
             if (producer) {
+#if !defined(DLPD_ABLATE_EPI_LOAD)
                 if (tile + p.grid < p.n_tiles) issue_loads(p, tile + p.grid, bufs + (slot ^ 1) * BUF, hbufs + (slot ^ 1) * HB);
+#endif
                 cp_async_commit();
                 cp_async_wait_pending();
             }
@@ -1017,6 +1050,186 @@ template <int L_, int C0, int C1, int H, int TY_ = 2> struct Epilogue {
                 score_tile(p, tm, bufs + slot * BUF, hbufs + slot * HB, tw0, pair, 2 * tile_xh(r), tile_y0(r), bestA, bestB);
         }
         if (cur_pair >= 0) flush_best(p, cur_pair, bestA, bestB, red);
+    }
+};
+
+// ------------------------------------------------------------------------------------------------------
+// EpiloguePipe: the same per-tile work as Epilogue, organised as a three-stage pipeline inside one persistent CTA so
+// that the inverse z transforms of one tile (shared-memory / latency bound, ~1/3 of the FP32 pipe) run WHILE the filter
+// of the previous tile (pure FFMA2, pipe bound) executes:
+//     producer warps : cp.async of half-tile it + 2.. into a ring of NB buffers            (waits FREE, signals FULL)
+//     FFT team       : inverse z transform of half-tile it + 1, in place                   (waits FULL, signals XF)
+//     filter team    : 48 -> 24 -> 1 filter, clash mask, argmin / candidates of half-tile it (waits XF,  signals FREE)
+// A half-tile is 2 x 1 (x,y) columns (one y of a 2x2 group): four half-tile buffers fit where two 2x2 buffers did.  The
+// two halves of a group are consecutive iterations of the same CTA and share the group's level-1 column h1, which
+// travels with the first half in a ring of NHB = 3 buffers.  The stages hand buffers over with named barriers
+// (bar.arrive by the finishing stage, bar.sync by the waiting one): FULL/XF/FREE x NB buffers + one barrier inside each team.
+// ------------------------------------------------------------------------------------------------------
+#ifndef DLPD_PIPE_NFFT
+#define DLPD_PIPE_NFFT 352
+#endif
+#ifndef DLPD_PIPE_NMLP
+#define DLPD_PIPE_NMLP 320
+#endif
+#ifndef DLPD_PIPE_NPROD
+#define DLPD_PIPE_NPROD 128
+#endif
+
+template <int L_, int C0, int C1, int H> struct EpiloguePipe {
+    typedef Epilogue<L_, C0, C1, H, 1> E;            // half-tile geometry, loads and scoring code
+    typedef EpiParams<C0, C1, H> Params;
+    static constexpr int L = L_, N = 2 * L_, N1 = L_, T = L_;
+    static constexpr int NL0 = E::NL0, BUF = N * NL0, HB = N1 * H;
+    static constexpr int NB = 4, NHB = 3;
+    static constexpr bool BIG = N >= 128;
+    static constexpr int NPROD = BIG ? DLPD_PIPE_NPROD : 64, PW = NPROD / 2;      // two producer groups: even / odd iterations
+    static constexpr int NFFT = BIG ? DLPD_PIPE_NFFT : 64, NMLP = BIG ? DLPD_PIPE_NMLP : 64;
+    static constexpr int NT = NPROD + NFFT + NMLP;
+    static constexpr int SMEM = (NB * BUF + NHB * HB + N) * (int)sizeof(cpx) + 64 * 8;
+    static constexpr int BAR_FFT = 1, BAR_MLP = 2, BAR_FULL = 3, BAR_XF = 3 + NB, BAR_FREE = 3 + 2 * NB;
+    static_assert(3 + 3 * NB <= 16 && PW % 32 == 0 && NFFT % 32 == 0 && NMLP % 32 == 0 && HB % 2 == 0, "pipeline shape");
+
+    struct Item { int pair, r4, half; };
+    // iteration `it` of CTA bx: half `it & 1` of 2x2 group bx + (it >> 1) * grid
+    static DLPD_DEV Item item(const Params& p, int bx, int it) {
+        const int g = bx + (it >> 1) * p.grid;
+        return Item{g / (T * T), g % (T * T), it & 1};
+    }
+
+    // copies of one half-tile (and, with its first half, the group's h1 column) by PW threads; tp = index among them
+    static DLPD_DEV void issue_loads(const Params& p, const Item& w, cpx* b0, cpx* hb, int tp) {
+        const cpx* s = p.s2_0 + ((long)w.pair * (C0 + 1) * N * T * T + w.r4) * 4 + 2 * w.half;
+        int c = tp / N, kz = tp % N;
+        const cpx* src = s + (long)tp * (T * T) * 4;                     // q = c*N + kz: 16 contiguous bytes per row
+        for (int q = tp; q < (C0 + 1) * N; q += PW) {
+            cp_async16(b0 + kz * NL0 + c * 2, src);
+            src += (long)PW * T * T * 4;
+            kz += PW % N;
+            c += PW / N;
+            if (kz >= N) { kz -= N; ++c; }
+        }
+        if (w.half == 0) {
+            const cpx* hs = p.h1 + ((long)w.pair * T * T + w.r4) * HB;
+            for (int t = tp; t < HB / 2; t += PW) cp_async16(hb + 2 * t, hs + 2 * t);
+        }
+    }
+
+#if !defined(DLPD_EMU)
+    static DLPD_DEV unsigned long long team_min_u64(unsigned long long v, unsigned long long* red, int tmid) {
+        DLPD_UNROLL
+        for (int o = 16; o > 0; o >>= 1) {
+            unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+            v = w < v ? w : v;
+        }
+        const int lane = tmid & 31, warp = tmid >> 5;
+        if (lane == 0) red[warp] = v;
+        named_barrier_sync(BAR_MLP, NMLP);
+        if (warp == 0) {
+            v = lane < NMLP / 32 ? red[lane] : ~0ull;
+            DLPD_UNROLL
+            for (int o = 16; o > 0; o >>= 1) {
+                unsigned long long w = __shfl_xor_sync(0xffffffffu, v, o);
+                v = w < v ? w : v;
+            }
+        }
+        named_barrier_sync(BAR_MLP, NMLP);
+        return v;      // valid in team thread 0
+    }
+#endif
+
+    static DLPD_DEV void flush_best(const Params& p, int pair, unsigned long long bestA, unsigned long long bestB,
+                                    unsigned long long* red, int tmid) {
+        const int rotA = 2 * pair, rotB = 2 * pair + 1;
+        const bool hasB = rotB < p.n_rot;
+#if defined(DLPD_EMU)
+        (void)red; (void)tmid;
+        if (bestA < p.best[rotA]) p.best[rotA] = bestA;
+        if (hasB && bestB < p.best[rotB]) p.best[rotB] = bestB;
+#else
+        bestA = team_min_u64(bestA, red, tmid);
+        bestB = team_min_u64(bestB, red, tmid);
+        if (tmid == 0) {
+            atomicMin(p.best + rotA, bestA);
+            if (hasB) atomicMin(p.best + rotB, bestB);
+        }
+#endif
+    }
+
+    // grid: x = p.grid persistent CTAs; p.n_tiles = number of 2x2 groups = P * T * T
+    static DLPD_DEV void body(const Params& p, int bx, int, int, char* smem) {
+        cpx* bufs = reinterpret_cast<cpx*>(smem);      // [NB][kz][NL0]
+        cpx* hbufs = bufs + NB * BUF;                  // [NHB][z'][H]
+        cpx* tw0 = hbufs + NHB * HB;
+        unsigned long long* red = reinterpret_cast<unsigned long long*>(tw0 + N);
+        const int my_groups = bx < p.n_tiles ? (p.n_tiles - bx + p.grid - 1) / p.grid : 0;
+        const int n_it = 2 * my_groups;
+        DLPD_FOR_TASKS(t, N, NT) tw0[t] = p.tw0[t];
+        DLPD_SYNC();
+#if defined(DLPD_EMU)
+        // one emulated thread plays the three roles in turn, copies complete at once
+        unsigned long long bestA = ~0ull, bestB = ~0ull;
+        int cur_pair = -1;
+        const CtaTeam<1> tm;
+        for (int it = 0; it < n_it; ++it) {
+            const Item w = item(p, bx, it);
+            cpx* b0 = bufs + (it % NB) * BUF;
+            cpx* hb = hbufs + ((it >> 1) % NHB) * HB;
+            for (int tp = 0; tp < PW; ++tp) issue_loads(p, w, b0, hb, tp);
+            E::transform_tile(tm, b0, tw0);
+            if (w.pair != cur_pair) {
+                if (cur_pair >= 0) flush_best(p, cur_pair, bestA, bestB, red, 0);
+                cur_pair = w.pair;
+                bestA = bestB = ~0ull;
+            }
+            E::score_voxels(p, tm, b0, hb, w.pair, 2 * (w.r4 / T), 2 * (w.r4 % T) + w.half, bestA, bestB);
+        }
+        if (cur_pair >= 0) flush_best(p, cur_pair, bestA, bestB, red, 0);
+#else
+        const int tid = (int)threadIdx.x;
+        if (tid < NPROD) {
+            // ---- producers: group `par` serves the iterations of its parity (buffer index has the same parity)
+            const int par = tid / PW, tp = tid % PW;
+            for (int it = par; it < n_it; it += 2) {
+                const int b = it % NB;
+                if (it >= NB) named_barrier_sync(BAR_FREE + b, PW + NMLP);          // filter team is done with buffer b
+#if !defined(DLPD_ABLATE_EPI_LOAD)
+                issue_loads(p, item(p, bx, it), bufs + b * BUF, hbufs + ((it >> 1) % NHB) * HB, tp);
+#endif
+                cp_async_commit();
+                cp_async_wait_pending();
+                named_barrier_arrive(BAR_FULL + b, PW + NFFT);
+            }
+        } else if (tid < NPROD + NFFT) {
+            // ---- FFT team
+            const SubTeam<NFFT> tm{tid - NPROD, BAR_FFT};
+            for (int it = 0; it < n_it; ++it) {
+                const int b = it % NB;
+                named_barrier_sync(BAR_FULL + b, PW + NFFT);
+                E::transform_tile(tm, bufs + b * BUF, tw0);
+                named_barrier_arrive(BAR_XF + b, NFFT + NMLP);
+            }
+        } else {
+            // ---- filter team
+            const int tmid = tid - NPROD - NFFT;
+            const SubTeam<NMLP> tm{tmid, BAR_MLP};
+            unsigned long long bestA = ~0ull, bestB = ~0ull;
+            int cur_pair = -1;
+            for (int it = 0; it < n_it; ++it) {
+                const int b = it % NB;
+                const Item w = item(p, bx, it);
+                if (w.pair != cur_pair) {
+                    if (cur_pair >= 0) flush_best(p, cur_pair, bestA, bestB, red, tmid);
+                    cur_pair = w.pair;
+                    bestA = bestB = ~0ull;
+                }
+                named_barrier_sync(BAR_XF + b, NFFT + NMLP);
+                E::score_voxels(p, tm, bufs + b * BUF, hbufs + ((it >> 1) % NHB) * HB, w.pair, 2 * (w.r4 / T), 2 * (w.r4 % T) + w.half,
+                                bestA, bestB);
+                if (it + NB < n_it) named_barrier_arrive(BAR_FREE + b, PW + NMLP);
+            }
+            if (cur_pair >= 0) flush_best(p, cur_pair, bestA, bestB, red, tmid);
+        }
+#endif
     }
 };
 

@@ -41,6 +41,7 @@
   #define DLPD_FOR_TEAMS(g, G, TNT) for (int g = 0; g < (G); ++g)
   #define DLPD_TEAM_TID(TNT) 0
   static inline void named_barrier_sync(int, int) {}
+  static inline void named_barrier_arrive(int, int) {}
   static inline void store_cpx2(float2* dst, float2 a, float2 b) { dst[0] = a; dst[1] = b; }
   static inline unsigned int atomic_inc_u32(unsigned int* p) { return (*p)++; }
   static inline void atomic_add_f32(float* p, float v) { *p += v; }
@@ -82,6 +83,7 @@
   #define DLPD_FOR_TEAMS(g, G, TNT) for (int g = threadIdx.x / (TNT), g##_once = 1; g##_once; g##_once = 0)
   #define DLPD_TEAM_TID(TNT) ((int)(threadIdx.x % (TNT)))
   DLPD_DEV void named_barrier_sync(int id, int nthreads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
+  DLPD_DEV void named_barrier_arrive(int id, int nthreads) { asm volatile("bar.arrive %0, %1;" ::"r"(id), "r"(nthreads) : "memory"); }
   DLPD_DEV void store_cpx2(float2* dst, float2 a, float2 b) {       // 16-byte aligned destination
       *reinterpret_cast<float4*>(dst) = make_float4(a.x, a.y, b.x, b.y);
   }

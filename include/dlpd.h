@@ -125,9 +125,14 @@ int dlpd_project_clash(const double* coords, const double* R, int nat, int n, in
  *                         compiled (box sizes 8, 16, 20, 40, 64, 80, 128).  The receptor spectra of
  *                         a plan are laid out for the mode in force at dlpd_set_receptor time: do not switch between
  *                         dlpd_set_receptor and dlpd_search.
- * DLPD_OPT_EPILOGUE_TILE  0 = automatic, 1 = 2x1, 2 = 2x2 (x,y) columns per epilogue tile */
+ * DLPD_OPT_EPILOGUE_TILE  0 = automatic, 1 = 2x1, 2 = 2x2 (x,y) columns per epilogue tile (classic epilogue)
+ * DLPD_OPT_EPILOGUE_KIND  AUTO / CLASSIC / PIPELINED, see below */
 #define DLPD_OPT_PLANE_MODE 1
 #define DLPD_OPT_EPILOGUE_TILE 2
+#define DLPD_OPT_EPILOGUE_KIND 3
+#define DLPD_EPILOGUE_AUTO 0
+#define DLPD_EPILOGUE_CLASSIC 1     /* one consumer team: transform then filter, next tile prefetched            */
+#define DLPD_EPILOGUE_PIPELINED 2   /* load / transform / filter of consecutive half-tiles overlap (N <= 160)    */
 #define DLPD_PLANE_AUTO 0
 #define DLPD_PLANE_SINGLE 1
 #define DLPD_PLANE_CLUSTER 2

@@ -105,7 +105,8 @@ class EmuPlan:
         return best
 
 
-OPT_PLANE_MODE, OPT_EPILOGUE_TILE = 1, 2
+OPT_PLANE_MODE, OPT_EPILOGUE_TILE, OPT_EPILOGUE_KIND = 1, 2, 3
+EPILOGUE_AUTO, EPILOGUE_CLASSIC, EPILOGUE_PIPELINED = 0, 1, 2
 PLANE_AUTO, PLANE_SINGLE, PLANE_CLUSTER = 0, 1, 2
 
 

@@ -217,3 +217,19 @@ def test_emu_project_clash_matches_oracle():
     for i in range(3):
         want = O.ligand_clash_volume(coords, Rs[i], L, res)
         assert (got[i] - want).abs().max() <= 2e-6 * max(1.0, float(want.abs().max()))
+
+
+@pytest.fixture
+def pipelined_epilogue():
+    emu.set_option(emu.OPT_EPILOGUE_KIND, emu.EPILOGUE_PIPELINED)
+    yield
+    emu.set_option(emu.OPT_EPILOGUE_KIND, emu.EPILOGUE_AUTO)
+
+
+@pytest.mark.parametrize("L,C0,C1,H,n", [(8, 4, 6, 5, 3), (20, 4, 6, 5, 3), (16, 16, 32, 24, 2)])
+def test_emu_pipelined_epilogue_matches_oracle(L, C0, C1, H, n, pipelined_epilogue):
+    test_emu_search_matches_oracle(L, C0, C1, H, n)
+
+
+def test_emu_pipelined_epilogue_candidates(pipelined_epilogue):
+    test_emu_candidates_are_exactly_the_translations_below_the_threshold()

@@ -275,3 +275,39 @@ def test_project_clash_matches_oracle():
         assert (got[i] - want).abs().max() <= 2e-6 * max(1.0, float(want.abs().max()))
     with pytest.raises(_lib.DlpdError):
         project_clash_rotated(coords, Rs, L, res)                      # CPU tensors: no CPU path
+
+
+# ---- pipelined epilogue (load / transform / filter stages overlapped with named barriers) --------------------------
+@pytest.fixture
+def pipelined_epilogue():
+    _lib.set_option("epilogue_kind", "pipelined")
+    yield
+    _lib.set_option("epilogue_kind", "auto")
+
+
+@pytest.mark.parametrize("L,C0,C1,H,n", [(8, 4, 6, 5, 5), (16, 4, 6, 5, 4), (20, 4, 6, 5, 3), (8, 16, 32, 24, 3),
+                                         (16, 16, 32, 24, 2), (20, 16, 32, 24, 5)])
+def test_pipelined_epilogue_small_matches_oracle(L, C0, C1, H, n, pipelined_epilogue):
+    test_search_small_matches_oracle(L, C0, C1, H, n)
+
+
+def test_pipelined_epilogue_80_matches_oracle(pipelined_epilogue):
+    test_search_full_size_80_matches_oracle()
+
+
+def test_pipelined_epilogue_80_many_rotations_equal_classic():
+    """33 rotations (17 pairs, odd tail) at L=80 through both epilogues: identical best poses and scores (same arithmetic)."""
+    L, C0, C1 = 80, 16, 32
+    rec, rec_clash = synthetic.learned_volumes(L, (C0, C1), seed=31)
+    lig, lig_clash = synthetic.learned_volumes(L, (C0, C1), seed=32)
+    filt = O.FilterWeights.random(C0 + C1, seed=33)
+    Rs = R20[torch.arange(33) * 53 + 2]
+    out = []
+    for kind in ("classic", "pipelined"):
+        _lib.set_option("epilogue_kind", kind)
+        eng = DockingSearch(L, (C0, C1), max_rot=16, device=DEV)
+        eng.set_receptor(rec, rec_clash); eng.set_ligand(lig, lig_clash); eng.set_filter((filt.W1, filt.b1, filt.W2, filt.b2))
+        out.append(eng.search(Rs, 30.0)[0].cpu())
+        eng.close()
+    _lib.set_option("epilogue_kind", "auto")
+    assert torch.equal(out[0], out[1])
