@@ -49,3 +49,27 @@ def merge_top_lists(local_top: Sequence[Tuple[int, int, int, int, float]], K: in
     merged = [t for part in gathered for t in part]
     merged.sort(key=lambda t: (t[4], t[0]))
     return merged[:K]
+
+
+def dock_sharded(docker, ureceptor, uligand, group=None):
+    """`Docker.dockSE3` with the rotation set sharded over the ranks of `group` (one process per GPU): every rank scores
+    rotations {i : i mod W = rank}, then one all_gather of the per-rotation best poses and one of the per-rank top lists
+    reproduce the single-process result; rank 0 writes the pose file (Docker.py:107-133).  Returns (best [N_rot,4], top)."""
+    if not dist.is_initialized() or dist.get_world_size(group) == 1:
+        docker.dockSE3(ureceptor, uligand)
+        return docker.best_per_rotation, docker.top_list
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    n_rot = len(docker.rot)
+    docker.dockSE3(ureceptor, uligand, rotation_subset=shard_indices(n_rot, rank, world), write=False)
+    local = docker.best_per_rotation.to(docker.device)
+    best = gather_best(local, n_rot, rank, world, group=group).cpu()
+    docker.best_per_rotation = best
+    if docker.max_conf > 1:
+        docker.top_list = merge_top_lists(docker.top_list, docker.max_conf, group=group)
+    else:
+        items = [(i, int(best[i, 1]), int(best[i, 2]), int(best[i, 3]), float(best[i, 0])) for i in range(n_rot)]
+        items.sort(key=lambda t: t[4])
+        docker.top_list = items[:docker.max_conf]
+    if rank == 0:
+        docker.write_conformations()
+    return best, docker.top_list

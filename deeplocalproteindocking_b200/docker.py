@@ -181,7 +181,7 @@ class Docker:
         return self._engine
 
     # ---- the search ----------------------------------------------------------------------------------------
-    def dockSE3(self, ureceptor, uligand, batch_size=None, rotation_subset: Optional[torch.Tensor] = None):
+    def dockSE3(self, ureceptor, uligand, batch_size=None, rotation_subset: Optional[torch.Tensor] = None, write: bool = True):
         """Dock two proteins (Docker.py:184-238).  `batch_size` is accepted for call compatibility (the reference
         scores that many rotations per step; here `rot_batch` rotations go into every fused call)."""
         self.top_list = []
@@ -238,7 +238,8 @@ class Docker:
                 items = [(int(r), int(b[j, 1]), int(b[j, 2]), int(b[j, 3]), float(b[j, 0])) for j, r in enumerate(rot_idx.tolist())]
                 items.sort(key=lambda t: t[4])
                 self.top_list = items[:self.max_conf]
-        self.write_conformations()
+        if write:
+            self.write_conformations()
 
     def _merge_candidates(self, cand: torch.Tensor, sel: torch.Tensor, N: int):
         """Merge (score, position in `sel`, linear index) candidates into the global list: same order as appending each
