@@ -331,7 +331,7 @@ template <int L_, int CG_, int YT_> struct FwdZC {
     typedef FwdZCParams Params;
     static constexpr int L = L_, N = 2 * L_, CG = CG_, YT = YT_, YTILES = L_ / YT_, CQ = CG_ / 4;
     static constexpr int CS = N * YT + 8;          // per-channel stride: +8 keeps 4 channel groups of a warp on distinct banks
-    static constexpr int NT = DLPD_FWDZC_NT;
+    static constexpr int NT = (L_ >= 80 && YT_ >= 8) ? 2 * DLPD_FWDZC_NT : DLPD_FWDZC_NT;   // 512 at L = 80: 1.51 vs 1.62 ms; worse at L = 40
     static constexpr int SMEM = (CG * CS + N) * (int)sizeof(cpx);
     static_assert(L_ % YT_ == 0 && CG_ % 4 == 0, "tile shape");
     struct Lines {
