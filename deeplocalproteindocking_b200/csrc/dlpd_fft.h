@@ -18,6 +18,10 @@
 #pragma once
 #include "dlpd_platform.h"
 
+#ifndef DLPD_DUAL_TASKS
+#define DLPD_DUAL_TASKS 0
+#endif
+
 // Complex arithmetic on packed fp32x2 instructions (sm_100 FADD2 / FMUL2 / FFMA2): a complex add is ONE instruction,
 // a complex multiply TWO (the swap / negate of halves folds into operand modifiers).
 DLPD_DEV cpx cadd(cpx a, cpx b) { return fadd2_(a, b); }
@@ -259,6 +263,33 @@ DLPD_DEV void fft_pass_team(const TM& tm, cpx* s, const cpx* tw, LineOff off, In
             for (int i = 0; i < RA; ++i) {
                 DLPD_UNROLL
                 for (int k = 0; k < RB; ++k) out.f(l, e0 + i * M + k * M2, a0[i][k], a1[i][k]);
+            }
+        }
+    } else if constexpr ((DLPD_DUAL_TASKS || TM::DUAL) && RA * RB <= 10 && std::is_same<Out, NoHook>::value && std::is_same<Mul, NoHook>::value) {
+        // two tasks per iteration (t and t + NT): both tasks' loads are issued before either butterfly, so the
+        // shared-memory latency of the second hides behind the arithmetic of the first (20 complex values in registers)
+        constexpr int NTASK = NLINES * TPL;
+        DLPD_TEAM_TASKS2(tm, t, NTASK) {
+            const int t1 = (t + tm.NT < NTASK) ? t + tm.NT : t;       // no second task: redo the first, store once
+            const int l0 = t % NLINES, b0 = t / NLINES, l1 = t1 % NLINES, b1 = t1 / NLINES;
+            const int k0 = b0 / M2, j0 = b0 - k0 * M2, k1 = b1 / M2, j1 = b1 - k1 * M2;
+            const int e0 = k0 * NB + j0, e1 = k1 * NB + j1;
+            cpx* p0 = s + off(l0) + e0 * ES;
+            cpx* p1 = s + off(l1) + e1 * ES;
+            cpx a0[RA][RB], a1[RA][RB];
+            T::run(a0, p0, tw, l0, e0, j0, in, mul);
+            T::run(a1, p1, tw, l1, e1, j1, in, mul);
+            DLPD_UNROLL
+            for (int i = 0; i < RA; ++i) {
+                DLPD_UNROLL
+                for (int k = 0; k < RB; ++k) p0[(i * M + k * M2) * ES] = a0[i][k];
+            }
+            if (t1 != t) {
+                DLPD_UNROLL
+                for (int i = 0; i < RA; ++i) {
+                    DLPD_UNROLL
+                    for (int k = 0; k < RB; ++k) p1[(i * M + k * M2) * ES] = a1[i][k];
+                }
             }
         }
     } else {

@@ -368,8 +368,9 @@ template <int L_, int CG_, int YT_> struct FwdZC {
             d[3 * CS] = make_float2(a.w, b.w);
         }
         DLPD_SYNC();
-        fft_fwd_head<N, CG * YT, YT, NT>(buf, tw, Lines());
-        fft_fwd_tail<N, CG * YT, YT, NT>(buf, tw, Lines());
+        const CtaTeam<NT, true> tm;
+        team_fwd_head<N, CG * YT, YT>(tm, buf, tw, Lines());
+        team_fwd_tail<N, CG * YT, YT>(tm, buf, tw, Lines());
         cpx* out = p.out + ((((long)pair * p.Ctot + c0) * N) * L + x) * L + y0;
         DLPD_FOR_TASKS(t, CG * N * YT, NT) {
             const int yl = t % YT, kz = (t / YT) % N, c = t / (YT * N);
@@ -841,8 +842,9 @@ template <int L_, int C0, int C1, int H> struct HiddenL1 {
         }
         cp_async_wait_all();
         DLPD_SYNC();
-        fft_inv_tail<N1, NL, P1, NT>(b1, tw1, LineMul<1>());
-        fft_inv_head<N1, NL, P1, NT>(b1, tw1, LineMul<1>());
+        const CtaTeam<NT, true> tm;
+        team_inv_tail<N1, NL, P1>(tm, b1, tw1, LineMul<1>());
+        team_inv_head<N1, NL, P1>(tm, b1, tw1, LineMul<1>());
         cpx* h1 = p.h1 + (((long)pair * N1 + x1) * N1 + y0) * N1 * H;
         DLPD_FOR_TASKS(t, (H / JG) * VP, NT) {
             const int v = t % VP, jg = t / VP;
@@ -851,8 +853,13 @@ template <int L_, int C0, int C1, int H> struct HiddenL1 {
                 cpx out[JG];
                 Level1Dispatch<C0, C1, H, JG, 0, YT>::run(p.filt, jg, b1 + z1 * P1 + yl, out);
                 cpx* d = h1 + ((long)yl * N1 + z1) * H + jg * JG;
-                DLPD_UNROLL
-                for (int jj = 0; jj < JG; ++jj) d[jj] = out[jj];
+                if constexpr (JG % 2 == 0 && H % 2 == 0) {           // 16-byte stores: half as many L2 write transactions
+                    DLPD_UNROLL
+                    for (int jj = 0; jj < JG; jj += 2) store_cpx2(d + jj, out[jj], out[jj + 1]);
+                } else {
+                    DLPD_UNROLL
+                    for (int jj = 0; jj < JG; ++jj) d[jj] = out[jj];
+                }
             }
         }
     }
