@@ -163,7 +163,11 @@ template <int L> struct Tile {
     static constexpr int FWD_YT = (L <= 40) ? L : ((L % 40 == 0) ? 40 : 32);      // y lines per FwdZ CTA
     static constexpr int INV_YT = ((2 * L) % 8 == 0) ? 8 : (((2 * L) % 4 == 0) ? 4 : 2);
     // y lines per FwdZC CTA (4 at L = 128: 68 KB of shared memory, three resident CTAs instead of one)
+#ifdef DLPD_CL_YT
+    static constexpr int CL_YT = (L % DLPD_CL_YT == 0) ? DLPD_CL_YT : 2;
+#else
     static constexpr int CL_YT = (L >= 128) ? 4 : ((L % 8 == 0) ? 8 : ((L % 4 == 0) ? 4 : 2));
+#endif
     static constexpr int CL_CG = 8;                                           // channels per FwdZC CTA
 };
 

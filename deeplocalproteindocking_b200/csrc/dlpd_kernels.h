@@ -21,6 +21,12 @@
 #ifndef DLPD_PLANE_NT
 #define DLPD_PLANE_NT 800
 #endif
+#ifndef DLPD_PLANE_NT_MID
+#define DLPD_PLANE_NT_MID 256      // Plane<40>: four resident CTAs of 256 threads beat two of 512 (1.27 -> 1.01 ms)
+#endif
+#ifndef DLPD_HID_YT
+#define DLPD_HID_YT 4
+#endif
 #ifndef DLPD_EPI_NT
 #define DLPD_EPI_NT 768
 #endif
@@ -401,7 +407,7 @@ struct PlaneParams {
 template <int L_> struct Plane {
     typedef PlaneParams Params;
     static constexpr int L = L_, N = 2 * L_, NP = N + 1;     // odd pitch: conflict-free along both axes
-    static constexpr int NT = (N >= 128) ? DLPD_PLANE_NT : ((N >= 64) ? 512 : 256);   // 800 = 5 x 160 lanes: whole passes per round, <= 80 registers
+    static constexpr int NT = (N >= 128) ? DLPD_PLANE_NT : ((N >= 64) ? DLPD_PLANE_NT_MID : 256);   // 800 = 5 x 160 lanes: whole passes per round, <= 80 registers
     static constexpr int SMEM = (N * NP + N) * (int)sizeof(cpx);
     // teams (see body): only for the big plane, and only when rows, columns and threads split evenly
     static constexpr int G = (N >= 128 && N % DLPD_PLANE_TEAMS == 0 && L_ % DLPD_PLANE_TEAMS == 0 && NT % (32 * DLPD_PLANE_TEAMS) == 0)
@@ -820,7 +826,7 @@ template <int C0, int C1, int H> struct HidParams {
 
 template <int L_, int C0, int C1, int H> struct HiddenL1 {
     typedef HidParams<C0, C1, H> Params;
-    static constexpr int N1 = L_, YT = 4, NL = C1 * YT;
+    static constexpr int N1 = L_, YT = DLPD_HID_YT, NL = C1 * YT;
     static constexpr int P1 = NL + 4;                        // row pitch: 16-byte rows, conflict-free (yl, z1) reads
     static constexpr int JG = (H % 8 == 0) ? 8 : H;          // hidden units per task
     static constexpr int VP = (YT * N1 + 31) / 32 * 32;      // (yl, z1) padded to whole warps (warp-uniform hidden group)
