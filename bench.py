@@ -242,7 +242,7 @@ def main():
     ap.add_argument("--ref-rot-per-step", type=int, default=2)
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config (1-based); 2 is the bench line")
     ap.add_argument("--plane-mode", default="auto", choices=["auto", "single", "cluster"], help="plane-stage kernel (tuning)")
-    ap.add_argument("--epilogue-kind", default="auto", choices=["auto", "classic", "pipelined"], help="epilogue kernel (tuning)")
+    ap.add_argument("--epilogue-kind", default="auto", choices=["auto", "classic", "pipelined", "duo"], help="epilogue kernel (tuning)")
     ap.add_argument("--epilogue-tile", type=int, default=0, choices=[0, 1, 2], help="epilogue tile shape (tuning)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

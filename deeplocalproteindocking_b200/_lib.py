@@ -41,7 +41,7 @@ SIGNATURES = {
 
 CENTER_MODES = {"box": 0, "grid": 1}
 OPTIONS = {"plane_mode": 1, "epilogue_tile": 2, "epilogue_kind": 3}      # DLPD_OPT_* of include/dlpd.h
-EPILOGUE_KINDS = {"auto": 0, "classic": 1, "pipelined": 2}
+EPILOGUE_KINDS = {"auto": 0, "classic": 1, "pipelined": 2, "duo": 3}
 PLANE_MODES = {"auto": 0, "single": 1, "cluster": 2}
 
 

@@ -104,6 +104,27 @@ template <class K> static int launch(dim3 g, const typename K::Params& p, dlpd_s
     ++g_launches;
     return 0;
 }
+// same for kernels that state how many CTAs per SM their register budget is cut for (K::MINB)
+template <class K>
+__global__ void __launch_bounds__(K::NT, K::MINB) dlpd_kernel_mb(const __grid_constant__ typename K::Params p) {
+    extern __shared__ __align__(16) char smem[];
+    K::body(p, blockIdx.x, blockIdx.y, blockIdx.z, smem);
+}
+template <class K> static int launch_mb(dim3 g, const typename K::Params& p, dlpd_stream_t st) {
+    static bool configured[64] = {};
+    int dev = 0;
+    CU(cudaGetDevice(&dev));
+    if (dev < 64 && !configured[dev]) {
+        if (K::SMEM > 48 * 1024)
+            CU(cudaFuncSetAttribute(dlpd_kernel_mb<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
+        CU(cudaFuncSetAttribute(dlpd_kernel_mb<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        configured[dev] = true;
+    }
+    dlpd_kernel_mb<K><<<g, K::NT, K::SMEM, st>>>(p);
+    CU(cudaGetLastError());
+    ++g_launches;
+    return 0;
+}
 
 // kernels that span a thread-block cluster of K::CL CTAs (distributed shared memory)
 template <class K>
@@ -217,6 +238,9 @@ static constexpr int SMEM_MAX = 227 * 1024;
 static int g_plane_mode = DLPD_PLANE_AUTO;
 static int g_epi_tile = 0;               // 0 = automatic, 1 / 2 = force 2x1 / 2x2 tiles in the epilogue
 static int g_epi_kind = DLPD_EPILOGUE_AUTO;
+#ifndef DLPD_EPILOGUE_DEFAULT_DUO
+#define DLPD_EPILOGUE_DEFAULT_DUO 0
+#endif
 #ifndef DLPD_EPILOGUE_DEFAULT_PIPELINED
 #define DLPD_EPILOGUE_DEFAULT_PIPELINED 0
 #endif
@@ -535,7 +559,30 @@ static int launch_epilogue_pipe(dlpd_plan* p, int n, int P, float tau, float* ou
     }
 }
 template <int L, int C0, int C1, int H>
+static int launch_epilogue_duo(dlpd_plan* p, int n, int P, float tau, float* out_scores, const CandArgs& ca, dlpd_stream_t st) {
+    typedef EpilogueDuo<L, C0, C1, H> K;
+    if constexpr (2 * (K::SMEM + 1024) <= 228 * 1024) {
+        typename K::Params e;
+        e.s2_0 = p->s2_0; e.h1 = p->h1; e.best = p->best; e.score_out = out_scores;
+        e.tw0 = p->tw0; e.n_rot = n; e.tau = tau;
+        e.cand = ca.cand; e.cand_count = ca.count; e.cand_cap = ca.cap; e.cand_key = ca.key; e.rot_base = ca.rot_base;
+        e.n_tiles = P * L * L;                      // 2x2 groups
+        e.grid = e.n_tiles < 2 * p->sm_count ? e.n_tiles : 2 * p->sm_count;
+        fill_filter(p, e.filt);
+#if defined(DLPD_EMU)
+        return launch<K>(dim3(e.grid), e, st);
+#else
+        return launch_mb<K>(dim3(e.grid), e, st);
+#endif
+    } else {
+        return fail(DLPD_EINVAL, "two epilogue CTAs per SM do not fit shared memory at this box size");
+    }
+}
+template <int L, int C0, int C1, int H>
 static int launch_epilogue(dlpd_plan* p, int n, int P, float tau, float* out_scores, const CandArgs& ca, dlpd_stream_t st) {
+    const bool duo_fits = 2 * (EpilogueDuo<L, C0, C1, H>::SMEM + 1024) <= 228 * 1024;
+    if (g_epi_kind == DLPD_EPILOGUE_DUO || (g_epi_kind == DLPD_EPILOGUE_AUTO && DLPD_EPILOGUE_DEFAULT_DUO && duo_fits && !g_epi_tile))
+        return launch_epilogue_duo<L, C0, C1, H>(p, n, P, tau, out_scores, ca, st);
     const bool pipe_fits = EpiloguePipe<L, C0, C1, H>::SMEM <= SMEM_MAX;
     if (g_epi_kind == DLPD_EPILOGUE_PIPELINED || (g_epi_kind == DLPD_EPILOGUE_AUTO && DLPD_EPILOGUE_DEFAULT_PIPELINED && pipe_fits && !g_epi_tile))
         return launch_epilogue_pipe<L, C0, C1, H>(p, n, P, tau, out_scores, ca, st);
@@ -696,7 +743,7 @@ extern "C" int dlpd_set_option(int key, int value) {
             g_plane_mode = value;
             return 0;
         case DLPD_OPT_EPILOGUE_KIND:
-            if (value < DLPD_EPILOGUE_AUTO || value > DLPD_EPILOGUE_PIPELINED) return fail(DLPD_EINVAL, "bad epilogue kind");
+            if (value < DLPD_EPILOGUE_AUTO || value > DLPD_EPILOGUE_DUO) return fail(DLPD_EINVAL, "bad epilogue kind");
             g_epi_kind = value;
             return 0;
         case DLPD_OPT_EPILOGUE_TILE:

@@ -1246,6 +1246,102 @@ template <int L_, int C0, int C1, int H> struct EpiloguePipe {
     }
 };
 
+// ------------------------------------------------------------------------------------------------------
+// EpilogueDuo: the epilogue as TWO independent persistent CTAs per SM (384 threads, ~104 KB each) instead of one CTA of
+// 768 threads: while one CTA is in its shared-memory-bound transform passes the other is in its FFMA2-bound filter loop,
+// with no hand-over protocol at all.  Half-tiles (2x1 columns: one y of a 2x2 group) halve the tile buffers; the two
+// halves of a group are consecutive iterations of the same CTA and share ONE h1 buffer, which is fetched at the start of
+// the first half and only needed after that half's transform passes.  Every thread issues its share of the cp.async
+// copies (next half-tile + h1), so there are no producer warps.
+// ------------------------------------------------------------------------------------------------------
+#ifndef DLPD_DUO_NT
+#define DLPD_DUO_NT 384
+#endif
+template <int L_, int C0, int C1, int H> struct EpilogueDuo {
+    typedef Epilogue<L_, C0, C1, H, 1> E;            // half-tile geometry and scoring code
+    typedef EpiParams<C0, C1, H> Params;
+    static constexpr int L = L_, N = 2 * L_, N1 = L_, T = L_;
+    static constexpr int NL0 = E::NL0, BUF = N * NL0, HB = N1 * H;
+    static constexpr int NT = (N >= 128) ? DLPD_DUO_NT : 128;
+    static constexpr int MINB = 2;
+    static constexpr int SMEM = (2 * BUF + HB + N) * (int)sizeof(cpx) + 64 * 8;
+    static_assert(HB % 2 == 0 && NT % 32 == 0, "shapes");
+
+    struct Item { int pair, r4, half; };
+    static DLPD_DEV Item item(const Params& p, int bx, int it) {
+        const int g = bx + (it >> 1) * p.grid;
+        return Item{g / (T * T), g % (T * T), it & 1};
+    }
+    static DLPD_DEV void issue_data(const Params& p, const Item& w, cpx* b0) {
+        const cpx* s = p.s2_0 + ((long)w.pair * (C0 + 1) * N * T * T + w.r4) * 4 + 2 * w.half;
+        DLPD_FOR_TASKS(q, (C0 + 1) * N, NT) {                                // q = c*N + kz: 16 contiguous bytes per row
+            const int c = q / N, kz = q - c * N;
+            cp_async16(b0 + kz * NL0 + c * 2, s + (long)q * (T * T) * 4);
+        }
+    }
+    static DLPD_DEV void issue_h1(const Params& p, const Item& w, cpx* hb) {
+        const cpx* hs = p.h1 + ((long)w.pair * T * T + w.r4) * HB;
+        DLPD_FOR_TASKS(t, HB / 2, NT) cp_async16(hb + 2 * t, hs + 2 * t);
+    }
+    static DLPD_DEV void flush_best(const Params& p, int pair, unsigned long long bestA, unsigned long long bestB,
+                                    unsigned long long* red) {
+        const int rotA = 2 * pair, rotB = 2 * pair + 1;
+        const bool hasB = rotB < p.n_rot;
+#if defined(DLPD_EMU)
+        (void)red;
+        if (bestA < p.best[rotA]) p.best[rotA] = bestA;
+        if (hasB && bestB < p.best[rotB]) p.best[rotB] = bestB;
+#else
+        bestA = block_min_u64<NT>(bestA, red);
+        bestB = block_min_u64<NT>(bestB, red + 32);
+        if (threadIdx.x == 0) {
+            atomicMin(p.best + rotA, bestA);
+            if (hasB) atomicMin(p.best + rotB, bestB);
+        }
+#endif
+    }
+
+    // grid: x = p.grid persistent CTAs (two per SM); p.n_tiles = number of 2x2 groups = P * T * T
+    static DLPD_DEV void body(const Params& p, int bx, int, int, char* smem) {
+        cpx* bufs = reinterpret_cast<cpx*>(smem);      // [2][kz][NL0]
+        cpx* hbuf = bufs + 2 * BUF;                    // [z'][H]: level-1 hidden column of the current group
+        cpx* tw0 = hbuf + HB;
+        unsigned long long* red = reinterpret_cast<unsigned long long*>(tw0 + N);
+        const int my_groups = bx < p.n_tiles ? (p.n_tiles - bx + p.grid - 1) / p.grid : 0;
+        const int n_it = 2 * my_groups;
+        DLPD_FOR_TASKS(t, N, NT) tw0[t] = p.tw0[t];
+        if (n_it > 0) issue_data(p, item(p, bx, 0), bufs);
+        cp_async_commit();
+        cp_async_wait_pending();
+        const CtaTeam<NT> tm;
+        unsigned long long bestA = ~0ull, bestB = ~0ull;
+        int cur_pair = -1;
+        for (int it = 0, slot = 0; it < n_it; ++it, slot ^= 1) {
+            DLPD_SYNC();                               // half-tile `it` has landed; everyone is done with the other buffers
+            const Item w = item(p, bx, it);
+            if (w.pair != cur_pair) {
+                if (cur_pair >= 0) flush_best(p, cur_pair, bestA, bestB, red);
+                cur_pair = w.pair;
+                bestA = bestB = ~0ull;
+            }
+            if (w.half == 0) issue_h1(p, w, hbuf);     // needed after the transform passes of this half
+            cp_async_commit();
+#if !defined(DLPD_ABLATE_EPI_LOAD)
+            if (it + 1 < n_it) issue_data(p, item(p, bx, it + 1), bufs + (slot ^ 1) * BUF);
+#endif
+            cp_async_commit();
+            E::transform_tile(tm, bufs + slot * BUF, tw0);
+            if (w.half == 0) {
+                cp_async_wait_allow1();                // my h1 copies are done (the prefetch may still be in flight)
+                DLPD_SYNC();                           // ... and everybody else's
+            }
+            E::score_voxels(p, tm, bufs + slot * BUF, hbuf, w.pair, 2 * (w.r4 / T), 2 * (w.r4 % T) + w.half, bestA, bestB);
+            cp_async_wait_pending();
+        }
+        if (cur_pair >= 0) flush_best(p, cur_pair, bestA, bestB, red);
+    }
+};
+
 // packed best -> [n_rot][4] floats (score, x, y, z)
 struct DecodeParams {
     const unsigned long long* best;

@@ -36,6 +36,7 @@
   static inline void cp_async_wait_all() {}
   static inline void cp_async_commit() {}
   static inline void cp_async_wait_pending() {}
+  static inline void cp_async_wait_allow1() {}
   static inline void prefetch_l2(const void*) {}
   // teams: the emulation runs the teams of a CTA one after the other (DLPD_FOR_TEAMS), each as one "thread"
   #define DLPD_FOR_TEAMS(g, G, TNT) for (int g = 0; g < (G); ++g)
@@ -78,6 +79,7 @@
   }
   DLPD_DEV void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
   DLPD_DEV void cp_async_wait_pending() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+  DLPD_DEV void cp_async_wait_allow1() { asm volatile("cp.async.wait_group 1;" ::: "memory"); }   // all but the newest group
   DLPD_DEV void prefetch_l2(const void* p) { asm volatile("prefetch.global.L2 [%0];" ::"l"(p)); }
   // teams: G contiguous groups of TNT threads, each working on its own sub-problem with its own named barrier
   #define DLPD_FOR_TEAMS(g, G, TNT) for (int g = threadIdx.x / (TNT), g##_once = 1; g##_once; g##_once = 0)

@@ -133,6 +133,7 @@ int dlpd_project_clash(const double* coords, const double* R, int nat, int n, in
 #define DLPD_EPILOGUE_AUTO 0
 #define DLPD_EPILOGUE_CLASSIC 1     /* one consumer team: transform then filter, next tile prefetched            */
 #define DLPD_EPILOGUE_PIPELINED 2   /* load / transform / filter of consecutive half-tiles overlap (N <= 160)    */
+#define DLPD_EPILOGUE_DUO 3         /* two independent half-tile CTAs per SM (N <= 160)                          */
 #define DLPD_PLANE_AUTO 0
 #define DLPD_PLANE_SINGLE 1
 #define DLPD_PLANE_CLUSTER 2
