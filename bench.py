@@ -243,6 +243,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config (1-based); 2 is the bench line")
     ap.add_argument("--plane-mode", default="auto", choices=["auto", "single", "cluster"], help="plane-stage kernel (tuning)")
     ap.add_argument("--epilogue-kind", default="auto", choices=["auto", "classic", "pipelined", "duo"], help="epilogue kernel (tuning)")
+    ap.add_argument("--filter-kind", default="auto", choices=["auto", "fp32", "tensor"], help="first filter layer: FFMA chain or fp16-split mma.sync (tuning)")
     ap.add_argument("--epilogue-tile", type=int, default=0, choices=[0, 1, 2], help="epilogue tile shape (tuning)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
@@ -261,6 +262,7 @@ def main():
     set_option("plane_mode", args.plane_mode)
     set_option("epilogue_tile", args.epilogue_tile)
     set_option("epilogue_kind", args.epilogue_kind)
+    set_option("filter_kind", args.filter_kind)
 
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)

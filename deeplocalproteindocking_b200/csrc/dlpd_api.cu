@@ -189,7 +189,11 @@ template <int L> struct Tile {
 #else
     static constexpr int CL_YT = (L >= 128) ? 4 : ((L % 8 == 0) ? 8 : ((L % 4 == 0) ? 4 : 2));
 #endif
+#ifdef DLPD_CL_CG
+    static constexpr int CL_CG = DLPD_CL_CG;
+#else
     static constexpr int CL_CG = 8;                                           // channels per FwdZC CTA
+#endif
 };
 
 // box sizes the single-level kernels are compiled for
@@ -235,9 +239,16 @@ template <int L> static int launch_fwdzc_t(const FwdZCParams& p, int P, dlpd_str
 }
 // Plane<L> needs the whole N x N plane in one SM's shared memory; PlaneX<L, 4> spreads it over a cluster of 4 CTAs.
 static constexpr int SMEM_MAX = 227 * 1024;
+#ifndef DLPD_PLANE_WAVES
+#define DLPD_PLANE_WAVES 1      // look-ahead distance of Plane's S1 prefetch in grid waves
+#endif
 static int g_plane_mode = DLPD_PLANE_AUTO;
 static int g_epi_tile = 0;               // 0 = automatic, 1 / 2 = force 2x1 / 2x2 tiles in the epilogue
 static int g_epi_kind = DLPD_EPILOGUE_AUTO;
+static int g_filter_kind = DLPD_FILTER_AUTO;
+#ifndef DLPD_FILTER_DEFAULT_TENSOR
+#define DLPD_FILTER_DEFAULT_TENSOR 0      // measured on B200: 4.40 ms vs 3.74 ms for the FFMA chain
+#endif
 #ifndef DLPD_EPILOGUE_DEFAULT_DUO
 #define DLPD_EPILOGUE_DEFAULT_DUO 0
 #endif
@@ -278,7 +289,7 @@ static int launch_fwdzc(int L, const FwdZCParams& p, int P, dlpd_stream_t st) {
     }
     return fail(DLPD_EINVAL, "unsupported box size");
 }
-static bool channel_last_ok(int C) { return C % 8 == 0; }
+static bool channel_last_ok(int C) { return C % 16 == 0; }     // multiple of every Tile<L>::CL_CG in use
 static int launch_plane(int L, const PlaneParams& p, dlpd_stream_t st) {
     switch (L) {
 #define X(L_) case L_: return launch_plane_t<L_>(p, st);
@@ -308,6 +319,8 @@ struct dlpd_plan {
     cpx *rspec0, *rspec1;        // receptor spectra [(C0+1)][N^3], [C1][L^3]
     cpx *s1_0, *s1_1, *s2_0, *s2_1;
     cpx* h1;                     // [P][L^3][H] level-1 part of the hidden layer (HiddenL1 -> Epilogue)
+    float *rec_ss, *lig_ss;      // [C0] squared norms of the level-0 feature volumes (bound the correlations: MlpDev)
+    void* mlp;                   // MlpDev<C0, H>: fp16-split first-layer weights for the tensor-core filter
     int sm_count;
     unsigned long long* best;    // [max_rot]
     float *pin_R, *pin_best;     // pinned staging for dlpd_search_host
@@ -382,6 +395,7 @@ extern "C" int dlpd_plan_destroy(dlpd_plan* p) {
     rt_free(p->tw0); rt_free(p->tw1); rt_free(p->tw2);
     rt_free(p->lig0); rt_free(p->lig1); rt_free(p->lig0_cl); rt_free(p->lig1_cl); rt_free(p->rspec0); rt_free(p->rspec1);
     rt_free(p->s1_0); rt_free(p->s1_1); rt_free(p->s2_0); rt_free(p->s2_1); rt_free(p->h1);
+    rt_free(p->rec_ss); rt_free(p->lig_ss); rt_free(p->mlp);
     rt_free(p->best); rt_free(p->dev_R); rt_free(p->dev_best);
     rt_free_host(p->pin_R); rt_free_host(p->pin_best);
 #if !defined(DLPD_EMU)
@@ -409,6 +423,7 @@ extern "C" int dlpd_plan_create(dlpd_plan** out, int L, int C0, int C1, int H, i
     p->tw0 = p->tw1 = p->tw2 = nullptr; p->lig0 = p->lig1 = nullptr; p->rspec0 = p->rspec1 = nullptr;
     p->lig0_cl = p->lig1_cl = nullptr;
     p->s1_0 = p->s1_1 = p->s2_0 = p->s2_1 = nullptr; p->best = nullptr; p->h1 = nullptr;
+    p->rec_ss = p->lig_ss = nullptr; p->mlp = nullptr;
     p->sm_count = rt_sm_count(device);
     p->pin_R = p->pin_best = p->dev_R = p->dev_best = nullptr; p->host_cap = 0;
     p->has_receptor = p->has_ligand = p->lig_has_clash = p->has_filter = false;
@@ -430,6 +445,9 @@ extern "C" int dlpd_plan_create(dlpd_plan** out, int L, int C0, int C1, int H, i
         {(void**)&p->s2_1, sizeof(cpx) * P * C1 * n3(N1)},
         {(void**)&p->h1, sizeof(cpx) * P * n3(N1) * H},
         {(void**)&p->best, sizeof(unsigned long long) * (size_t)max_rot},
+        {(void**)&p->rec_ss, sizeof(float) * C0},
+        {(void**)&p->lig_ss, sizeof(float) * C0},
+        {(void**)&p->mlp, 8192},
     };
     p->bytes = 0;
     for (auto& a : allocs) {
@@ -459,6 +477,14 @@ static int real_spectra(int L, const float* vols, int C, cpx* s1, cpx* spec, con
     return 0;
 }
 
+// squared L2 norm per level-0 feature channel (max over the n volume sets): bounds the correlations for the fp16-split filter
+static int channel_sumsq(const float* vols, int C, int V, int n, float* out, dlpd_stream_t st) {
+    TRY(rt_memset(out, 0, sizeof(float) * C, st));
+    SumSqParams q;
+    q.v = vols; q.out = out; q.C = C; q.V = V;
+    return launch<SumSq>(dim3(C, n), q, st);
+}
+
 extern "C" int dlpd_set_receptor(dlpd_plan* p, const float* vol0, const float* vol1, const float* clash, void* stream) {
     if (!p || !vol0 || !vol1 || !clash) return fail(DLPD_EINVAL, "dlpd_set_receptor: NULL argument");
     dlpd_stream_t st = (dlpd_stream_t)stream;
@@ -468,6 +494,7 @@ extern "C" int dlpd_set_receptor(dlpd_plan* p, const float* vol0, const float* v
     TRY(rt_copy(p->lig0, vol0, sizeof(float) * p->C0 * n3(L), D2D, st));
     TRY(rt_copy(p->lig0 + p->C0 * n3(L), clash, sizeof(float) * n3(L), D2D, st));
     TRY(real_spectra(L, p->lig0, p->C0 + 1, p->s1_0, p->rspec0, p->tw0, st));
+    TRY(channel_sumsq(vol0, p->C0, (int)n3(L), 1, p->rec_ss, st));
     TRY(real_spectra(L1, vol1, p->C1, p->s1_1, p->rspec1, p->tw1, st));
     p->has_receptor = true;
     p->has_ligand = false;      // lig0 was used as staging
@@ -483,6 +510,7 @@ extern "C" int dlpd_set_ligand(dlpd_plan* p, const float* vol0, const float* vol
     if (clash) TRY(rt_copy(p->lig0 + p->C0 * n3(L), clash, sizeof(float) * n3(L), D2D, st));
     else TRY(rt_memset(p->lig0 + p->C0 * n3(L), 0, sizeof(float) * n3(L), st));
     TRY(rt_copy(p->lig1, vol1, sizeof(float) * p->C1 * n3(L1), D2D, st));
+    TRY(channel_sumsq(vol0, p->C0, (int)n3(L), 1, p->lig_ss, st));
     ChannelLastParams cl;
     cl.in = p->lig0; cl.out = p->lig0_cl; cl.C = p->C0; cl.V = (int)n3(L);
     TRY(launch<ToChannelLast>(dim3((cl.V + ToChannelLast::VOX_PER_CTA - 1) / ToChannelLast::VOX_PER_CTA), cl, st));
@@ -526,9 +554,32 @@ struct CandArgs {
     unsigned int cap = 0, key = 0;
     int rot_base = 0;
 };
-template <int L, int C0, int C1, int H, int TY>
+// tensor-core filter: on unless switched off, wherever the epilogue kernel has the path (C0 = 16, H % 8 = 0)
+template <int L, int C0, int C1, int H> static bool filter_tensor() {
+#if defined(DLPD_EMU)
+    return false;
+#else
+    const bool want = g_filter_kind == DLPD_FILTER_TENSOR || (g_filter_kind == DLPD_FILTER_AUTO && DLPD_FILTER_DEFAULT_TENSOR);
+    return want && C0 == 16 && H % 8 == 0;
+#endif
+}
+template <int L, int C0, int C1, int H> static int launch_filter_prep(dlpd_plan* p, dlpd_stream_t st) {
+#if !defined(DLPD_EMU)
+    if constexpr (C0 == 16 && H % 8 == 0) {
+        static_assert(sizeof(MlpDev<C0, H>) <= 8192, "plan->mlp allocation");
+        typedef FilterPrep<C0, C1, H> K;
+        typename K::Params e;
+        e.rec_ss = p->rec_ss; e.lig_ss = p->lig_ss; e.out = (MlpDev<C0, H>*)p->mlp;
+        fill_filter(p, e.filt);
+        return launch<K>(dim3(1), e, st);
+    }
+#endif
+    (void)p; (void)st;
+    return 0;
+}
+template <int L, int C0, int C1, int H, int TY, bool TC = false>
 static int launch_epilogue_t(dlpd_plan* p, int n, int P, float tau, float* out_scores, const CandArgs& ca, dlpd_stream_t st) {
-    typedef Epilogue<L, C0, C1, H, TY> K;
+    typedef Epilogue<L, C0, C1, H, TY, TC> K;
     if constexpr (K::SMEM <= SMEM_MAX) {
         typename K::Params e;
         e.s2_0 = p->s2_0; e.h1 = p->h1; e.best = p->best; e.score_out = out_scores;
@@ -537,6 +588,11 @@ static int launch_epilogue_t(dlpd_plan* p, int n, int P, float tau, float* out_s
         e.n_tiles = P * K::TILES;
         e.grid = e.n_tiles < p->sm_count ? e.n_tiles : p->sm_count;
         fill_filter(p, e.filt);
+        e.mlp = nullptr;
+        if constexpr (K::MMA_OK) {
+            TRY((launch_filter_prep<L, C0, C1, H>(p, st)));
+            e.mlp = (const MlpDev<C0, H>*)p->mlp;
+        }
         return launch<K>(dim3(e.grid), e, st);
     } else {
         return fail(DLPD_EINVAL, "epilogue tile does not fit shared memory");
@@ -551,6 +607,7 @@ static int launch_epilogue_pipe(dlpd_plan* p, int n, int P, float tau, float* ou
         e.tw0 = p->tw0; e.n_rot = n; e.tau = tau;
         e.cand = ca.cand; e.cand_count = ca.count; e.cand_cap = ca.cap; e.cand_key = ca.key; e.rot_base = ca.rot_base;
         e.n_tiles = P * L * L;                      // 2x2 groups
+        e.mlp = nullptr;
         e.grid = e.n_tiles < p->sm_count ? e.n_tiles : p->sm_count;
         fill_filter(p, e.filt);
         return launch<K>(dim3(e.grid), e, st);
@@ -567,6 +624,7 @@ static int launch_epilogue_duo(dlpd_plan* p, int n, int P, float tau, float* out
         e.tw0 = p->tw0; e.n_rot = n; e.tau = tau;
         e.cand = ca.cand; e.cand_count = ca.count; e.cand_cap = ca.cap; e.cand_key = ca.key; e.rot_base = ca.rot_base;
         e.n_tiles = P * L * L;                      // 2x2 groups
+        e.mlp = nullptr;
         e.grid = e.n_tiles < 2 * p->sm_count ? e.n_tiles : 2 * p->sm_count;
         fill_filter(p, e.filt);
 #if defined(DLPD_EMU)
@@ -588,6 +646,13 @@ static int launch_epilogue(dlpd_plan* p, int n, int P, float tau, float* out_sco
         return launch_epilogue_pipe<L, C0, C1, H>(p, n, P, tau, out_scores, ca, st);
     const bool fits2 = Epilogue<L, C0, C1, H, 2>::SMEM <= SMEM_MAX;
     const int ty = g_epi_tile ? g_epi_tile : (fits2 ? 2 : 1);
+#if !defined(DLPD_EMU)
+    if constexpr (C0 == 16 && H % 8 == 0) {
+        if (filter_tensor<L, C0, C1, H>())
+            return ty == 2 ? launch_epilogue_t<L, C0, C1, H, 2, true>(p, n, P, tau, out_scores, ca, st)
+                           : launch_epilogue_t<L, C0, C1, H, 1, true>(p, n, P, tau, out_scores, ca, st);
+    }
+#endif
     return ty == 2 ? launch_epilogue_t<L, C0, C1, H, 2>(p, n, P, tau, out_scores, ca, st)
                    : launch_epilogue_t<L, C0, C1, H, 1>(p, n, P, tau, out_scores, ca, st);
 }
@@ -605,6 +670,7 @@ static int search_chunk(dlpd_plan* p, const float* R, const float* clash_rot, co
         f.src_pair_stride = 0; f.R = R; f.out = p->s1_0; f.tw = p->tw0; f.Ctot = p->C0 + 1; f.n_rot = n; f.ext_all = 0;
         f.center = center_of(L, p->center_mode);
         if (lig0_rot) {
+            TRY(channel_sumsq(lig0_rot, p->C0, (int)n3(L), n, p->lig_ss, st));
             f.src = p->lig0; f.src_rot = lig0_rot; f.C = p->C0; f.c_out0 = 0; f.c_ext = -1; f.ext_all = 1;
             TRY(launch_fwdz(L, f, P, st));
             f.ext_all = 0;
@@ -641,7 +707,7 @@ static int search_chunk(dlpd_plan* p, const float* R, const float* clash_rot, co
     }
     PlaneParams q;
     q.in = p->s1_0; q.out = p->s2_0; q.spec = p->rspec0; q.spec_pair_stride = 0; q.tw = p->tw0; q.C = p->C0 + 1; q.P = P;
-    q.scale = 1.f; q.tiled = 1; q.wave = p->sm_count;
+    q.scale = 1.f; q.tiled = 1; q.wave = DLPD_PLANE_WAVES * p->sm_count;
     { ProfScope ps(p, DLPD_PROFILE_PLANE0, st); TRY(launch_plane(L, q, st)); }
     q.in = p->s1_1; q.out = p->s2_1; q.spec = p->rspec1; q.tw = p->tw1; q.C = p->C1; q.tiled = 0; q.wave = 2 * p->sm_count;
     { ProfScope ps(p, DLPD_PROFILE_PLANE1, st); TRY(launch_plane(L1, q, st)); }
@@ -749,6 +815,10 @@ extern "C" int dlpd_set_option(int key, int value) {
         case DLPD_OPT_EPILOGUE_TILE:
             if (value < 0 || value > 2) return fail(DLPD_EINVAL, "epilogue tile must be 0 (auto), 1 (2x1) or 2 (2x2)");
             g_epi_tile = value;
+            return 0;
+        case DLPD_OPT_FILTER_KIND:
+            if (value < DLPD_FILTER_AUTO || value > DLPD_FILTER_TENSOR) return fail(DLPD_EINVAL, "bad filter kind");
+            g_filter_kind = value;
             return 0;
     }
     return fail(DLPD_EINVAL, "unknown option");

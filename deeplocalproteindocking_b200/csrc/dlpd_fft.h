@@ -18,6 +18,9 @@
 #pragma once
 #include "dlpd_platform.h"
 
+#ifndef DLPD_PLANE_ALT_PLAN
+#define DLPD_PLANE_ALT_PLAN 0
+#endif
 #ifndef DLPD_DUAL_TASKS
 #define DLPD_DUAL_TASKS 0
 #endif
@@ -49,6 +52,28 @@ DLPD_DEV cpx mul_w16(cpx a, int m) {
     if (m == 8) return make_float2(-a.x, -a.y);
     if (m == 12) return make_float2(a.y, -a.x);
     return cmul(a, make_float2(w16_cos(m), w16_cos((m + 12) & 15)));       // sin(t) = cos(t - pi/2)
+}
+
+// the same for 20th roots of unity (innermost (5,4) pass of the 8 x 20 factorisation)
+DLPD_DEV float w20_cos(int m) {
+    return m == 0 ? 1.0f : m == 1 ? 0.95105651629515357f : m == 2 ? 0.80901699437494742f : m == 3 ? 0.58778525229247313f
+         : m == 4 ? 0.30901699437494742f : m == 5 ? 0.0f : m == 6 ? -0.30901699437494742f : m == 7 ? -0.58778525229247313f
+         : m == 8 ? -0.80901699437494742f : m == 9 ? -0.95105651629515357f : m == 10 ? -1.0f : m == 11 ? -0.95105651629515357f
+         : m == 12 ? -0.80901699437494742f : m == 13 ? -0.58778525229247313f : m == 14 ? -0.30901699437494742f : m == 15 ? 0.0f
+         : m == 16 ? 0.30901699437494742f : m == 17 ? 0.58778525229247313f : m == 18 ? 0.80901699437494742f : 0.95105651629515357f;
+}
+DLPD_DEV cpx mul_w20(cpx a, int m) {
+    m %= 20;
+    if (m == 0) return a;
+    if (m == 5) return cmul_i(a);
+    if (m == 10) return make_float2(-a.x, -a.y);
+    if (m == 15) return make_float2(a.y, -a.x);
+    return cmul(a, make_float2(w20_cos(m), w20_cos((m + 15) % 20)));       // sin(t) = cos(t - pi/2)
+}
+// a * w_NB^m with compile-time m, NB | 16 or NB == 20
+template <int NB> DLPD_DEV cpx mul_wconst(cpx a, int m) {
+    if constexpr (NB == 20) return mul_w20(a, m);
+    else return mul_w16(a, (16 / NB) * m);
 }
 
 // ---- small DFTs, sign + ------------------------------------------------------------------------
@@ -130,6 +155,14 @@ DLPD_LINEPLAN(80, 5, 8, 1)
 DLPD_LINEPLAN(128, 8, 8, 1)
 DLPD_LINEPLAN(160, 5, 4, 4)
 DLPD_LINEPLAN(256, 8, 4, 4)
+// alternative factorisation for the plane kernel's x / y passes (private to it: the receptor spectrum is produced by the same
+// code): 160 = (2,4) x (5,4) gives 20 / 8 tasks per line, i.e. whole rounds for teams of 128 threads on 32 lines
+template <int N> struct PlanePlan : LinePlan<N> {};
+#if DLPD_PLANE_ALT_PLAN
+template <> struct PlanePlan<160> {
+    static constexpr int R0 = 4, TA = 5, TB = 4, TAIL = 20;
+};
+#endif
 
 // hooks of fft_pass: where a task's values come from / go to, and an optional pointwise multiplier
 struct NoHook {};
@@ -161,7 +194,7 @@ template <int KIND, int RA, int RB, int LEN, int NB, int TWN, int ES> struct Fft
     static constexpr bool INV = KIND == PASS_DIT || KIND == PASS_MID;
     static_assert(KIND != PASS_DIF_PRUNED || RA == 2, "pruned pass is the outermost radix-2 step");
     // innermost pass (one butterfly per block, j == 0): every twiddle is a compile-time power of w_NB, NB | 16
-    static constexpr bool CONST_TW = (M2 == 1) && (16 % NB == 0);
+    static constexpr bool CONST_TW = (M2 == 1) && (16 % NB == 0 || NB == 20);
 
     // load the RA x RB values of the task whose first element is e0 = blk*NB + j (line l at `p`) and transform them
     template <class In, class Mul>
@@ -192,7 +225,7 @@ template <int KIND, int RA, int RB, int LEN, int NB, int TWN, int ES> struct Fft
                 a[0][k] = c[0];
                 DLPD_UNROLL
                 for (int i = 1; i < RA; ++i) {
-                    if constexpr (CONST_TW) a[i][k] = mul_w16(c[i], (16 / NB) * k * i);
+                    if constexpr (CONST_TW) a[i][k] = mul_wconst<NB>(c[i], k * i);
                     else a[i][k] = cmul(c[i], tw[TWO * (j + k * M2) * i]);
                 }
             }
@@ -230,7 +263,7 @@ template <int KIND, int RA, int RB, int LEN, int NB, int TWN, int ES> struct Fft
                 c[0] = a[0][k];
                 DLPD_UNROLL
                 for (int i = 1; i < RA; ++i) {
-                    if constexpr (CONST_TW) c[i] = mul_w16(a[i][k], (16 / NB) * k * i);
+                    if constexpr (CONST_TW) c[i] = mul_wconst<NB>(a[i][k], k * i);
                     else c[i] = cmul(a[i][k], tw[TWO * (j + k * M2) * i]);
                 }
                 Dft<RA>::run(c);
@@ -323,56 +356,50 @@ DLPD_DEV void fft_pass(cpx* s, const cpx* tw, LineOff off, In in = In(), Out out
 
 // ---- whole-line helpers -------------------------------------------------------------------------------------
 // forward head: pruned (2, R0) pair at block N; reads elements [0, N/2) only (optionally from global via `in`)
-template <int N, int NLINES, int ES, int NT, class LineOff, class In = NoHook>
+template <int N, int NLINES, int ES, int NT, class P = LinePlan<N>, class LineOff, class In = NoHook>
 DLPD_DEV void fft_fwd_head(cpx* s, const cpx* tw, LineOff off, In in = In()) {
-    fft_pass<PASS_DIF_PRUNED, 2, LinePlan<N>::R0, NLINES, N, N, N, ES, NT>(s, tw, off, in);
+    fft_pass<PASS_DIF_PRUNED, 2, P::R0, NLINES, N, N, N, ES, NT>(s, tw, off, in);
 }
 // forward tail: (TA, TB) pair at block N / (2 R0)   (nothing to do when TAIL == 1)
-template <int N, int NLINES, int ES, int NT, class LineOff>
+template <int N, int NLINES, int ES, int NT, class P = LinePlan<N>, class LineOff>
 DLPD_DEV void fft_fwd_tail(cpx* s, const cpx* tw, LineOff off) {
-    typedef LinePlan<N> P;
     if constexpr (P::TAIL > 1) fft_pass<PASS_DIF, P::TA, P::TB, NLINES, N, P::TAIL, N, ES, NT>(s, tw, off);
 }
 // forward tail, pointwise multiply, inverse tail in one pass (a plain multiply pass when TAIL == 1)
-template <int N, int NLINES, int ES, int NT, class LineOff, class Mul>
+template <int N, int NLINES, int ES, int NT, class P = LinePlan<N>, class LineOff, class Mul>
 DLPD_DEV void fft_mid(cpx* s, const cpx* tw, LineOff off, Mul mul) {
-    typedef LinePlan<N> P;
     fft_pass<PASS_MID, P::TA, P::TB, NLINES, N, P::TAIL, N, ES, NT>(s, tw, off, NoHook(), NoHook(), mul);
 }
-template <int N, int NLINES, int ES, int NT, class LineOff, class In = NoHook>
+template <int N, int NLINES, int ES, int NT, class P = LinePlan<N>, class LineOff, class In = NoHook>
 DLPD_DEV void fft_inv_tail(cpx* s, const cpx* tw, LineOff off, In in = In()) {
-    typedef LinePlan<N> P;
     if constexpr (P::TAIL > 1 || !std::is_same<In, NoHook>::value)
         fft_pass<PASS_DIT, P::TA, P::TB, NLINES, N, P::TAIL, N, ES, NT>(s, tw, off, in);
 }
 // inverse head: (2, R0) pair at block N (optionally writing to global via `out`)
-template <int N, int NLINES, int ES, int NT, class LineOff, class Out = NoHook>
+template <int N, int NLINES, int ES, int NT, class P = LinePlan<N>, class LineOff, class Out = NoHook>
 DLPD_DEV void fft_inv_head(cpx* s, const cpx* tw, LineOff off, Out out = Out()) {
-    fft_pass<PASS_DIT, 2, LinePlan<N>::R0, NLINES, N, N, N, ES, NT>(s, tw, off, NoHook(), out);
+    fft_pass<PASS_DIT, 2, P::R0, NLINES, N, N, N, ES, NT>(s, tw, off, NoHook(), out);
 }
 
 // ---- the same helpers for an explicit team (SubTeam / CtaTeam) ------------------------------------------------
-template <int N, int NLINES, int ES, class TM, class LineOff, class In = NoHook>
+template <int N, int NLINES, int ES, class P = LinePlan<N>, class TM, class LineOff, class In = NoHook>
 DLPD_DEV void team_fwd_head(const TM& tm, cpx* s, const cpx* tw, LineOff off, In in = In()) {
-    fft_pass_team<PASS_DIF_PRUNED, 2, LinePlan<N>::R0, NLINES, N, N, N, ES>(tm, s, tw, off, in);
+    fft_pass_team<PASS_DIF_PRUNED, 2, P::R0, NLINES, N, N, N, ES>(tm, s, tw, off, in);
 }
-template <int N, int NLINES, int ES, class TM, class LineOff>
+template <int N, int NLINES, int ES, class P = LinePlan<N>, class TM, class LineOff>
 DLPD_DEV void team_fwd_tail(const TM& tm, cpx* s, const cpx* tw, LineOff off) {
-    typedef LinePlan<N> P;
     if constexpr (P::TAIL > 1) fft_pass_team<PASS_DIF, P::TA, P::TB, NLINES, N, P::TAIL, N, ES>(tm, s, tw, off);
 }
-template <int N, int NLINES, int ES, class TM, class LineOff, class Mul>
+template <int N, int NLINES, int ES, class P = LinePlan<N>, class TM, class LineOff, class Mul>
 DLPD_DEV void team_mid(const TM& tm, cpx* s, const cpx* tw, LineOff off, Mul mul) {
-    typedef LinePlan<N> P;
     fft_pass_team<PASS_MID, P::TA, P::TB, NLINES, N, P::TAIL, N, ES>(tm, s, tw, off, NoHook(), NoHook(), mul);
 }
-template <int N, int NLINES, int ES, class TM, class LineOff, class In = NoHook>
+template <int N, int NLINES, int ES, class P = LinePlan<N>, class TM, class LineOff, class In = NoHook>
 DLPD_DEV void team_inv_tail(const TM& tm, cpx* s, const cpx* tw, LineOff off, In in = In()) {
-    typedef LinePlan<N> P;
     if constexpr (P::TAIL > 1 || !std::is_same<In, NoHook>::value)
         fft_pass_team<PASS_DIT, P::TA, P::TB, NLINES, N, P::TAIL, N, ES>(tm, s, tw, off, in);
 }
-template <int N, int NLINES, int ES, class TM, class LineOff, class Out = NoHook>
+template <int N, int NLINES, int ES, class P = LinePlan<N>, class TM, class LineOff, class Out = NoHook>
 DLPD_DEV void team_inv_head(const TM& tm, cpx* s, const cpx* tw, LineOff off, Out out = Out()) {
-    fft_pass_team<PASS_DIT, 2, LinePlan<N>::R0, NLINES, N, N, N, ES>(tm, s, tw, off, NoHook(), out);
+    fft_pass_team<PASS_DIT, 2, P::R0, NLINES, N, N, N, ES>(tm, s, tw, off, NoHook(), out);
 }

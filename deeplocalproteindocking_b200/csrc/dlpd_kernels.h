@@ -19,7 +19,7 @@
 
 // tunables (overridable with -D for experiments; the defaults are what ships)
 #ifndef DLPD_PLANE_NT
-#define DLPD_PLANE_NT 800
+#define DLPD_PLANE_NT 640          // with two tasks per iteration (DLPD_PLANE_DUAL): 5.41 ms vs 5.95 ms at 800 threads, single tasks
 #endif
 #ifndef DLPD_PLANE_NT_MID
 #define DLPD_PLANE_NT_MID 256      // Plane<40>: four resident CTAs of 256 threads beat two of 512 (1.27 -> 1.01 ms)
@@ -38,6 +38,9 @@
 #endif
 #ifndef DLPD_PLANE_TEAMS
 #define DLPD_PLANE_TEAMS 5
+#endif
+#ifndef DLPD_PLANE_DUAL
+#define DLPD_PLANE_DUAL 1            // two butterfly tasks per iteration in Plane's plain passes (needs registers: 640 threads x 96)
 #endif
 #ifndef DLPD_PLANE_PREFETCH
 #define DLPD_PLANE_PREFETCH 2
@@ -407,7 +410,8 @@ struct PlaneParams {
 template <int L_> struct Plane {
     typedef PlaneParams Params;
     static constexpr int L = L_, N = 2 * L_, NP = N + 1;     // odd pitch: conflict-free along both axes
-    static constexpr int NT = (N >= 128) ? DLPD_PLANE_NT : ((N >= 64) ? DLPD_PLANE_NT_MID : 256);   // 800 = 5 x 160 lanes: whole passes per round, <= 80 registers
+    typedef PlanePlan<N> PP;                                 // factorisation of the x / y lines
+    static constexpr int NT = (N >= 128) ? DLPD_PLANE_NT : ((N >= 64) ? DLPD_PLANE_NT_MID : 256);   // 640 = 5 teams x 128: whole head passes per round, <= 102 registers
     static constexpr int SMEM = (N * NP + N) * (int)sizeof(cpx);
     // teams (see body): only for the big plane, and only when rows, columns and threads split evenly
     static constexpr int G = (N >= 128 && N % DLPD_PLANE_TEAMS == 0 && L_ % DLPD_PLANE_TEAMS == 0 && NT % (32 * DLPD_PLANE_TEAMS) == 0)
@@ -465,45 +469,45 @@ template <int L_> struct Plane {
             // arithmetic phases overlap; only the two transpositions (x -> y -> x) need the whole CTA
             if (spec != nullptr) {
                 DLPD_FOR_TEAMS(g, G, TNT) {
-                    const SubTeam<TNT> tm{DLPD_TEAM_TID(TNT), g + 1};
+                    const SubTeam<TNT, DLPD_PLANE_DUAL != 0> tm{DLPD_TEAM_TID(TNT), g + 1};
                     GlobalIn<LoadS1> in{LoadS1{p.in + plane * L * L + g * (L / G)}};
-                    team_fwd_head<N, L / G, NP>(tm, pl + g * (L / G), tw, LineMul<1>(), in);        // along x, columns y < L
+                    team_fwd_head<N, L / G, NP, PP>(tm, pl + g * (L / G), tw, LineMul<1>(), in);        // along x, columns y < L
                     if (g == 0) prefetch(p, bx, spec);
-                    team_fwd_tail<N, L / G, NP>(tm, pl + g * (L / G), tw, LineMul<1>());
+                    team_fwd_tail<N, L / G, NP, PP>(tm, pl + g * (L / G), tw, LineMul<1>());
                 }
                 DLPD_SYNC();
                 DLPD_FOR_TEAMS(g, G, TNT) {
-                    const SubTeam<TNT> tm{DLPD_TEAM_TID(TNT), g + 1};
+                    const SubTeam<TNT, DLPD_PLANE_DUAL != 0> tm{DLPD_TEAM_TID(TNT), g + 1};
                     cpx* rows = pl + g * (N / G) * NP;
                     PointMul<MulSpec> mul{MulSpec{spec + g * (N / G)}};
-                    team_fwd_head<N, N / G, 1>(tm, rows, tw, LineMul<NP>());                        // along y, rows kx'
-                    team_mid<N, N / G, 1>(tm, rows, tw, LineMul<NP>(), mul);                        // y tail . multiply . inverse y tail
-                    team_inv_head<N, N / G, 1>(tm, rows, tw, LineMul<NP>());                        // inverse y
+                    team_fwd_head<N, N / G, 1, PP>(tm, rows, tw, LineMul<NP>());                        // along y, rows kx'
+                    team_mid<N, N / G, 1, PP>(tm, rows, tw, LineMul<NP>(), mul);                        // y tail . multiply . inverse y tail
+                    team_inv_head<N, N / G, 1, PP>(tm, rows, tw, LineMul<NP>());                        // inverse y
                 }
                 DLPD_SYNC();
                 DLPD_FOR_TEAMS(g, G, TNT) {
-                    const SubTeam<TNT> tm{DLPD_TEAM_TID(TNT), g + 1};
+                    const SubTeam<TNT, DLPD_PLANE_DUAL != 0> tm{DLPD_TEAM_TID(TNT), g + 1};
                     cpx* cols = pl + g * (N / G);
-                    team_inv_tail<N, N / G, NP>(tm, cols, tw, LineMul<1>());                        // inverse x
+                    team_inv_tail<N, N / G, NP, PP>(tm, cols, tw, LineMul<1>());                        // inverse x
                     if (p.tiled) {
-                        static_assert((N / G) % 2 == 0 && (N / 2 / LinePlan<N>::R0) % 2 == 0, "tiled pair stores");
+                        static_assert((N / G) % 2 == 0 && (N / 2 / PP::R0) % 2 == 0, "tiled pair stores");
                         GlobalOutPair<StoreS2TiledPair> out{StoreS2TiledPair{p.out + plane * N * N + g * (N / G / 2) * 4}};
-                        team_inv_head<N, N / G, NP>(tm, cols, tw, LineMul<1>(), out);
+                        team_inv_head<N, N / G, NP, PP>(tm, cols, tw, LineMul<1>(), out);
                     } else {
                         GlobalOut<StoreS2> out{StoreS2{p.out + plane * N * N + g * (N / G)}};
-                        team_inv_head<N, N / G, NP>(tm, cols, tw, LineMul<1>(), out);
+                        team_inv_head<N, N / G, NP, PP>(tm, cols, tw, LineMul<1>(), out);
                     }
                 }
                 return;
             }
         }
         GlobalIn<LoadS1> in{LoadS1{p.in + plane * L * L}};
-        fft_fwd_head<N, L, NP, NT>(pl, tw, LineMul<1>(), in);                   // along x, columns y < L
+        fft_fwd_head<N, L, NP, NT, PP>(pl, tw, LineMul<1>(), in);                   // along x, columns y < L
         prefetch(p, bx, spec);
-        fft_fwd_tail<N, L, NP, NT>(pl, tw, LineMul<1>());
-        fft_fwd_head<N, N, 1, NT>(pl, tw, LineMul<NP>());                       // along y, all rows kx'
+        fft_fwd_tail<N, L, NP, NT, PP>(pl, tw, LineMul<1>());
+        fft_fwd_head<N, N, 1, NT, PP>(pl, tw, LineMul<NP>());                       // along y, all rows kx'
         if (p.spec == nullptr) {
-            fft_fwd_tail<N, N, 1, NT>(pl, tw, LineMul<NP>());
+            fft_fwd_tail<N, N, 1, NT, PP>(pl, tw, LineMul<NP>());
             cpx* out = p.out + plane * N * N;
             DLPD_FOR_TASKS(t, N * N, NT) {
                 const int kx = t % N, ky = t / N;                               // transposed store, coalesced over kx
@@ -513,20 +517,20 @@ template <int L_> struct Plane {
             return;
         }
         PointMul<MulSpec> mul{MulSpec{spec}};
-        fft_mid<N, N, 1, NT>(pl, tw, LineMul<NP>(), mul);                       // y tail . multiply . inverse y tail
-        fft_inv_head<N, N, 1, NT>(pl, tw, LineMul<NP>());                       // inverse y
-        fft_inv_tail<N, N, NP, NT>(pl, tw, LineMul<1>());                       // inverse x
+        fft_mid<N, N, 1, NT, PP>(pl, tw, LineMul<NP>(), mul);                       // y tail . multiply . inverse y tail
+        fft_inv_head<N, N, 1, NT, PP>(pl, tw, LineMul<NP>());                       // inverse y
+        fft_inv_tail<N, N, NP, NT, PP>(pl, tw, LineMul<1>());                       // inverse x
         if (p.tiled) {
-            if constexpr ((N / 2 / LinePlan<N>::R0) % 2 == 0) {
+            if constexpr ((N / 2 / PP::R0) % 2 == 0) {
                 GlobalOutPair<StoreS2TiledPair> out{StoreS2TiledPair{p.out + plane * N * N}};
-                fft_inv_head<N, N, NP, NT>(pl, tw, LineMul<1>(), out);
+                fft_inv_head<N, N, NP, NT, PP>(pl, tw, LineMul<1>(), out);
             } else {
                 GlobalOut<StoreS2Tiled> out{StoreS2Tiled{p.out + plane * N * N}};
-                fft_inv_head<N, N, NP, NT>(pl, tw, LineMul<1>(), out);
+                fft_inv_head<N, N, NP, NT, PP>(pl, tw, LineMul<1>(), out);
             }
         } else {
             GlobalOut<StoreS2> out{StoreS2{p.out + plane * N * N}};
-            fft_inv_head<N, N, NP, NT>(pl, tw, LineMul<1>(), out);
+            fft_inv_head<N, N, NP, NT, PP>(pl, tw, LineMul<1>(), out);
         }
     }
 
@@ -747,6 +751,121 @@ template <int C0, int C1, int H> struct FilterW {
 };
 DLPD_DEV float2 dup2(float w) { return make_float2(w, w); }
 
+// ------------------------------------------------------------------------------------------------------
+// Tensor-core form of the filter's first layer (level-0 half: C0 = 16 correlation channels -> H hidden units).
+// mma.sync.m16n8k16 on fp16 operands with fp32 accumulation, each fp32 factor split into two fp16 terms
+//     a = a_hi + a_lo,  w = w_hi + w_lo,   a w ~= a_hi w_hi + a_lo w_hi + a_hi w_lo        (22 significant bits)
+// so the result agrees with the FFMA chain to fp32 rounding level.  fp16 has a 5-bit exponent, so every correlation
+// channel is first scaled by a power of two 2^-e_c chosen from the Cauchy-Schwarz bound
+//     |corr_c[t]| <= ||A_c||_2 ||B_c^rot||_2   (x4 head room for the trilinear resampling of B)
+// to |a'| <= 2^15, and the weights by 2^(e_c - f) with f such that max |w'| <= 2^14: all scalings are exact, 2^-f is
+// carried through the ReLU into the second layer's weights.  SumSq measures the norms (set_receptor / set_ligand /
+// per chunk for pre-rotated ligands), FilterPrep turns them plus the weights into the per-lane B fragments.
+// ------------------------------------------------------------------------------------------------------
+template <int C0, int H> struct MlpDev {
+    float ascale[C0];                        // 2^-e_c
+    float W2s[H];                            // W2[j] 2^f
+    float hscale, pad_[3];                   // 2^-f: applied to the level-1 hidden contribution (h1) on load
+    unsigned int wfrag[(H + 7) / 8][2][2][32];   // [n-tile][hi | lo][B register][lane] packed half2
+};
+
+struct SumSqParams {
+    const float* v;          // [n][C][V]
+    float* out;              // [C]: max over n of sum_v v^2  (pre-zeroed; non-negative floats order like their bits)
+    int C, V;
+};
+struct SumSq {
+    typedef SumSqParams Params;
+    static constexpr int NT = 256;
+    static constexpr int SMEM = 0;
+    // grid: x = C, y = n
+    static DLPD_DEV void body(const Params& p, int bx, int by, int, char*) {
+        const float* v = p.v + ((long)by * p.C + bx) * p.V;
+        float acc = 0.0f;
+        DLPD_FOR_TASKS(t, p.V, NT) acc = fmaf_(v[t], v[t], acc);
+#if defined(DLPD_EMU)
+        if (acc > p.out[bx]) p.out[bx] = acc;
+#else
+        __shared__ float red[NT / 32];
+        DLPD_UNROLL
+        for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+        if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = acc;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float s = 0.0f;
+            for (int w = 0; w < NT / 32; ++w) s += red[w];
+            atomicMax(reinterpret_cast<unsigned int*>(p.out) + bx, __float_as_uint(s));
+        }
+#endif
+    }
+};
+
+#if !defined(DLPD_EMU)
+DLPD_DEV unsigned int pack_h2(float lo, float hi) {       // low half <- lo, high half <- hi (round to nearest)
+    unsigned int r;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+DLPD_DEV float h_round(float w) {                          // fp16(w) as fp32
+    unsigned short h;
+    float r;
+    asm("cvt.rn.f16.f32 %0, %1;" : "=h"(h) : "f"(w));
+    asm("cvt.f32.f16 %0, %1;" : "=f"(r) : "h"(h));
+    return r;
+}
+DLPD_DEV void mma_f16_16816(float (&d)[4], const unsigned int (&a)[4], unsigned int b0, unsigned int b1) {
+    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+                 : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+// k index of the MMA -> correlation channel: lane q (= lane & 3) holds k = 2q, 2q+1, 2q+8, 2q+9 and reads channels
+// q, q+4, q+8, q+12 -- its four loads of a voxel row then hit distinct shared-memory banks across the warp
+DLPD_DEV int mlp_channel(int q, int kk) { return q + 4 * kk; }
+
+template <int C0, int C1, int H> struct PrepParams {
+    const float* rec_ss;     // [C0] sum of squares of the receptor's level-0 feature volumes
+    const float* lig_ss;     // [C0] same for the ligand (max over rotations when it arrives pre-rotated)
+    MlpDev<C0, H>* out;
+    FilterW<C0, C1, H> filt;
+};
+template <int C0, int C1, int H> struct FilterPrep {
+    typedef PrepParams<C0, C1, H> Params;
+    static constexpr int NT = 128;
+    static constexpr int SMEM = 0;
+    static_assert(C0 == 16 && H % 8 == 0, "m16n8k16 tiling of the first filter layer");
+    static DLPD_DEV void body(const Params& p, int, int, int, char*) {
+        int e[C0];
+        DLPD_UNROLL
+        for (int c = 0; c < C0; ++c) {
+            const float rs = p.rec_ss[c], ls = p.lig_ss[c];
+            int ec = 0;
+            if (rs > 0.0f && ls > 0.0f && rs < 3.0e38f && ls < 3.0e38f)
+                ec = (int)ceilf(2.0f + 0.5f * (log2f(rs) + log2f(ls))) - 15;
+            e[c] = ec < -60 ? -60 : (ec > 60 ? 60 : ec);
+        }
+        float m = 0.0f;
+        for (int c = 0; c < C0; ++c)
+            for (int j = 0; j < H; ++j) m = fmaxf(m, fabsf(ldexpf(p.filt.W1t[c * H + j], e[c])));
+        int f = 0;
+        if (m > 0.0f && m < 3.0e38f) f = (int)ceilf(log2f(m)) - 14;
+        f = f < -100 ? -100 : (f > 100 ? 100 : f);
+        MlpDev<C0, H>& o = *p.out;
+        DLPD_FOR_TASKS(t, C0, NT) o.ascale[t] = ldexpf(1.0f, -e[t]);
+        DLPD_FOR_TASKS(t, H, NT) o.W2s[t] = ldexpf(p.filt.W2[t], f);
+        if (threadIdx.x == 0) o.hscale = ldexpf(1.0f, -f);
+        DLPD_FOR_TASKS(t, (H / 8) * 2 * 32, NT) {
+            const int lane = t % 32, r = (t / 32) % 2, nt = t / 64;
+            const int g = lane >> 2, q = lane & 3, j = 8 * nt + g;
+            const int ca = mlp_channel(q, 2 * r), cb = mlp_channel(q, 2 * r + 1);
+            const float wa = ldexpf(p.filt.W1t[ca * H + j], e[ca] - f), wb = ldexpf(p.filt.W1t[cb * H + j], e[cb] - f);
+            const float ha = h_round(wa), hb = h_round(wb);
+            o.wfrag[nt][0][r][lane] = pack_h2(ha, hb);
+            o.wfrag[nt][1][r][lane] = pack_h2(wa - ha, wb - hb);
+        }
+    }
+};
+#endif
+
 // order-preserving map float -> uint32 (a < b  <=>  key(a) < key(b)); +-0 collapse to +0 like torch.min
 DLPD_HD unsigned int score_key(float s) {
     if (s == 0.0f) s = 0.0f;
@@ -888,13 +1007,14 @@ template <int C0, int C1, int H> struct EpiParams {
     unsigned int* cand_count;     // total number of qualifying translations (may exceed cand_cap: caller re-runs exactly)
     unsigned int cand_cap, cand_key;
     int rot_base;                 // index of this chunk's first rotation within the caller's batch
+    const MlpDev<C0, H>* mlp;     // tensor-core form of the first filter layer (FilterPrep), or nullptr: FP32 FFMA chain
     const cpx* tw0;               // [N]
     int n_rot, n_tiles, grid;     // tiles = P * (N/2)^2; grid = number of CTAs walking over them
     float tau;
     FilterW<C0, C1, H> filt;
 };
 
-template <int L_, int C0, int C1, int H, int TY_ = 2> struct Epilogue {
+template <int L_, int C0, int C1, int H, int TY_ = 2, bool TC_ = false> struct Epilogue {
     typedef EpiParams<C0, C1, H> Params;
     static constexpr int L = L_, N = 2 * L_, N1 = L_, T = L_;      // T = N/2 tile rows along x
     // tile = 2 x TY (x,y) columns: 2x2 normally; 2x1 when two 2x2 buffers do not fit shared memory (N = 256) -- the
@@ -907,7 +1027,8 @@ template <int L_, int C0, int C1, int H, int TY_ = 2> struct Epilogue {
     // stalling every warp); the first NC threads transform and score
     static constexpr int NPROD = (N >= 128) ? DLPD_EPI_NPROD : 32, NC = NT - NPROD;
     static constexpr int BUF = N * NL0, HB = N1 * H;
-    static constexpr int SMEM = (2 * BUF + 2 * HB + N) * (int)sizeof(cpx) + 64 * 8;
+    static constexpr int MLP_BYTES = TC_ ? ((int)sizeof(MlpDev<C0, H>) + 15) / 16 * 16 : 0;      // shared-memory copy of the MMA fragments
+    static constexpr int SMEM = (2 * BUF + 2 * HB + N) * (int)sizeof(cpx) + 64 * 8 + MLP_BYTES;
     static constexpr int QPT = NPROD / TY;         // (c, kz) rows covered per sweep of the producer threads
     static constexpr int TILES = T * TPR;          // tiles per pair
     static_assert(HB % 2 == 0 && NPROD % 32 == 0 && NC % 32 == 0 && (TY_ == 1 || TY_ == 2), "team shapes");
@@ -966,11 +1087,146 @@ template <int L_, int C0, int C1, int H, int TY_ = 2> struct Epilogue {
 
     // transform + score one tile (consumer team)
     template <class TM>
-    static DLPD_DEV void score_tile(const Params& p, const TM& tm, cpx* b0, const cpx* h1, const cpx* tw0, int pair, int x0, int y0,
-                                    unsigned long long& bestA, unsigned long long& bestB) {
+    static DLPD_DEV void score_tile(const Params& p, const TM& tm, cpx* b0, const cpx* h1, const cpx* tw0, const MlpDev<C0, H>* ms,
+                                    int pair, int x0, int y0, unsigned long long& bestA, unsigned long long& bestB) {
         transform_tile(tm, b0, tw0);
+#if !defined(DLPD_EMU)
+        if constexpr (MMA_OK) {
+            if (p.mlp != nullptr) {
+                score_voxels_mma(p, tm, b0, h1, *ms, pair, x0, y0, bestA, bestB);
+                return;
+            }
+        }
+#endif
         score_voxels(p, tm, b0, h1, pair, x0, y0, bestA, bestB);
     }
+    // TC_: this instantiation carries the tensor-core filter path (a separate kernel, so the FP32 kernel keeps its registers)
+    static constexpr bool MMA_OK = TC_ && (C0 == 16) && (H % 8 == 0) && ((XY * N) % 16 == 0) && (NC % 32 == 0);
+
+#if !defined(DLPD_EMU)
+    // The same filter with the level-0 half of the first layer on the tensor cores (see MlpDev).  One warp per 16 voxels
+    // (M) x 2 rotations; K = 16 channels; N = H hidden units in tiles of 8.  Lane (g = lane / 4, q = lane % 4) owns voxel
+    // rows g and g + 8 in the A / C fragments; after the layer-2 partial sums are reduced over the quad, lane q finishes
+    // (row q / 2, rotation q % 2): clash mask, argmin key, optional score / candidate output.
+    template <class TM>
+    static DLPD_DEV void score_voxels_mma(const Params& p, const TM& tm, const cpx* b0, const cpx* h1, const MlpDev<C0, H>& m,
+                                          int pair, int x0, int y0, unsigned long long& bestA, unsigned long long& bestB) {
+        constexpr int NTL = H / 8, NMT = XY * N / 16;
+        const int lane = tm.tid() & 31, warp = tm.tid() >> 5, g = lane >> 2, q = lane & 3;
+        // m is the CTA's shared-memory copy: the B fragments stay in registers for the whole tile, the scales and the
+        // second-layer weights are re-read where they are used (short live ranges: no spills at 768 threads)
+        unsigned int wf[NTL][2][2];
+        DLPD_UNROLL
+        for (int nt = 0; nt < NTL; ++nt) {
+            DLPD_UNROLL
+            for (int s = 0; s < 2; ++s) {
+                wf[nt][s][0] = m.wfrag[nt][s][0][lane];
+                wf[nt][s][1] = m.wfrag[nt][s][1][lane];
+            }
+        }
+        const int rotA = 2 * pair, rotB = 2 * pair + 1;
+        const bool hasB = rotB < p.n_rot;
+        for (int mt = warp; mt < NMT; mt += TM::NT / 32) {
+            int zr[2], xyr[2];
+            float2 x[2][4];
+            DLPD_UNROLL
+            for (int r = 0; r < 2; ++r) {
+                const int v = 16 * mt + g + 8 * r;
+                xyr[r] = v % XY;
+                zr[r] = v / XY;
+                DLPD_UNROLL
+                for (int kk = 0; kk < 4; ++kk) x[r][kk] = b0[zr[r] * NL0 + mlp_channel(q, kk) * XY + xyr[r]];
+            }
+            // accumulators start from the level-1 hidden contribution (+ b1) of the voxel's level-1 parent
+            float acc[2][NTL][4];
+            DLPD_UNROLL
+            for (int r = 0; r < 2; ++r) {
+                const cpx* hz = h1 + (zr[r] >> 1) * H + 2 * q;
+                DLPD_UNROLL
+                for (int nt = 0; nt < NTL; ++nt) {
+                    const float4 hv = *reinterpret_cast<const float4*>(hz + 8 * nt);     // (j: rotA, rotB), (j+1: rotA, rotB)
+                    const float hs = m.hscale;
+                    acc[0][nt][2 * r] = hv.x * hs;
+                    acc[1][nt][2 * r] = hv.y * hs;
+                    acc[0][nt][2 * r + 1] = hv.z * hs;
+                    acc[1][nt][2 * r + 1] = hv.w * hs;
+                }
+            }
+            // scale, split into fp16 hi + lo, pack the A fragments of both rotations
+            unsigned int ah[2][4], al[2][4];
+            {
+                float2 xh[2][4], xl[2][4];
+                DLPD_UNROLL
+                for (int r = 0; r < 2; ++r) {
+                    DLPD_UNROLL
+                    for (int kk = 0; kk < 4; ++kk) {
+                        const float2 xs = fmul2_(x[r][kk], dup2(m.ascale[mlp_channel(q, kk)]));
+                        xh[r][kk] = make_float2(__uint_as_float(__float_as_uint(xs.x) & 0xffffe000u),
+                                                __uint_as_float(__float_as_uint(xs.y) & 0xffffe000u));
+                        xl[r][kk] = fadd2_(xs, make_float2(-xh[r][kk].x, -xh[r][kk].y));
+                    }
+                }
+                DLPD_UNROLL
+                for (int r = 0; r < 2; ++r) {
+                    DLPD_UNROLL
+                    for (int h = 0; h < 2; ++h) {          // register r + 2h: row g + 8r, k = 2q + 8h, 2q + 8h + 1
+                        ah[0][r + 2 * h] = pack_h2(xh[r][2 * h].x, xh[r][2 * h + 1].x);
+                        ah[1][r + 2 * h] = pack_h2(xh[r][2 * h].y, xh[r][2 * h + 1].y);
+                        al[0][r + 2 * h] = pack_h2(xl[r][2 * h].x, xl[r][2 * h + 1].x);
+                        al[1][r + 2 * h] = pack_h2(xl[r][2 * h].y, xl[r][2 * h + 1].y);
+                    }
+                }
+            }
+            // three products per term; the 2 * NTL accumulators are independent, so consecutive MMAs never wait on each other
+            DLPD_UNROLL
+            for (int rot = 0; rot < 2; ++rot) {
+                DLPD_UNROLL
+                for (int nt = 0; nt < NTL; ++nt) mma_f16_16816(acc[rot][nt], al[rot], wf[nt][0][0], wf[nt][0][1]);
+            }
+            DLPD_UNROLL
+            for (int rot = 0; rot < 2; ++rot) {
+                DLPD_UNROLL
+                for (int nt = 0; nt < NTL; ++nt) mma_f16_16816(acc[rot][nt], ah[rot], wf[nt][1][0], wf[nt][1][1]);
+            }
+            DLPD_UNROLL
+            for (int rot = 0; rot < 2; ++rot) {
+                DLPD_UNROLL
+                for (int nt = 0; nt < NTL; ++nt) mma_f16_16816(acc[rot][nt], ah[rot], wf[nt][0][0], wf[nt][0][1]);
+            }
+            // ReLU + second layer: partial sums over this lane's 2 * NTL hidden units, reduced over the quad
+            float s[2][2];
+            DLPD_UNROLL
+            for (int rot = 0; rot < 2; ++rot) {
+                DLPD_UNROLL
+                for (int r = 0; r < 2; ++r) {
+                    float t = 0.0f;
+                    DLPD_UNROLL
+                    for (int nt = 0; nt < NTL; ++nt) {
+                        const float2 w2 = *reinterpret_cast<const float2*>(&m.W2s[8 * nt + 2 * q]);
+                        t = fmaf_(w2.x, fmaxf(acc[rot][nt][2 * r], 0.0f), t);
+                        t = fmaf_(w2.y, fmaxf(acc[rot][nt][2 * r + 1], 0.0f), t);
+                    }
+                    t += __shfl_xor_sync(0xffffffffu, t, 1);
+                    t += __shfl_xor_sync(0xffffffffu, t, 2);
+                    s[rot][r] = t;
+                }
+            }
+            const int r = q >> 1, rot = q & 1;
+            const float sc = p.filt.b2 + (r ? (rot ? s[1][1] : s[0][1]) : (rot ? s[1][0] : s[0][0]));
+            const int z = r ? zr[1] : zr[0], xy = r ? xyr[1] : xyr[0];
+            const cpx clash = b0[z * NL0 + C0 * XY + xy];
+            const float V = (rot ? clash.y : clash.x) < p.tau ? sc : 0.0f;     // (clash < tau).float() * score   (Docker.py:226,232)
+            const unsigned int lin = (unsigned int)(((x0 + (xy & 1)) * N + (y0 + (xy >> 1))) * N + z);
+            const unsigned long long key = ((unsigned long long)score_key(V) << 32) | lin;
+            if (rot) bestB = key < bestB ? key : bestB;
+            else bestA = key < bestA ? key : bestA;
+            if (rot == 0 || hasB) {
+                if (p.score_out != nullptr) p.score_out[(long)(rot ? rotB : rotA) * N * N * N + lin] = V;
+                if (p.cand != nullptr && (unsigned int)(key >> 32) <= p.cand_key) emit_candidate(p, V, rot ? rotB : rotA, lin);
+            }
+        }
+    }
+#endif
 
     // inverse z transform of the NL0 lines of a tile, in place
     template <class TM> static DLPD_DEV void transform_tile(const TM& tm, cpx* b0, const cpx* tw0) {
@@ -1031,7 +1287,12 @@ template <int L_, int C0, int C1, int H, int TY_ = 2> struct Epilogue {
         cpx* hbufs = bufs + 2 * BUF;                   // [2][z'][H]  (rotA, rotB): b1 + level-1 part of the hidden layer
         cpx* tw0 = hbufs + 2 * HB;
         unsigned long long* red = reinterpret_cast<unsigned long long*>(tw0 + N);
+        MlpDev<C0, H>* ms = reinterpret_cast<MlpDev<C0, H>*>(red + 64);
         DLPD_FOR_TASKS(t, N, NT) tw0[t] = p.tw0[t];
+        if (MMA_OK && p.mlp != nullptr) {
+            DLPD_FOR_TASKS(t, (int)sizeof(MlpDev<C0, H>) / 4, NT)
+                reinterpret_cast<unsigned int*>(ms)[t] = reinterpret_cast<const unsigned int*>(p.mlp)[t];
+        }
         if (bx < p.n_tiles) issue_loads(p, bx, bufs, hbufs);
         cp_async_commit();
         cp_async_wait_pending();
@@ -1060,7 +1321,7 @@ template <int L_, int C0, int C1, int H, int TY_ = 2> struct Epilogue {
                 cp_async_wait_pending();
             }
             if (consumer)
-                score_tile(p, tm, bufs + slot * BUF, hbufs + slot * HB, tw0, pair, 2 * tile_xh(r), tile_y0(r), bestA, bestB);
+                score_tile(p, tm, bufs + slot * BUF, hbufs + slot * HB, tw0, ms, pair, 2 * tile_xh(r), tile_y0(r), bestA, bestB);
         }
         if (cur_pair >= 0) flush_best(p, cur_pair, bestA, bestB, red);
     }

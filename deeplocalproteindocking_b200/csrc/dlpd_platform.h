@@ -110,9 +110,9 @@ template <int NT_, bool DUAL_ = false> struct CtaTeam {
 #endif
     DLPD_DEV void sync() const { DLPD_SYNC(); }
 };
-template <int NT_> struct SubTeam {
+template <int NT_, bool DUAL_ = false> struct SubTeam {
     static constexpr int NT = NT_;
-    static constexpr bool DUAL = false;
+    static constexpr bool DUAL = DUAL_;
     int tid_, bar_;
     DLPD_DEV int tid() const { return tid_; }
     DLPD_DEV void sync() const { named_barrier_sync(bar_, NT_); }

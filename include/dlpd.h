@@ -126,10 +126,18 @@ int dlpd_project_clash(const double* coords, const double* R, int nat, int n, in
  *                         a plan are laid out for the mode in force at dlpd_set_receptor time: do not switch between
  *                         dlpd_set_receptor and dlpd_search.
  * DLPD_OPT_EPILOGUE_TILE  0 = automatic, 1 = 2x1, 2 = 2x2 (x,y) columns per epilogue tile (classic epilogue)
- * DLPD_OPT_EPILOGUE_KIND  AUTO / CLASSIC / PIPELINED, see below */
+ * DLPD_OPT_EPILOGUE_KIND  AUTO / CLASSIC / PIPELINED, see below
+ * DLPD_OPT_FILTER_KIND    how the classic epilogue evaluates the level-0 half of SimpleFilter's first layer
+ *                         (DockingModels.py:29, 16 -> H): FP32 = packed FFMA chain; TENSOR = mma.sync m16n8k16 on fp16
+ *                         operands split hi + lo (three products per term, fp32 accumulation: agrees with the FFMA
+ *                         chain to fp32 rounding level; C0 = 16, H % 8 = 0 only); AUTO = FP32 (faster on B200) */
 #define DLPD_OPT_PLANE_MODE 1
 #define DLPD_OPT_EPILOGUE_TILE 2
 #define DLPD_OPT_EPILOGUE_KIND 3
+#define DLPD_OPT_FILTER_KIND 4
+#define DLPD_FILTER_AUTO 0
+#define DLPD_FILTER_FP32 1
+#define DLPD_FILTER_TENSOR 2
 #define DLPD_EPILOGUE_AUTO 0
 #define DLPD_EPILOGUE_CLASSIC 1     /* one consumer team: transform then filter, next tile prefetched            */
 #define DLPD_EPILOGUE_PIPELINED 2   /* load / transform / filter of consecutive half-tiles overlap (N <= 160)    */

@@ -329,3 +329,50 @@ def test_epilogue_kinds_80_many_rotations_identical():
         eng.close()
     _lib.set_option("epilogue_kind", "auto")
     assert torch.equal(out[0], out[1]) and torch.equal(out[0], out[2])
+
+
+# ---- first filter layer: packed FFMA chain vs fp16-split mma.sync -------------------------------------------------
+@pytest.fixture
+def tensor_filter():
+    _lib.set_option("filter_kind", "tensor")
+    yield
+    _lib.set_option("filter_kind", "auto")
+
+
+@pytest.mark.parametrize("L,C0,C1,H,n", [(8, 16, 32, 24, 3), (16, 16, 32, 24, 2), (20, 16, 32, 24, 5)])
+def test_tensor_filter_small_matches_oracle(L, C0, C1, H, n, tensor_filter):
+    test_search_small_matches_oracle(L, C0, C1, H, n)
+
+
+def test_tensor_filter_80_matches_oracle(tensor_filter):
+    test_search_full_size_80_matches_oracle()
+
+
+@pytest.mark.parametrize("scale", [1.0, 1e-3, 3e3])
+def test_filter_kinds_80_agree(scale):
+    """Tensor-core (fp16 hi+lo split, three products) vs FFMA first layer at L=80, 9 rotations, volumes scaled over six orders
+    of magnitude (the per-channel power-of-two scaling must keep fp16 in range): identical best translations, scores and the
+    whole masked score volume of one rotation within 1e-5 of the score range."""
+    L, C0, C1 = 80, 16, 32
+    rec, rec_clash = synthetic.learned_volumes(L, (C0, C1), seed=41)
+    lig, lig_clash = synthetic.learned_volumes(L, (C0, C1), seed=42)
+    rec = [v * scale for v in rec]
+    rec[0][3] *= 37.0                                   # channels of very different magnitude
+    rec[0][7] *= 1.0 / 64.0
+    filt = O.FilterWeights.random(C0 + C1, seed=43)
+    W1 = filt.W1.clone()
+    W1[:, :C0] /= scale                                 # keep the hidden pre-activations O(1)
+    Rs = R20[torch.arange(9) * 201 + 5]
+    out, vol = [], []
+    for kind in ("fp32", "tensor"):
+        _lib.set_option("filter_kind", kind)
+        eng = DockingSearch(L, (C0, C1), max_rot=8, device=DEV)
+        eng.set_receptor(rec, rec_clash); eng.set_ligand(lig, lig_clash); eng.set_filter((W1, filt.b1, filt.W2, filt.b2))
+        out.append(eng.search(Rs, 30.0)[0].cpu())
+        vol.append(eng.search(Rs[:1], 30.0, return_scores=True)[1].cpu())
+        eng.close()
+    _lib.set_option("filter_kind", "auto")
+    assert torch.equal(out[0][:, 1:], out[1][:, 1:])
+    rng = float(vol[0].abs().max())
+    assert (out[0][:, 0] - out[1][:, 0]).abs().max() <= 1e-5 * rng
+    assert (vol[0] - vol[1]).abs().max() <= 1e-5 * rng
