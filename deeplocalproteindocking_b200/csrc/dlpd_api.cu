@@ -13,6 +13,10 @@
 #include <string>
 #include <vector>
 
+#ifndef DLPD_PLANEX_PERSISTENT
+#define DLPD_PLANEX_PERSISTENT 1      // cluster plane kernel: resident clusters loop over the planes
+#endif
+
 // ------------------------------------------------------------------------------------------------------
 // runtime shim
 // ------------------------------------------------------------------------------------------------------
@@ -46,6 +50,7 @@ template <class K> static int launch(dim3 g, const typename K::Params& p, dlpd_s
     ++g_launches;
     return 0;
 }
+template <class K> static int launch_mb(dim3 g, const typename K::Params& p, dlpd_stream_t st) { return launch<K>(g, p, st); }
 // thread-block clusters: the CL CTAs of a cluster run phase A one after the other, then phase B with every CTA's
 // shared memory visible (distributed shared memory on the device)
 template <class K> static int launch_cluster(unsigned clusters, const typename K::Params& p, dlpd_stream_t) {
@@ -53,7 +58,7 @@ template <class K> static int launch_cluster(unsigned clusters, const typename K
     cpx* slabs[K::CL];
     for (int r = 0; r < K::CL; ++r) slabs[r] = reinterpret_cast<cpx*>(smem[r].data());
     for (unsigned cid = 0; cid < clusters; ++cid) {
-        for (int r = 0; r < K::CL; ++r) K::phase_a(p, (int)cid, r, smem[r].data());
+        for (int r = 0; r < K::CL; ++r) K::phase_a(p, (int)cid, r, smem[r].data(), cid + 1 < clusters ? (int)cid + 1 : -1);
         if (K::exchanges(p))
             for (int r = 0; r < K::CL; ++r) K::phase_b(p, (int)cid, r, slabs, smem[r].data());
     }
@@ -127,20 +132,26 @@ template <class K> static int launch_mb(dim3 g, const typename K::Params& p, dlp
 }
 
 // kernels that span a thread-block cluster of K::CL CTAs (distributed shared memory)
+// persistent: the resident clusters walk over the work items cid0, cid0 + n_resident, ... (no cluster launch per item)
 template <class K>
-__global__ void __launch_bounds__(K::NT, K::MINB) dlpd_cluster_kernel(const __grid_constant__ typename K::Params p) {
+__global__ void __launch_bounds__(K::NT, K::MINB) dlpd_cluster_kernel(const __grid_constant__ typename K::Params p, int n_items) {
     extern __shared__ __align__(16) char smem[];
     namespace cg = cooperative_groups;
     cg::cluster_group cl = cg::this_cluster();
-    const int rank = (int)cl.block_rank(), cid = (int)(blockIdx.x / K::CL);
-    K::phase_a(p, cid, rank, smem);
-    if (K::exchanges(p)) {                 // uniform over the cluster
-        cl.sync();
-        cpx* slabs[K::CL];
+    const int rank = (int)cl.block_rank(), step = (int)(gridDim.x / K::CL);
+    cpx* slabs[K::CL];
 #pragma unroll
-        for (int r = 0; r < K::CL; ++r) slabs[r] = cl.map_shared_rank(reinterpret_cast<cpx*>(smem), r);
-        K::phase_b(p, cid, rank, slabs, smem);
-        cl.sync();                         // nobody leaves while its shared memory is still being read
+    for (int r = 0; r < K::CL; ++r) slabs[r] = cl.map_shared_rank(reinterpret_cast<cpx*>(smem), r);
+    const bool exch = K::exchanges(p);     // uniform over the grid
+    for (int cid = (int)(blockIdx.x / K::CL); cid < n_items; cid += step) {
+        K::phase_a(p, cid, rank, smem, cid + step < n_items ? cid + step : -1);
+        if (exch) {
+            cl.sync();
+            K::phase_b(p, cid, rank, slabs, smem);
+            cl.sync();                     // nobody re-fills (or leaves) while its shared memory is still being read
+        } else {
+            __syncthreads();
+        }
     }
 }
 template <class K> static int launch_cluster(unsigned clusters, const typename K::Params& p, dlpd_stream_t st) {
@@ -165,7 +176,15 @@ template <class K> static int launch_cluster(unsigned clusters, const typename K
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    CU(cudaLaunchKernelEx(&cfg, dlpd_cluster_kernel<K>, p));
+    static int resident[64] = {};          // clusters of this kernel the device can hold at once
+    if (dev < 64 && resident[dev] == 0) {
+        int n = 0;
+        if (cudaOccupancyMaxActiveClusters(&n, dlpd_cluster_kernel<K>, &cfg) != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = 1 << 30; }
+        resident[dev] = n;
+    }
+    const unsigned grid_clusters = (DLPD_PLANEX_PERSISTENT && dev < 64 && (unsigned)resident[dev] < clusters) ? (unsigned)resident[dev] : clusters;
+    cfg.gridDim = dim3(grid_clusters * K::CL);
+    CU(cudaLaunchKernelEx(&cfg, dlpd_cluster_kernel<K>, p, (int)clusters));
     ++g_launches;
     return 0;
 }
@@ -265,7 +284,17 @@ template <int L> static int launch_plane_t(const PlaneParams& p, dlpd_stream_t s
         if constexpr (HasPlaneX<L>::value) return launch_cluster<PlaneX<L, 4> >((unsigned)(p.P * 2 * L * p.C), p, st);
         else return fail(DLPD_EINVAL, "the cluster plane kernel is not compiled for this box size");
     } else {
-        if constexpr (HasPlane<L>::value) return launch<Plane<L> >(dim3((unsigned)(p.P * 2 * L * p.C)), p, st);
+        if constexpr (HasPlane<L>::value) {
+            const int total = p.P * 2 * L * p.C;
+            PlaneParams q = p;
+            q.grid = 0;
+            // fused search on the big plane: one persistent CTA per SM walking over the planes
+            if (DLPD_PLANE_PERSISTENT && Plane<L>::G > 1 && p.spec != nullptr && p.wave > 0 && p.wave < total) {
+                q.grid = p.wave;
+                return launch_mb<Plane<L> >(dim3((unsigned)q.grid), q, st);
+            }
+            return launch_mb<Plane<L> >(dim3((unsigned)total), q, st);
+        }
         else return fail(DLPD_EINVAL, "the plane of this box size does not fit one SM: use the cluster plane kernel");
     }
 }
@@ -471,7 +500,7 @@ static int real_spectra(int L, const float* vols, int C, cpx* s1, cpx* spec, con
     f.C = C; f.Ctot = C; f.c_out0 = 0; f.c_ext = -1; f.ext_all = 0; f.n_rot = 1; f.center = 0.f;
     TRY(launch_fwdz(L, f, 1, st));
     PlaneParams q;
-    q.in = s1; q.out = spec; q.spec = nullptr; q.spec_pair_stride = 0; q.tw = tw; q.C = C; q.P = 1; q.tiled = 0; q.wave = 1 << 30;
+    q.in = s1; q.out = spec; q.spec = nullptr; q.spec_pair_stride = 0; q.tw = tw; q.C = C; q.P = 1; q.tiled = 0; q.wave = 1 << 30; q.grid = 0;
     q.scale = (float)(1.0 / ((double)N * N * N));
     TRY(launch_plane(L, q, st));
     return 0;
@@ -707,7 +736,7 @@ static int search_chunk(dlpd_plan* p, const float* R, const float* clash_rot, co
     }
     PlaneParams q;
     q.in = p->s1_0; q.out = p->s2_0; q.spec = p->rspec0; q.spec_pair_stride = 0; q.tw = p->tw0; q.C = p->C0 + 1; q.P = P;
-    q.scale = 1.f; q.tiled = 1; q.wave = DLPD_PLANE_WAVES * p->sm_count;
+    q.scale = 1.f; q.tiled = 1; q.wave = DLPD_PLANE_WAVES * p->sm_count; q.grid = 0;
     { ProfScope ps(p, DLPD_PROFILE_PLANE0, st); TRY(launch_plane(L, q, st)); }
     q.in = p->s1_1; q.out = p->s2_1; q.spec = p->rspec1; q.tw = p->tw1; q.C = p->C1; q.tiled = 0; q.wave = 2 * p->sm_count;
     { ProfScope ps(p, DLPD_PROFILE_PLANE1, st); TRY(launch_plane(L1, q, st)); }
@@ -904,7 +933,7 @@ extern "C" int dlpd_volume_correlate(const float* v1, const float* v2, float* ou
         f.C = 1; f.Ctot = 1; f.c_out0 = 0; f.c_ext = -1; f.ext_all = 0; f.n_rot = 1; f.center = 0.f;
         TRY(launch_fwdz(L, f, q, st));
         PlaneParams pl;
-        pl.in = w.s1; pl.out = w.spec; pl.spec = nullptr; pl.spec_pair_stride = 0; pl.tw = w.tw; pl.C = 1; pl.P = q; pl.tiled = 0; pl.wave = 1 << 30;
+        pl.in = w.s1; pl.out = w.spec; pl.spec = nullptr; pl.spec_pair_stride = 0; pl.tw = w.tw; pl.C = 1; pl.P = q; pl.tiled = 0; pl.wave = 1 << 30; pl.grid = 0;
         pl.scale = (float)(1.0 / ((double)N * N * N));
         TRY(launch_plane(L, pl, st));
         f.src = v2 + n3(L) * i0;

@@ -209,6 +209,11 @@ template <int KIND, int RA, int RB, int LEN, int NB, int TWN, int ES> struct Fft
                 else a[i][k] = in.f(l, e0 + i * M + k * M2);
             }
         }
+        compute(a, tw, l, e0, j, mul);
+    }
+    // the butterflies of a task whose values are already in a[][] (pruned pass: a[0][*] only)
+    template <class Mul>
+    static DLPD_DEV void compute(cpx (&a)[RA][RB], const cpx* tw, int l, int e0, int j, Mul& mul) {
         if (FWD) {
             // outer DFT over i for each k, then twiddle w_NB^{(j + k*M2) * pa}
             DLPD_UNROLL
@@ -353,6 +358,41 @@ template <int KIND, int RA, int RB, int NLINES, int LEN, int NB, int TWN, int ES
 DLPD_DEV void fft_pass(cpx* s, const cpx* tw, LineOff off, In in = In(), Out out = Out(), Mul mul = Mul()) {
     fft_pass_team<KIND, RA, RB, NLINES, LEN, NB, TWN, ES>(CtaTeam<NT>(), s, tw, off, in, out, mul);
 }
+
+// Pruned forward head whose inputs were fetched into registers ahead of time (persistent kernels: the next work item's
+// global loads are issued while the current one finishes).  Thread `tid` owns tasks tid, tid + NT, ...: exactly NPRE each.
+template <int RB, int NLINES, int LEN, int TWN, int ES, int NPRE, class TM, class LineOff>
+struct PrunedHeadPre {
+    typedef FftTask<PASS_DIF_PRUNED, 2, RB, LEN, LEN, TWN, ES> T;
+    static_assert(NLINES * T::TPL == NPRE * TM::NT, "every thread owns exactly NPRE tasks");
+    // fetch: v[u][k] <- element (j + k*M2) of line l of task u, through `in`
+    template <class In> static DLPD_DEV void fetch(const TM& tm, cpx (&v)[NPRE][RB], In in) {
+        DLPD_UNROLL
+        for (int u = 0; u < NPRE; ++u) {
+            const int t = tm.tid() + u * TM::NT, l = t % NLINES, j = t / NLINES;
+            DLPD_UNROLL
+            for (int k = 0; k < RB; ++k) v[u][k] = in.f(l, j + k * T::M2);
+        }
+    }
+    static DLPD_DEV void run(const TM& tm, cpx* s, const cpx* tw, LineOff off, const cpx (&v)[NPRE][RB]) {
+        NoHook none;
+        DLPD_UNROLL
+        for (int u = 0; u < NPRE; ++u) {
+            const int t = tm.tid() + u * TM::NT, l = t % NLINES, j = t / NLINES;
+            cpx a[2][RB];
+            DLPD_UNROLL
+            for (int k = 0; k < RB; ++k) a[0][k] = v[u][k];
+            T::compute(a, tw, l, j, j, none);
+            cpx* p = s + off(l) + j * ES;
+            DLPD_UNROLL
+            for (int i = 0; i < 2; ++i) {
+                DLPD_UNROLL
+                for (int k = 0; k < RB; ++k) p[(i * T::M + k * T::M2) * ES] = a[i][k];
+            }
+        }
+        tm.sync();
+    }
+};
 
 // ---- whole-line helpers -------------------------------------------------------------------------------------
 // forward head: pruned (2, R0) pair at block N; reads elements [0, N/2) only (optionally from global via `in`)

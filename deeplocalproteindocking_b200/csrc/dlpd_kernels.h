@@ -33,6 +33,12 @@
 #ifndef DLPD_EPI_NPROD
 #define DLPD_EPI_NPROD 64
 #endif
+#ifndef DLPD_EPI_DUAL
+#define DLPD_EPI_DUAL 0
+#endif
+#ifndef DLPD_PLANE_MID_DUAL
+#define DLPD_PLANE_MID_DUAL 0
+#endif
 #ifndef DLPD_HID_NT
 #define DLPD_HID_NT 512
 #endif
@@ -41,6 +47,12 @@
 #endif
 #ifndef DLPD_PLANE_DUAL
 #define DLPD_PLANE_DUAL 1            // two butterfly tasks per iteration in Plane's plain passes (needs registers: 640 threads x 96)
+#endif
+#ifndef DLPD_PLANE_PRELOAD
+#define DLPD_PLANE_PRELOAD 0         // persistent Plane: next plane's first-pass inputs fetched into registers early (measured: 5.81 vs 5.38 ms without -- the 20 registers cost more than the hidden latency)
+#endif
+#ifndef DLPD_PLANE_PERSISTENT
+#define DLPD_PLANE_PERSISTENT 1
 #endif
 #ifndef DLPD_PLANE_PREFETCH
 #define DLPD_PLANE_PREFETCH 2
@@ -403,6 +415,8 @@ struct PlaneParams {
     const cpx* tw;           // [N]
     int C, P;
     int wave;                // CTAs per wave (SM count x resident CTAs): distance of the S1 look-ahead prefetch
+    int grid;                // > 0: persistent launch with this many CTAs, each walking planes bx, bx + grid, ... (fused search,
+                             //      team path); 0: one CTA per plane
     int tiled;               // S2 rows in natural [x][y] order (0) or in 2x2 tiles [x/2][y/2][x&1][y&1] (1, fused search)
     float scale;
 };
@@ -413,6 +427,7 @@ template <int L_> struct Plane {
     typedef PlanePlan<N> PP;                                 // factorisation of the x / y lines
     static constexpr int NT = (N >= 128) ? DLPD_PLANE_NT : ((N >= 64) ? DLPD_PLANE_NT_MID : 256);   // 640 = 5 teams x 128: whole head passes per round, <= 102 registers
     static constexpr int SMEM = (N * NP + N) * (int)sizeof(cpx);
+    static constexpr int MINB = (SMEM <= 56 * 1024) ? 4 : 1;   // resident CTAs per SM the register budget is cut for
     // teams (see body): only for the big plane, and only when rows, columns and threads split evenly
     static constexpr int G = (N >= 128 && N % DLPD_PLANE_TEAMS == 0 && L_ % DLPD_PLANE_TEAMS == 0 && NT % (32 * DLPD_PLANE_TEAMS) == 0)
                                  ? DLPD_PLANE_TEAMS : 1;
@@ -466,48 +481,86 @@ template <int L_> struct Plane {
         if constexpr (G > 1) {
             // G teams of TNT threads: each owns L/G columns (x passes) or N/G rows (y passes) and synchronises on its own
             // named barrier between the passes of one direction, so the teams drift apart and their shared-memory and
-            // arithmetic phases overlap; only the two transpositions (x -> y -> x) need the whole CTA
+            // arithmetic phases overlap; only the two transpositions (x -> y -> x) need the whole CTA.
+            // Persistent form (p.grid > 0): the CTA walks planes bx, bx + grid, ...; while the last two passes of a plane run,
+            // every thread already holds the S1 values of ITS tasks of the next plane's first pass in registers, so neither
+            // the CTA launch nor the L2 round trip of the first loads is exposed between planes.
             if (spec != nullptr) {
-                DLPD_FOR_TEAMS(g, G, TNT) {
-                    const SubTeam<TNT, DLPD_PLANE_DUAL != 0> tm{DLPD_TEAM_TID(TNT), g + 1};
-                    GlobalIn<LoadS1> in{LoadS1{p.in + plane * L * L + g * (L / G)}};
-                    team_fwd_head<N, L / G, NP, PP>(tm, pl + g * (L / G), tw, LineMul<1>(), in);        // along x, columns y < L
-                    if (g == 0) prefetch(p, bx, spec);
-                    team_fwd_tail<N, L / G, NP, PP>(tm, pl + g * (L / G), tw, LineMul<1>());
-                }
-                DLPD_SYNC();
-                DLPD_FOR_TEAMS(g, G, TNT) {
-                    const SubTeam<TNT, DLPD_PLANE_DUAL != 0> tm{DLPD_TEAM_TID(TNT), g + 1};
-                    cpx* rows = pl + g * (N / G) * NP;
-                    PointMul<MulSpec> mul{MulSpec{spec + g * (N / G)}};
-                    team_fwd_head<N, N / G, 1, PP>(tm, rows, tw, LineMul<NP>());                        // along y, rows kx'
-                    team_mid<N, N / G, 1, PP>(tm, rows, tw, LineMul<NP>(), mul);                        // y tail . multiply . inverse y tail
-                    team_inv_head<N, N / G, 1, PP>(tm, rows, tw, LineMul<NP>());                        // inverse y
-                }
-                DLPD_SYNC();
-                DLPD_FOR_TEAMS(g, G, TNT) {
-                    const SubTeam<TNT, DLPD_PLANE_DUAL != 0> tm{DLPD_TEAM_TID(TNT), g + 1};
-                    cpx* cols = pl + g * (N / G);
-                    team_inv_tail<N, N / G, NP, PP>(tm, cols, tw, LineMul<1>());                        // inverse x
-                    if (p.tiled) {
-                        static_assert((N / G) % 2 == 0 && (N / 2 / PP::R0) % 2 == 0, "tiled pair stores");
-                        GlobalOutPair<StoreS2TiledPair> out{StoreS2TiledPair{p.out + plane * N * N + g * (N / G / 2) * 4}};
-                        team_inv_head<N, N / G, NP, PP>(tm, cols, tw, LineMul<1>(), out);
-                    } else {
-                        GlobalOut<StoreS2> out{StoreS2{p.out + plane * N * N + g * (N / G)}};
-                        team_inv_head<N, N / G, NP, PP>(tm, cols, tw, LineMul<1>(), out);
+                const int total = p.P * N * p.C, stride = p.grid > 0 ? p.grid : total;
+                typedef SubTeam<TNT, DLPD_PLANE_DUAL != 0> Team;
+#if !defined(DLPD_EMU)
+                constexpr int NPRE = (L / G) * (N / (2 * PP::R0)) / TNT;            // first-pass tasks per thread
+                constexpr bool PRE = DLPD_PLANE_PRELOAD && ((L / G) * (N / (2 * PP::R0)) == NPRE * TNT) && NPRE >= 1 && NPRE <= 2;
+                typedef PrunedHeadPre<PP::R0, L / G, N, N, NP, PRE ? NPRE : 1, Team, LineMul<1> > Pre;
+                cpx nx[PRE ? NPRE : 1][PP::R0];
+                bool have = false;
+#endif
+                for (int b = bx; b < total; b += stride) {
+                    const int pair_b = b % p.P, kz_b = (b / p.P) % N, c_b = b / (p.P * N);
+                    const long plane_b = ((long)pair_b * p.C + c_b) * N + kz_b;
+                    const cpx* spec_b = p.spec + (long)pair_b * p.spec_pair_stride + ((long)c_b * N + kz_b) * N * N;
+                    DLPD_FOR_TEAMS(g, G, TNT) {
+                        const Team tm{DLPD_TEAM_TID(TNT), g + 1};
+                        GlobalIn<LoadS1> in{LoadS1{p.in + plane_b * L * L + g * (L / G)}};
+                        bool first_done = false;                                                         // along x, columns y < L
+#if !defined(DLPD_EMU)
+                        if constexpr (PRE) {
+                            if (have) {
+                                Pre::run(tm, pl + g * (L / G), tw, LineMul<1>(), nx);
+                                first_done = true;
+                            }
+                        }
+#endif
+                        if (!first_done) team_fwd_head<N, L / G, NP, PP>(tm, pl + g * (L / G), tw, LineMul<1>(), in);
+                        if (g == 0) prefetch(p, b, spec_b);
+                        team_fwd_tail<N, L / G, NP, PP>(tm, pl + g * (L / G), tw, LineMul<1>());
                     }
+                    DLPD_SYNC();
+                    DLPD_FOR_TEAMS(g, G, TNT) {
+                        const Team tm{DLPD_TEAM_TID(TNT), g + 1};
+                        cpx* rows = pl + g * (N / G) * NP;
+                        PointMul<MulSpec> mul{MulSpec{spec_b + g * (N / G)}};
+                        team_fwd_head<N, N / G, 1, PP>(tm, rows, tw, LineMul<NP>());                        // along y, rows kx'
+                        team_mid<N, N / G, 1, PP>(tm, rows, tw, LineMul<NP>(), mul);                        // y tail . multiply . inverse y tail
+                        team_inv_head<N, N / G, 1, PP>(tm, rows, tw, LineMul<NP>());                        // inverse y
+                    }
+                    DLPD_SYNC();
+                    DLPD_FOR_TEAMS(g, G, TNT) {
+                        const Team tm{DLPD_TEAM_TID(TNT), g + 1};
+                        cpx* cols = pl + g * (N / G);
+#if !defined(DLPD_EMU)
+                        if constexpr (PRE) {
+                            have = b + stride < total;
+                            if (have) {
+                                const int b2 = b + stride;
+                                const long plane2 = ((long)(b2 % p.P) * p.C + b2 / (p.P * N)) * N + (b2 / p.P) % N;
+                                Pre::fetch(tm, nx, GlobalIn<LoadS1>{LoadS1{p.in + plane2 * L * L + g * (L / G)}});
+                            }
+                        }
+#endif
+                        team_inv_tail<N, N / G, NP, PP>(tm, cols, tw, LineMul<1>());                        // inverse x
+                        if (p.tiled) {
+                            static_assert((N / G) % 2 == 0 && (N / 2 / PP::R0) % 2 == 0, "tiled pair stores");
+                            GlobalOutPair<StoreS2TiledPair> out{StoreS2TiledPair{p.out + plane_b * N * N + g * (N / G / 2) * 4}};
+                            team_inv_head<N, N / G, NP, PP>(tm, cols, tw, LineMul<1>(), out);
+                        } else {
+                            GlobalOut<StoreS2> out{StoreS2{p.out + plane_b * N * N + g * (N / G)}};
+                            team_inv_head<N, N / G, NP, PP>(tm, cols, tw, LineMul<1>(), out);
+                        }
+                    }
+                    if (b + stride < total) DLPD_SYNC();      // the next plane's first pass overwrites columns other teams still read
                 }
                 return;
             }
         }
+        const CtaTeam<NT, (N < 128) && (DLPD_PLANE_MID_DUAL != 0)> tmc;
         GlobalIn<LoadS1> in{LoadS1{p.in + plane * L * L}};
-        fft_fwd_head<N, L, NP, NT, PP>(pl, tw, LineMul<1>(), in);                   // along x, columns y < L
+        team_fwd_head<N, L, NP, PP>(tmc, pl, tw, LineMul<1>(), in);                   // along x, columns y < L
         prefetch(p, bx, spec);
-        fft_fwd_tail<N, L, NP, NT, PP>(pl, tw, LineMul<1>());
-        fft_fwd_head<N, N, 1, NT, PP>(pl, tw, LineMul<NP>());                       // along y, all rows kx'
+        team_fwd_tail<N, L, NP, PP>(tmc, pl, tw, LineMul<1>());
+        team_fwd_head<N, N, 1, PP>(tmc, pl, tw, LineMul<NP>());                       // along y, all rows kx'
         if (p.spec == nullptr) {
-            fft_fwd_tail<N, N, 1, NT, PP>(pl, tw, LineMul<NP>());
+            team_fwd_tail<N, N, 1, PP>(tmc, pl, tw, LineMul<NP>());
             cpx* out = p.out + plane * N * N;
             DLPD_FOR_TASKS(t, N * N, NT) {
                 const int kx = t % N, ky = t / N;                               // transposed store, coalesced over kx
@@ -517,20 +570,20 @@ template <int L_> struct Plane {
             return;
         }
         PointMul<MulSpec> mul{MulSpec{spec}};
-        fft_mid<N, N, 1, NT, PP>(pl, tw, LineMul<NP>(), mul);                       // y tail . multiply . inverse y tail
-        fft_inv_head<N, N, 1, NT, PP>(pl, tw, LineMul<NP>());                       // inverse y
-        fft_inv_tail<N, N, NP, NT, PP>(pl, tw, LineMul<1>());                       // inverse x
+        team_mid<N, N, 1, PP>(tmc, pl, tw, LineMul<NP>(), mul);                       // y tail . multiply . inverse y tail
+        team_inv_head<N, N, 1, PP>(tmc, pl, tw, LineMul<NP>());                       // inverse y
+        team_inv_tail<N, N, NP, PP>(tmc, pl, tw, LineMul<1>());                       // inverse x
         if (p.tiled) {
             if constexpr ((N / 2 / PP::R0) % 2 == 0) {
                 GlobalOutPair<StoreS2TiledPair> out{StoreS2TiledPair{p.out + plane * N * N}};
-                fft_inv_head<N, N, NP, NT, PP>(pl, tw, LineMul<1>(), out);
+                team_inv_head<N, N, NP, PP>(tmc, pl, tw, LineMul<1>(), out);
             } else {
                 GlobalOut<StoreS2Tiled> out{StoreS2Tiled{p.out + plane * N * N}};
-                fft_inv_head<N, N, NP, NT, PP>(pl, tw, LineMul<1>(), out);
+                team_inv_head<N, N, NP, PP>(tmc, pl, tw, LineMul<1>(), out);
             }
         } else {
             GlobalOut<StoreS2> out{StoreS2{p.out + plane * N * N}};
-            fft_inv_head<N, N, NP, NT, PP>(pl, tw, LineMul<1>(), out);
+            team_inv_head<N, N, NP, PP>(tmc, pl, tw, LineMul<1>(), out);
         }
     }
 
@@ -616,7 +669,8 @@ template <int L_, int CL_> struct PlaneX {
     static DLPD_DEV bool exchanges(const Params& p) { return p.spec != nullptr; }
 
     // everything up to the partial inverse along x: local to the slab
-    static DLPD_DEV void phase_a(const Params& p, int cid, int q, char* smem) {
+    // cid_next: the work item this cluster handles next (-1: none) -- its S1 plane is pulled into L2 meanwhile
+    static DLPD_DEV void phase_a(const Params& p, int cid, int q, char* smem, int cid_next) {
         cpx* pl = reinterpret_cast<cpx*>(smem);        // [M local rows kx'][y], pitch NP
         cpx* tw = pl + M * NP;
         const int pair = cid % p.P, kz = (cid / p.P) % N, c = cid / (p.P * N);
@@ -637,6 +691,11 @@ template <int L_, int CL_> struct PlaneX {
             constexpr int LPR = (M * (int)sizeof(cpx) + 127) / 128 + 1;
             DLPD_FOR_TASKS(t, N * LPR, NT)
                 prefetch_l2(reinterpret_cast<const char*>(spec + (long)(t / LPR) * N) + 128 * (t % LPR));
+        }
+        if (cid_next >= 0) {             // next S1 plane -> L2: each CTA of the cluster takes a quarter
+            const long plane2 = ((long)(cid_next % p.P) * p.C + cid_next / (p.P * N)) * N + (cid_next / p.P) % N;
+            const char* s1n = reinterpret_cast<const char*>(p.in + plane2 * L * L) + (long)q * (L * L * (int)sizeof(cpx) / CL);
+            DLPD_FOR_TASKS(t, L * L * (int)sizeof(cpx) / CL / 128, NT) prefetch_l2(s1n + 128 * t);
         }
         DLPD_FOR_TASKS(t, N, NT) tw[t] = p.tw[t];
         cp_async_wait_all();
@@ -1302,7 +1361,7 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, bool TC_ = false> struct E
         const CtaTeam<NC> tm;
         const bool producer = true, consumer = true;   // one emulated thread plays both roles, copies complete at once
 #else
-        const SubTeam<NC> tm{(int)threadIdx.x, 1};
+        const SubTeam<NC, DLPD_EPI_DUAL != 0> tm{(int)threadIdx.x, 1};
         const bool producer = threadIdx.x >= NC, consumer = !producer;
 #endif
         for (int tile = bx; tile < p.n_tiles; tile += p.grid, slot ^= 1) {
