@@ -21,6 +21,9 @@
 #ifndef DLPD_PLANE_ALT_PLAN
 #define DLPD_PLANE_ALT_PLAN 0
 #endif
+#ifndef DLPD_MUL_EARLY
+#define DLPD_MUL_EARLY 1        // pointwise multipliers of a MID pass are fetched before the task's shared-memory loads (5.37 -> 5.33 ms)
+#endif
 #ifndef DLPD_DUAL_TASKS
 #define DLPD_DUAL_TASKS 0
 #endif
@@ -199,21 +202,54 @@ template <int KIND, int RA, int RB, int LEN, int NB, int TWN, int ES> struct Fft
     // load the RA x RB values of the task whose first element is e0 = blk*NB + j (line l at `p`) and transform them
     template <class In, class Mul>
     static DLPD_DEV void run(cpx (&a)[RA][RB], const cpx* p, const cpx* tw, int l, int e0, int j, In& in, Mul& mul) {
-        // ---- load: a[i][k] <- element e0 + i*M + k*M2
-        DLPD_UNROLL
-        for (int i = 0; i < RA; ++i) {
-            if (KIND == PASS_DIF_PRUNED && i > 0) break;
+        if constexpr (DLPD_MUL_EARLY && !std::is_same<Mul, NoHook>::value && std::is_same<In, NoHook>::value) {
+            // pointwise multipliers (global memory, L2 latency) first: in flight during the loads and the forward butterflies
+            cpx mv[RA][RB];
             DLPD_UNROLL
-            for (int k = 0; k < RB; ++k) {
-                if constexpr (std::is_same<In, NoHook>::value) a[i][k] = p[(i * M + k * M2) * ES];
-                else a[i][k] = in.f(l, e0 + i * M + k * M2);
+            for (int i = 0; i < RA; ++i) {
+                DLPD_UNROLL
+                for (int k = 0; k < RB; ++k) mv[i][k] = mul.f(l, e0 + i * M + k * M2);
             }
+            DLPD_UNROLL
+            for (int i = 0; i < RA; ++i) {
+                DLPD_UNROLL
+                for (int k = 0; k < RB; ++k) a[i][k] = p[(i * M + k * M2) * ES];
+            }
+            compute_fwd(a, tw, j);
+            DLPD_UNROLL
+            for (int i = 0; i < RA; ++i) {
+                DLPD_UNROLL
+                for (int k = 0; k < RB; ++k) a[i][k] = cmul(a[i][k], mv[i][k]);
+            }
+            compute_inv(a, tw, j);
+        } else {
+            // ---- load: a[i][k] <- element e0 + i*M + k*M2
+            DLPD_UNROLL
+            for (int i = 0; i < RA; ++i) {
+                if (KIND == PASS_DIF_PRUNED && i > 0) break;
+                DLPD_UNROLL
+                for (int k = 0; k < RB; ++k) {
+                    if constexpr (std::is_same<In, NoHook>::value) a[i][k] = p[(i * M + k * M2) * ES];
+                    else a[i][k] = in.f(l, e0 + i * M + k * M2);
+                }
+            }
+            compute(a, tw, l, e0, j, mul);
         }
-        compute(a, tw, l, e0, j, mul);
     }
     // the butterflies of a task whose values are already in a[][] (pruned pass: a[0][*] only)
     template <class Mul>
     static DLPD_DEV void compute(cpx (&a)[RA][RB], const cpx* tw, int l, int e0, int j, Mul& mul) {
+        compute_fwd(a, tw, j);
+        if constexpr (!std::is_same<Mul, NoHook>::value) {
+            DLPD_UNROLL
+            for (int i = 0; i < RA; ++i) {
+                DLPD_UNROLL
+                for (int k = 0; k < RB; ++k) a[i][k] = cmul(a[i][k], mul.f(l, e0 + i * M + k * M2));
+            }
+        }
+        compute_inv(a, tw, j);
+    }
+    static DLPD_DEV void compute_fwd(cpx (&a)[RA][RB], const cpx* tw, int j) {
         if (FWD) {
             // outer DFT over i for each k, then twiddle w_NB^{(j + k*M2) * pa}
             DLPD_UNROLL
@@ -244,13 +280,8 @@ template <int KIND, int RA, int RB, int LEN, int NB, int TWN, int ES> struct Fft
                 }
             }
         }
-        if constexpr (!std::is_same<Mul, NoHook>::value) {
-            DLPD_UNROLL
-            for (int i = 0; i < RA; ++i) {
-                DLPD_UNROLL
-                for (int k = 0; k < RB; ++k) a[i][k] = cmul(a[i][k], mul.f(l, e0 + i * M + k * M2));
-            }
-        }
+    }
+    static DLPD_DEV void compute_inv(cpx (&a)[RA][RB], const cpx* tw, int j) {
         if (INV) {
             // inner: twiddle w_M^{j * s}, DFT over s for each pa
             DLPD_UNROLL
