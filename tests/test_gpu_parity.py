@@ -141,6 +141,50 @@ def test_search_full_size_80_matches_oracle():
     _check_against_oracle(best.cpu(), scores.cpu(), rec, lig, rec_clash, lig_clash, Rs, filt, tau)
 
 
+@pytest.mark.parametrize("L", [80, 128])
+def test_search_full_size_translation_equivariance(L):
+    """Size-independent property at the BASELINE box sizes (no oracle needed): moving the ligand by an (even) voxel offset s
+    inside its box moves every score by the same offset, V'[d] = V[d + s], so the best pose moves by -s and keeps its score.
+    With R = identity the trilinear gather is exact, so the check isolates FFT correlation + filter + mask + argmin."""
+    C0, C1, N = 16, 32, 2 * L
+    rec, rec_clash = synthetic.learned_volumes(L, (C0, C1), seed=51)
+    lig, lig_clash = synthetic.learned_volumes(L, (C0, C1), seed=52)
+    q = L // 4                                       # ligand content confined to the central half of the box
+    m0 = torch.zeros(L, L, L); m0[q:3 * q, q:3 * q, q:3 * q] = 1.0
+    m1 = torch.zeros(L // 2, L // 2, L // 2); m1[q // 2:3 * q // 2, q // 2:3 * q // 2, q // 2:3 * q // 2] = 1.0
+    lig = [lig[0] * m0, lig[1] * m1]
+    lig_clash = lig_clash * m0
+    s = (4, -6, 8)
+    lig_s = [torch.roll(lig[0], s, dims=(1, 2, 3)), torch.roll(lig[1], tuple(v // 2 for v in s), dims=(1, 2, 3))]
+    clash_s = torch.roll(lig_clash, s, dims=(0, 1, 2))
+    filt = O.FilterWeights.random(C0 + C1, seed=53)
+    eye = torch.eye(3)[None]
+    tau = 30.0
+    eng = DockingSearch(L, (C0, C1), max_rot=2, device=DEV)
+    eng.set_receptor(rec, rec_clash); eng.set_filter((filt.W1, filt.b1, filt.W2, filt.b2))
+    eng.set_ligand(lig, lig_clash)
+    b0, v0 = eng.search(eye, tau, return_scores=True)
+    eng.set_ligand(lig_s, clash_s)
+    b1, v1 = eng.search(eye, tau, return_scores=True)
+    eng.close()
+    v0, v1 = v0[0], v1[0]
+    want = torch.roll(v0, tuple(-a for a in s), dims=(0, 1, 2))          # want[d] = v0[d + s]
+    # compare where neither d nor d + s crosses the d = +-L seam of the circular index
+    idx = torch.arange(N, device=v0.device)
+    dd = torch.where(idx < L, idx, idx - N)
+    ok1 = (dd.abs() < L - 10)
+    ok = ok1[:, None, None] & ok1[None, :, None] & ok1[None, None, :]
+    scale = float(v0.abs().max())
+    assert float((v1 - want).abs()[ok].max()) <= 2e-5 * scale
+    assert float(v0.abs().max()) > 0 and float((v1 - v0).abs().max()) > 1e-3 * scale     # the shift did something
+    b0, b1 = b0.cpu()[0], b1.cpu()[0]
+    d0 = [int(b0[i + 1]) - (N if b0[i + 1] >= L else 0) for i in range(3)]
+    if all(abs(d0[i]) < L - 20 for i in range(3)):
+        d1 = [int(b1[i + 1]) - (N if b1[i + 1] >= L else 0) for i in range(3)]
+        assert d1 == [d0[i] - s[i] for i in range(3)]
+        assert abs(float(b1[0] - b0[0])) <= 2e-5 * scale
+
+
 def test_search_prerotated_clash_and_chunking_invariance():
     L, C0, C1, H = 20, 16, 32, 24
     rec, lig, rf, lf = _case(L, C0, C1, seed=5)
