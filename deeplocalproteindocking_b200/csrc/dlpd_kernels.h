@@ -1574,6 +1574,9 @@ template <int L_, int C0, int C1, int H> struct EpiloguePipe {
 // the first half and only needed after that half's transform passes.  Every thread issues its share of the cp.async
 // copies (next half-tile + h1), so there are no producer warps.
 // ------------------------------------------------------------------------------------------------------
+#ifndef DLPD_DUO_SKEW
+#define DLPD_DUO_SKEW 0
+#endif
 #ifndef DLPD_DUO_NT
 #define DLPD_DUO_NT 384
 #endif
@@ -1636,6 +1639,14 @@ template <int L_, int C0, int C1, int H> struct EpilogueDuo {
         const CtaTeam<NT> tm;
         unsigned long long bestA = ~0ull, bestB = ~0ull;
         int cur_pair = -1;
+#if !defined(DLPD_EMU) && DLPD_DUO_SKEW > 0
+        // the two CTAs of an SM start together and would stay in phase (both transforming, then both filtering): delay the
+        // second one by about half a half-tile period so that one is in its FFMA-bound filter while the other transforms
+        if (bx >= p.grid / 2) {
+            const long long t0 = clock64();
+            while (clock64() - t0 < DLPD_DUO_SKEW) {}
+        }
+#endif
         for (int it = 0, slot = 0; it < n_it; ++it, slot ^= 1) {
             DLPD_SYNC();                               // half-tile `it` has landed; everyone is done with the other buffers
             const Item w = item(p, bx, it);
