@@ -50,7 +50,7 @@ template <class K> static int launch(dim3 g, const typename K::Params& p, dlpd_s
     ++g_launches;
     return 0;
 }
-template <class K> static int launch_mb(dim3 g, const typename K::Params& p, dlpd_stream_t st) { return launch<K>(g, p, st); }
+template <class K, bool CARVE = true> static int launch_mb(dim3 g, const typename K::Params& p, dlpd_stream_t st) { return launch<K>(g, p, st); }
 // thread-block clusters: the CL CTAs of a cluster run phase A one after the other, then phase B with every CTA's
 // shared memory visible (distributed shared memory on the device)
 template <class K> static int launch_cluster(unsigned clusters, const typename K::Params& p, dlpd_stream_t) {
@@ -115,14 +115,17 @@ __global__ void __launch_bounds__(K::NT, K::MINB) dlpd_kernel_mb(const __grid_co
     extern __shared__ __align__(16) char smem[];
     K::body(p, blockIdx.x, blockIdx.y, blockIdx.z, smem);
 }
-template <class K> static int launch_mb(dim3 g, const typename K::Params& p, dlpd_stream_t st) {
+// CARVE: ask for the maximum shared-memory carve-out (kernels that live in shared memory); false for kernels whose
+// global gathers need the L1 cache (FwdZC)
+template <class K, bool CARVE = true> static int launch_mb(dim3 g, const typename K::Params& p, dlpd_stream_t st) {
     static bool configured[64] = {};
     int dev = 0;
     CU(cudaGetDevice(&dev));
     if (dev < 64 && !configured[dev]) {
         if (K::SMEM > 48 * 1024)
             CU(cudaFuncSetAttribute(dlpd_kernel_mb<K>, cudaFuncAttributeMaxDynamicSharedMemorySize, K::SMEM));
-        CU(cudaFuncSetAttribute(dlpd_kernel_mb<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
+        if (CARVE)
+            CU(cudaFuncSetAttribute(dlpd_kernel_mb<K>, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
         configured[dev] = true;
     }
     dlpd_kernel_mb<K><<<g, K::NT, K::SMEM, st>>>(p);
@@ -254,7 +257,7 @@ template <int L> static int launch_fwdz_t(const FwdZParams& p, int P, dlpd_strea
 }
 template <int L> static int launch_fwdzc_t(const FwdZCParams& p, int P, dlpd_stream_t st) {
     typedef FwdZC<L, Tile<L>::CL_CG, Tile<L>::CL_YT> K;
-    return launch<K>(dim3(L * K::YTILES, p.C / K::CG, P), p, st);
+    return launch_mb<K, false>(dim3(L * K::YTILES, p.C / K::CG, P), p, st);
 }
 // Plane<L> needs the whole N x N plane in one SM's shared memory; PlaneX<L, 4> spreads it over a cluster of 4 CTAs.
 static constexpr int SMEM_MAX = 227 * 1024;

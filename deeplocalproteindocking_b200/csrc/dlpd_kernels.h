@@ -354,6 +354,7 @@ template <int L_, int CG_, int YT_> struct FwdZC {
     static constexpr int CS = N * YT + 8;          // per-channel stride: +8 keeps 4 channel groups of a warp on distinct banks
     static constexpr int NT = (L_ >= 80 && YT_ >= 8) ? 2 * DLPD_FWDZC_NT : DLPD_FWDZC_NT;   // 512 at L = 80: 1.51 vs 1.62 ms; worse at L = 40
     static constexpr int SMEM = (CG * CS + N) * (int)sizeof(cpx);
+    static constexpr int MINB = 1024 / NT;         // resident CTAs the register budget is cut for (64 registers per thread)
     static_assert(L_ % YT_ == 0 && CG_ % 4 == 0, "tile shape");
     struct Lines {
         DLPD_DEV int operator()(int l) const { return (l / YT) * CS + (l % YT); }
@@ -1019,10 +1020,32 @@ template <int L_, int C0, int C1, int H> struct HiddenL1 {
         DLPD_FOR_TASKS(t, N1, NT) tw1[t] = p.tw1[t];
         {
             const cpx* s = p.s2_1 + (long)pair * C1 * N1 * N1 * N1 + (long)x1 * N1 + y0;
+#if defined(DLPD_EMU)
             DLPD_FOR_TASKS(t, C1 * N1 * (YT / 2), NT) {
                 const int h = t % (YT / 2), q = t / (YT / 2), kz = q % N1, c = q / N1;
                 cp_async16(b1 + kz * P1 + c * YT + 2 * h, s + (long)q * N1 * N1 + 2 * h);     // q = c*N1 + kz
             }
+#else
+            if constexpr (NT % (YT / 2) == 0) {
+                // thread t copies rows q = t / (YT/2), + QS, + 2 QS, ...: (c, kz) and both addresses advance by constants
+                constexpr int HT = YT / 2, QS = NT / HT;
+                const int h = (int)threadIdx.x % HT;
+                int q = (int)threadIdx.x / HT, c = q / N1, kz = q - c * N1;
+                const cpx* src = s + (long)q * N1 * N1 + 2 * h;
+                for (; q < C1 * N1; q += QS) {
+                    cp_async16(b1 + kz * P1 + c * YT + 2 * h, src);
+                    src += (long)QS * N1 * N1;
+                    kz += QS % N1;
+                    c += QS / N1;
+                    if (kz >= N1) { kz -= N1; ++c; }
+                }
+            } else {
+                DLPD_FOR_TASKS(t, C1 * N1 * (YT / 2), NT) {
+                    const int h = t % (YT / 2), q = t / (YT / 2), kz = q % N1, c = q / N1;
+                    cp_async16(b1 + kz * P1 + c * YT + 2 * h, s + (long)q * N1 * N1 + 2 * h);
+                }
+            }
+#endif
         }
         cp_async_wait_all();
         DLPD_SYNC();
