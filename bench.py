@@ -183,6 +183,57 @@ def cpu_baseline(rec_vols, rec_clash, lig_vols, lig_coords, filt, Rs, n_rot, war
     return sum(times), len(times)
 
 
+def torch_loop_body(rec_vols, rec_clash, lig_vols, lig_clash_rot, R, W1, b1, W2, b2, tau, rec_spectra=None):
+    """ONE rotation of the reference's loop body (Docker.py:218-232 + DockingModels.py:63-84) written with PyTorch LIBRARY
+    calls on whatever device the tensors live on -- the formulation the reference itself runs (grid_sample rotation, FFT
+    correlation per level, nearest up-sampling, cat / transpose / contiguous, two Linear layers, mask, min).  It is the
+    same-GPU comparator of SURVEY.md 8(d) (TorchProteinLibrary's compiled operators cannot be built here); never used by
+    the product path.  rec_spectra=None re-transforms the receptor on every call like VolumeConvolution does.
+    Returns (best score, flat argmin index)."""
+    import torch.nn.functional as F
+    dev, N = rec_vols[0].device, 2 * rec_vols[0].shape[-1]
+    convs = []
+    for k, (rv, lv) in enumerate(zip(rec_vols, lig_vols)):
+        Lk, n = lv.shape[-1], 2 * lv.shape[-1]
+        ax = torch.arange(Lk, device=dev, dtype=torch.float32) - 0.5 * Lk
+        P = torch.stack(torch.meshgrid(ax, ax, ax, indexing="ij"), dim=-1)
+        S = torch.einsum("xyzb,ba->xyza", P, R) + 0.5 * Lk                      # source voxel of every output voxel
+        g = 2.0 * S / (Lk - 1) - 1.0
+        grid = torch.stack([g[..., 2], g[..., 1], g[..., 0]], dim=-1)[None]
+        rot = F.grid_sample(lv[None], grid, mode="bilinear", padding_mode="zeros", align_corners=True)
+        spec = rec_spectra[k] if rec_spectra is not None else torch.fft.rfftn(rv[None], s=(n, n, n), dim=(-3, -2, -1))
+        corr = torch.fft.irfftn(spec * torch.conj(torch.fft.rfftn(rot, s=(n, n, n), dim=(-3, -2, -1))), s=(n, n, n), dim=(-3, -2, -1))
+        convs.append(corr if n == N else F.interpolate(corr, scale_factor=N // n, mode="nearest"))
+    x = torch.cat(convs, dim=1).transpose(1, 2).transpose(2, 3).transpose(3, 4).contiguous()      # DockingModels.py:79-81
+    score = F.linear(torch.relu(F.linear(x.reshape(-1, x.shape[-1]), W1, b1)), W2.reshape(1, -1), b2.reshape(-1)).reshape(N, N, N)
+    cspec = rec_spectra[-1] if rec_spectra is not None else torch.fft.rfftn(rec_clash[None, None], s=(N, N, N), dim=(-3, -2, -1))
+    clash = torch.fft.irfftn(cspec * torch.conj(torch.fft.rfftn(lig_clash_rot[None, None], s=(N, N, N), dim=(-3, -2, -1))),
+                             s=(N, N, N), dim=(-3, -2, -1))[0, 0]
+    V = (clash < tau).float() * score                                           # Docker.py:226,232
+    best, idx = torch.min(V.reshape(-1), dim=0)                                 # first extraction of update_top
+    return best, idx
+
+
+def torch_gpu_baseline(rec_vols, rec_clash, lig_vols, clash_rot, Rs, filt, n_rot, precomputed, device):
+    """rotations/s of torch_loop_body on `device`, timed with CUDA events after one warm-up."""
+    W1, b1, W2, b2 = (t.detach().float().to(device) for t in (filt.fc[0].weight, filt.fc[0].bias, filt.fc[2].weight, filt.fc[2].bias))
+    spectra = None
+    if precomputed:
+        spectra = [torch.fft.rfftn(v[None], s=(2 * v.shape[-1],) * 3, dim=(-3, -2, -1)) for v in rec_vols]
+        spectra.append(torch.fft.rfftn(rec_clash[None, None], s=(2 * L,) * 3, dim=(-3, -2, -1)))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with torch.no_grad():
+        for i in range(n_rot + 1):
+            if i == 1:
+                e0.record()
+            best, idx = torch_loop_body(rec_vols, rec_clash, lig_vols, clash_rot[i % clash_rot.shape[0]], Rs[i].float().to(device),
+                                        W1, b1, W2, b2, TAU, spectra)
+            float(best)                                                          # the reference reads the minimum back every step
+        e1.record()
+    torch.cuda.synchronize(device)
+    return n_rot / (1e-3 * e0.elapsed_time(e1))
+
+
 def run_reference(args, rank, world):
     """`--impl reference`: the reference's own CPU formulation of the path (oracle port; TorchProteinLibrary's
     compiled operators are not vendored) on the host cores.  Rank 0 only."""
@@ -239,6 +290,8 @@ def main():
     ap.add_argument("--rot-batch", type=int, default=64, help="rotations per step per GPU")
     ap.add_argument("--max-rot", type=int, default=32, help="rotations per internal chunk (workspace size)")
     ap.add_argument("--cpu-rotations", type=int, default=8, help="rotations of the cpu_baseline sample (0 = skip)")
+    ap.add_argument("--torch-gpu-rotations", type=int, default=6,
+                    help="rotations of the same-GPU PyTorch (cuFFT / grid_sample) comparator sample (0 = skip)")
     ap.add_argument("--ref-rot-per-step", type=int, default=2)
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config (1-based); 2 is the bench line")
     ap.add_argument("--plane-mode", default="auto", choices=["auto", "single", "cluster"], help="plane-stage kernel (tuning)")
@@ -419,6 +472,20 @@ def main():
             line["cpu_baseline"] = {"value": n / t, "unit": "rotations/s", "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": "%d rotations of oim10 (after 1 warm-up), CPU PyTorch torch.fft oracle, "
                                               "receptor spectra precomputed" % n}
+        if world == 1 and args.torch_gpu_rotations > 0 and cfg["source"] == "atoms":
+            eng.close()
+            torch.cuda.empty_cache()
+            Rt = Rall[:args.torch_gpu_rotations + 1]
+            cl = clash_volumes(lig_dev, Rt.to(device), device)
+            line["gpu_torch_baseline"] = {
+                "unit": "rotations/s", "kind": "port",
+                "what": "the reference's loop body as plain PyTorch library calls on the same GPU (grid_sample, cuFFT "
+                        "rfftn/irfftn, interpolate, Linear, min): same-GPU comparator, SURVEY.md 8(d)",
+                "receptor_retransformed_each_call": torch_gpu_baseline(rec_vols, rec_clash, lig_vols, cl, Rt, filt,
+                                                                       args.torch_gpu_rotations, False, device),
+                "receptor_spectra_precomputed": torch_gpu_baseline(rec_vols, rec_clash, lig_vols, cl, Rt, filt,
+                                                                   args.torch_gpu_rotations, True, device),
+                "sample": "%d rotations of oim10 after 1 warm-up, one rotation per call" % args.torch_gpu_rotations}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:

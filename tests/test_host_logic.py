@@ -98,3 +98,30 @@ def test_projection_matches_oracle_and_typed_layout():
     assert torch.allclose(vol[0], want, atol=1e-6)
     batched = dk.project_density_batched(moved.coords.float()[None], L, res)
     assert torch.allclose(batched[0], want.sum(0), atol=1e-5)
+
+
+def test_bench_torch_loop_body_matches_oracle():
+    """bench.py's same-GPU comparator (the reference loop body as PyTorch library calls) computes what the oracle computes."""
+    import bench
+    from oracle import docking_oracle as O
+    from deeplocalproteindocking_b200 import rotations, synthetic
+    L, C0, C1 = 8, 4, 6
+    rec, rec_clash = synthetic.learned_volumes(L, (C0, C1), seed=61)
+    lig, lig_clash = synthetic.learned_volumes(L, (C0, C1), seed=62)
+    filt = O.FilterWeights.random(C0 + C1, 5, seed=63)
+    R = rotations.Rotations(20).R[321]
+    tau = 2.0
+    clash_rot = O.rotate_volume(lig_clash[None, None].double(), R[None])[0, 0].float()
+    spectra = O.ReceptorSpectra([v[None].double() for v in rec], rec_clash[None, None].double())
+    V = O.score_rotation(spectra, [v[None].double() for v in lig], clash_rot.double(), R, filt.to(torch.float64), tau,
+                         ligand_forbidden_is_rotated=True)
+    s, x, y, z = O.best_pose(V)
+    for pre in (False, True):
+        sp = None
+        if pre:
+            sp = [torch.fft.rfftn(v[None], s=(2 * v.shape[-1],) * 3, dim=(-3, -2, -1)) for v in rec]
+            sp.append(torch.fft.rfftn(rec_clash[None, None], s=(2 * L,) * 3, dim=(-3, -2, -1)))
+        best, idx = bench.torch_loop_body(rec, rec_clash, lig, clash_rot, R.float(), filt.W1, filt.b1, filt.W2, filt.b2, tau, sp)
+        N = 2 * L
+        assert int(idx) == (x * N + y) * N + z
+        assert abs(float(best) - s) <= 1e-4 * max(abs(s), 1e-3 * float(V.abs().max()))
