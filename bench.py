@@ -162,9 +162,10 @@ class ClockSampler:
         return out
 
 
-def cpu_baseline(rec_vols, rec_clash, lig_vols, lig_coords, filt, Rs, n_rot, warm=1):
-    """The oracle (CPU PyTorch + torch.fft restatement of the reference loop, receptor spectra precomputed) timed on
-    all host cores over `n_rot` rotations.  kind = "port"."""
+def cpu_baseline(rec_vols, rec_clash, lig_vols, lig_coords, filt, Rs, n_rot, warm=1, retransform_receptor=False):
+    """The oracle (CPU PyTorch + torch.fft restatement of the reference loop) timed on all host cores over `n_rot` rotations;
+    receptor spectra precomputed (kind to the baseline) or, with `retransform_receptor`, recomputed for every rotation like
+    the reference's VolumeConvolution does (DockingModels.py:71).  kind = "port"."""
     from oracle import docking_oracle as O
     torch.set_num_threads(os.cpu_count() or 1)
     cpu = lambda t: t.detach().float().cpu()
@@ -175,6 +176,8 @@ def cpu_baseline(rec_vols, rec_clash, lig_vols, lig_coords, filt, Rs, n_rot, war
     times = []
     for i in range(warm + n_rot):
         t0 = time.perf_counter()
+        if retransform_receptor:
+            spectra = O.ReceptorSpectra([cpu(v)[None] for v in rec_vols], cpu(rec_clash)[None, None])
         clash = O.ligand_clash_volume(lc, Rs[i % Rs.shape[0]], L, 1.25)
         V = O.score_rotation(spectra, ligs, clash, Rs[i % Rs.shape[0]], f, TAU, ligand_forbidden_is_rotated=True)
         O.best_pose(V)
@@ -472,6 +475,9 @@ def main():
             line["cpu_baseline"] = {"value": n / t, "unit": "rotations/s", "cores": os.cpu_count() or 1, "kind": "port",
                                     "sample": "%d rotations of oim10 (after 1 warm-up), CPU PyTorch torch.fft oracle, "
                                               "receptor spectra precomputed" % n}
+            t2, n2 = cpu_baseline(rec_vols, rec_clash, lig_vols, lig_coords, filt, Rall, max(2, args.cpu_rotations // 2),
+                                  retransform_receptor=True)
+            line["cpu_baseline"]["value_receptor_retransformed_each_call"] = n2 / t2       # faithful to DockingModels.py:71
         if world == 1 and args.torch_gpu_rotations > 0 and cfg["source"] == "atoms":
             eng.close()
             torch.cuda.empty_cache()

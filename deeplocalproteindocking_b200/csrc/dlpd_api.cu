@@ -321,7 +321,16 @@ static int launch_fwdzc(int L, const FwdZCParams& p, int P, dlpd_stream_t st) {
     }
     return fail(DLPD_EINVAL, "unsupported box size");
 }
-static bool channel_last_ok(int C) { return C % 16 == 0; }     // multiple of every Tile<L>::CL_CG in use
+static bool channel_last_ok(int C) { return C % 16 == 0; }
+// channels per FwdZC CTA at box size L (= the group size of the channel-last ligand copy)
+static int cl_group(int L) {
+    switch (L) {
+#define X(L_) case L_: return Tile<L_>::CL_CG;
+        DLPD_OP_SIZES(X)
+#undef X
+    }
+    return 8;
+}     // multiple of every Tile<L>::CL_CG in use
 static int launch_plane(int L, const PlaneParams& p, dlpd_stream_t st) {
     switch (L) {
 #define X(L_) case L_: return launch_plane_t<L_>(p, st);
@@ -544,9 +553,9 @@ extern "C" int dlpd_set_ligand(dlpd_plan* p, const float* vol0, const float* vol
     TRY(rt_copy(p->lig1, vol1, sizeof(float) * p->C1 * n3(L1), D2D, st));
     TRY(channel_sumsq(vol0, p->C0, (int)n3(L), 1, p->lig_ss, st));
     ChannelLastParams cl;
-    cl.in = p->lig0; cl.out = p->lig0_cl; cl.C = p->C0; cl.V = (int)n3(L);
+    cl.in = p->lig0; cl.out = p->lig0_cl; cl.C = p->C0; cl.V = (int)n3(L); cl.G = cl_group(L);
     TRY(launch<ToChannelLast>(dim3((cl.V + ToChannelLast::VOX_PER_CTA - 1) / ToChannelLast::VOX_PER_CTA), cl, st));
-    cl.in = p->lig1; cl.out = p->lig1_cl; cl.C = p->C1; cl.V = (int)n3(L1);
+    cl.in = p->lig1; cl.out = p->lig1_cl; cl.C = p->C1; cl.V = (int)n3(L1); cl.G = cl_group(L1);
     TRY(launch<ToChannelLast>(dim3((cl.V + ToChannelLast::VOX_PER_CTA - 1) / ToChannelLast::VOX_PER_CTA), cl, st));
     p->has_ligand = true;
     p->lig_has_clash = clash != nullptr;

@@ -283,12 +283,15 @@ template <int L_, int YT_> struct FwdZ {
 };
 
 // ------------------------------------------------------------------------------------------------------
-// ToChannelLast: [C][V] -> [V][C]  (ligand feature volumes, once per pair)
+// ToChannelLast: [C][V] -> [C/G][V][G]  (ligand feature volumes, once per pair): channel-last within groups of G
+// channels, one group per FwdZC CTA -- every byte of a cache line the gather pulls in belongs to the CTA's own channels
+// (with all C channels in one record half of each line was another group's data), and one group of a 128^3 volume
+// (67 MB) fits the L2 where the whole volume (134 MB) does not.  G = 0 or C: plain [V][C].
 // ------------------------------------------------------------------------------------------------------
 struct ChannelLastParams {
     const float* in;
     float* out;
-    int C, V;
+    int C, V, G;
 };
 struct ToChannelLast {
     typedef ChannelLastParams Params;
@@ -297,9 +300,10 @@ struct ToChannelLast {
     static constexpr int VOX_PER_CTA = 256;
     // grid: x = ceil(V / VOX_PER_CTA)
     static DLPD_DEV void body(const Params& p, int bx, int, int, char*) {
+        const int G = (p.G > 0 && p.C % p.G == 0) ? p.G : p.C;
         DLPD_FOR_TASKS(t, VOX_PER_CTA * p.C, NT) {
             const int c = t % p.C, v = bx * VOX_PER_CTA + t / p.C;
-            if (v < p.V) p.out[(long)v * p.C + c] = p.in[(long)c * p.V + v];
+            if (v < p.V) p.out[((long)(c / G) * p.V + v) * G + (c % G)] = p.in[(long)c * p.V + v];
         }
     }
 };
@@ -310,7 +314,7 @@ struct ToChannelLast {
 // one 16-byte load per 4 channels (full 32-byte sectors for CG = 8) instead of CG scattered 4-byte loads.
 // ------------------------------------------------------------------------------------------------------
 struct FwdZCParams {
-    const float* src;        // [L^3][C] channel-last
+    const float* src;        // [C/CG][L^3][CG] channel-last within groups of CG channels (ToChannelLast)
     const float* R;          // [n_rot][9]
     cpx* out;                // S1 [P][Ctot][N][L][L]
     const cpx* tw;
@@ -372,16 +376,16 @@ template <int L_, int CG_, int YT_> struct FwdZC {
             rb[i] = hasB ? p.R[9 * rotB + i] : 0.0f;
         }
         DLPD_FOR_TASKS(t, N, NT) tw[t] = p.tw[t];
-        const float* src = p.src + c0;
+        const float* src = p.src + (long)by * L * L * L * CG;       // this CTA's channel group
         DLPD_FOR_TASKS(t, CQ * YT * L, NT) {
             const int cq = t % CQ, yl = (t / CQ) % YT, z = t / (CQ * YT), y = y0 + yl;
             float sx, sy, sz;
             rotate_point(ra, p.center, x, y, z, sx, sy, sz);
-            const float4 a = trilinear_zero_cl4(src + 4 * cq, L, p.C, sx, sy, sz);
+            const float4 a = trilinear_zero_cl4(src + 4 * cq, L, CG, sx, sy, sz);
             float4 b = make_float4(0.f, 0.f, 0.f, 0.f);
             if (hasB) {
                 rotate_point(rb, p.center, x, y, z, sx, sy, sz);
-                b = trilinear_zero_cl4(src + 4 * cq, L, p.C, sx, sy, sz);
+                b = trilinear_zero_cl4(src + 4 * cq, L, CG, sx, sy, sz);
             }
             cpx* d = buf + (4 * cq) * CS + z * YT + yl;
             d[0] = make_float2(a.x, b.x);
