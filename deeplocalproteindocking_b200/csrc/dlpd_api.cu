@@ -518,6 +518,9 @@ static int real_spectra(int L, const float* vols, int C, cpx* s1, cpx* spec, con
     return 0;
 }
 
+static bool filter_tensor_wanted() {
+    return g_filter_kind == DLPD_FILTER_TENSOR || (g_filter_kind == DLPD_FILTER_AUTO && DLPD_FILTER_DEFAULT_TENSOR);
+}
 // squared L2 norm per level-0 feature channel (max over the n volume sets): bounds the correlations for the fp16-split filter
 static int channel_sumsq(const float* vols, int C, int V, int n, float* out, dlpd_stream_t st) {
     TRY(rt_memset(out, 0, sizeof(float) * C, st));
@@ -600,8 +603,7 @@ template <int L, int C0, int C1, int H> static bool filter_tensor() {
 #if defined(DLPD_EMU)
     return false;
 #else
-    const bool want = g_filter_kind == DLPD_FILTER_TENSOR || (g_filter_kind == DLPD_FILTER_AUTO && DLPD_FILTER_DEFAULT_TENSOR);
-    return want && C0 == 16 && H % 8 == 0;
+    return filter_tensor_wanted() && C0 == 16 && H % 8 == 0;
 #endif
 }
 template <int L, int C0, int C1, int H> static int launch_filter_prep(dlpd_plan* p, dlpd_stream_t st) {
@@ -711,7 +713,7 @@ static int search_chunk(dlpd_plan* p, const float* R, const float* clash_rot, co
         f.src_pair_stride = 0; f.R = R; f.out = p->s1_0; f.tw = p->tw0; f.Ctot = p->C0 + 1; f.n_rot = n; f.ext_all = 0;
         f.center = center_of(L, p->center_mode);
         if (lig0_rot) {
-            TRY(channel_sumsq(lig0_rot, p->C0, (int)n3(L), n, p->lig_ss, st));
+            if (filter_tensor_wanted()) TRY(channel_sumsq(lig0_rot, p->C0, (int)n3(L), n, p->lig_ss, st));
             f.src = p->lig0; f.src_rot = lig0_rot; f.C = p->C0; f.c_out0 = 0; f.c_ext = -1; f.ext_all = 1;
             TRY(launch_fwdz(L, f, P, st));
             f.ext_all = 0;
