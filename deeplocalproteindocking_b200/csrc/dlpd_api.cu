@@ -278,13 +278,21 @@ static int g_filter_kind = DLPD_FILTER_AUTO;
 #define DLPD_EPILOGUE_DEFAULT_PIPELINED 0
 #endif
 template <int L> struct HasPlaneX { static constexpr bool value = (L == 8 || L == 16 || L == 20 || L == 40 || L == 64 || L == 80 || L == 128); };
+// CTAs per cluster of the cluster plane kernel: 8 at N = 256 (three planes resident per SM), else 4
+#ifndef DLPD_PLANEX_CL_BIG
+#define DLPD_PLANEX_CL_BIG 8
+#endif
+#ifndef DLPD_PLANEX_CL_16
+#define DLPD_PLANEX_CL_16 4          // test builds set 8 to run the 8-CTA code at a box size the emulation can afford
+#endif
+template <int L> struct PlaneXCL { static constexpr int value = (L == 128) ? DLPD_PLANEX_CL_BIG : ((L == 16) ? DLPD_PLANEX_CL_16 : 4); };
 template <int L> struct HasPlane { static constexpr bool value = ((2 * L) * (2 * L + 1) + 2 * L) * 8 <= SMEM_MAX; };
 template <int L> static int launch_plane_t(const PlaneParams& p, dlpd_stream_t st) {
     bool cluster = !HasPlane<L>::value;
     if (g_plane_mode == DLPD_PLANE_CLUSTER && HasPlaneX<L>::value) cluster = true;
     if (g_plane_mode == DLPD_PLANE_SINGLE) cluster = false;
     if (cluster) {
-        if constexpr (HasPlaneX<L>::value) return launch_cluster<PlaneX<L, 4> >((unsigned)(p.P * 2 * L * p.C), p, st);
+        if constexpr (HasPlaneX<L>::value) return launch_cluster<PlaneX<L, PlaneXCL<L>::value> >((unsigned)(p.P * 2 * L * p.C), p, st);
         else return fail(DLPD_EINVAL, "the cluster plane kernel is not compiled for this box size");
     } else {
         if constexpr (HasPlane<L>::value) {

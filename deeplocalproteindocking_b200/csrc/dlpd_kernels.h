@@ -39,6 +39,9 @@
 #ifndef DLPD_PLANE_MID_DUAL
 #define DLPD_PLANE_MID_DUAL 0
 #endif
+#ifndef DLPD_HID_DIRECT
+#define DLPD_HID_DIRECT 0
+#endif
 #ifndef DLPD_HID_NT
 #define DLPD_HID_NT 512
 #endif
@@ -650,11 +653,15 @@ template <int L_, int CL_> struct PlaneX {
     typedef PlaneParams Params;
     static constexpr int L = L_, N = 2 * L_, CL = CL_, M = N / CL_, NP = N + 1;
     static constexpr int XA = XPlan<M>::XA, XB = XPlan<M>::XB;
-    static constexpr int NT = (N > 160) ? DLPD_PLANEX_NT_BIG : ((N >= 128) ? DLPD_PLANEX_NT : 128);
+    // 8-CTA clusters hold N/8 rows each (68 KB at N = 256): three CTAs = three planes in flight per SM instead of one, which
+    // is what the latency-bound passes of this kernel need; 256 threads each so that the register file still fits them
+    static constexpr int NT = (CL_ == 8 && N > 160) ? 256 : ((N > 160) ? DLPD_PLANEX_NT_BIG : ((N >= 128) ? DLPD_PLANEX_NT : 128));
     static constexpr int SMEM = (M * NP + N) * (int)sizeof(cpx);
-    static_assert(CL_ == 4 && N % CL_ == 0 && M % 2 == 0 && N % XB == 0, "cluster shape");
+    static_assert((CL_ == 4 || CL_ == 8) && N % CL_ == 0 && M % 2 == 0 && N % XB == 0, "cluster shape");
+    // the S1 plane (L x L) can be staged in the slab (M x N) up to CL = 4; larger clusters fold straight from global memory
+    static constexpr bool STAGE = (L * L <= M * N);
 
-    static constexpr int MINB = (SMEM <= 56 * 1024) ? 4 : 1;   // resident CTAs per SM the register budget is cut for
+    static constexpr int MINB = (SMEM <= 56 * 1024) ? 4 : ((SMEM <= 75 * 1024) ? 3 : 1);   // resident CTAs per SM the register budget is cut for
     struct FoldS1 {          // element e = j of column l = y of slab q: w_N^{q j} (x[j] + i^q x[j + M])
         const cpx* pl;       // staged S1 plane: pl[j][y] = x[j][y], pl[j][L + y] = x[j + M][y]   (j < M, y < L)
         const cpx* tw;
@@ -664,6 +671,17 @@ template <int L_, int CL_> struct PlaneX {
             const cpx a = pl[e * NP + l], b = pl[e * NP + L + l];
             const cpx w = tw[e * q];                                   // q = 0: tw[0] = 1
             return cadd(cmul(a, w), cmul(b, cmul(w, iq)));
+        }
+    };
+    struct FoldG {           // the same fold for any CL, reading the S1 plane from global memory (L2: all CL CTAs read it):
+        const cpx* in;       //   y_q[j] = w_N^{q j} sum_{m < CL/2} x[j + m M] e^{2 pi i q m / CL}
+        const cpx* tw;
+        int q;
+        DLPD_DEV cpx operator()(int l, int e) const {
+            cpx acc = __ldg(in + e * L + l);
+            DLPD_UNROLL
+            for (int m = 1; m < CL / 2; ++m) acc = cadd(acc, cmul(__ldg(in + (e + m * M) * L + l), tw[(N / CL) * ((q * m) & (CL - 1))]));
+            return cmul(acc, tw[e * q]);
         }
     };
     struct MulSpec {         // element e = ky' of local row l (global row kx' = q M + l); spectrum stored [ky'][kx']
@@ -684,7 +702,7 @@ template <int L_, int CL_> struct PlaneX {
         // copies -- every load is in flight at once instead of one dependent round trip per butterfly task: row j < M
         // holds x = j in its left half (columns y < L) and x = j + M in its right half, which the y transform only
         // fills later
-        {
+        if constexpr (STAGE) {
             const cpx* s1 = p.in + plane * L * L;
             DLPD_FOR_TASKS(t, L * L, NT) {
                 const int x = t / L, y = t - x * L;
@@ -706,9 +724,14 @@ template <int L_, int CL_> struct PlaneX {
         cp_async_wait_all();
         DLPD_SYNC();
         // forward x on the columns y < L: radix-CL fold in place, then the M-point transform
-        const cpx iq = q == 0 ? make_float2(1.f, 0.f) : q == 1 ? make_float2(0.f, 1.f) : q == 2 ? make_float2(-1.f, 0.f) : make_float2(0.f, -1.f);
-        GlobalIn<FoldS1> in{FoldS1{pl, tw, q, iq}};
-        fft_pass<PASS_DIF, XA, 1, L, M, M, N, NP, NT>(pl, tw, LineMul<1>(), in);
+        if constexpr (STAGE && CL == 4) {
+            const cpx iq = q == 0 ? make_float2(1.f, 0.f) : q == 1 ? make_float2(0.f, 1.f) : q == 2 ? make_float2(-1.f, 0.f) : make_float2(0.f, -1.f);
+            GlobalIn<FoldS1> in{FoldS1{pl, tw, q, iq}};
+            fft_pass<PASS_DIF, XA, 1, L, M, M, N, NP, NT>(pl, tw, LineMul<1>(), in);
+        } else {
+            GlobalIn<FoldG> in{FoldG{p.in + plane * L * L, tw, q}};
+            fft_pass<PASS_DIF, XA, 1, L, M, M, N, NP, NT>(pl, tw, LineMul<1>(), in);
+        }
         if constexpr (XB > 1) fft_pass<PASS_DIF, XB, 1, L, M, XB, N, NP, NT>(pl, tw, LineMul<1>());
         fft_fwd_head<N, M, 1, NT>(pl, tw, LineMul<NP>());                       // along y, my rows
         if (p.spec == nullptr) {
@@ -1016,12 +1039,27 @@ template <int L_, int C0, int C1, int H> struct HiddenL1 {
     static constexpr int NT = (N1 >= 64) ? DLPD_HID_NT : 128;
     static constexpr int SMEM = (N1 * P1 + N1) * (int)sizeof(cpx);
     static_assert(N1 % YT == 0, "level-1 y tile");
+    struct LoadS2 {          // element e = kz' of line l = c*YT + yl
+        const cpx* s;
+        DLPD_DEV cpx operator()(int l, int e) const { return __ldg(s + ((long)(l / YT) * N1 + e) * N1 * N1 + (l % YT)); }
+    };
     // grid: x = N1 / YT, y = N1 (x1), z = P
     static DLPD_DEV void body(const Params& p, int bx, int by, int bz, char* smem) {
         cpx* b1 = reinterpret_cast<cpx*>(smem);        // [kz1][P1]   line = c*YT + yl
         cpx* tw1 = b1 + N1 * P1;
         const int y0 = YT * bx, x1 = by, pair = bz;
         DLPD_FOR_TASKS(t, N1, NT) tw1[t] = p.tw1[t];
+        const CtaTeam<NT, true> tm;
+#if DLPD_HID_DIRECT
+        {
+            // the first inverse pass reads its inputs straight from global memory (two tasks = 2 x TAIL loads in flight per
+            // thread) instead of staging the tile in shared memory first: no cp.async issue loop, one shared-memory
+            // round trip less
+            DLPD_SYNC();
+            GlobalIn<LoadS2> in{LoadS2{p.s2_1 + (long)pair * C1 * N1 * N1 * N1 + (long)x1 * N1 + y0}};
+            team_inv_tail<N1, NL, P1>(tm, b1, tw1, LineMul<1>(), in);
+        }
+#else
         {
             const cpx* s = p.s2_1 + (long)pair * C1 * N1 * N1 * N1 + (long)x1 * N1 + y0;
 #if defined(DLPD_EMU)
@@ -1053,8 +1091,8 @@ template <int L_, int C0, int C1, int H> struct HiddenL1 {
         }
         cp_async_wait_all();
         DLPD_SYNC();
-        const CtaTeam<NT, true> tm;
         team_inv_tail<N1, NL, P1>(tm, b1, tw1, LineMul<1>());
+#endif
         team_inv_head<N1, NL, P1>(tm, b1, tw1, LineMul<1>());
         cpx* h1 = p.h1 + (((long)pair * N1 + x1) * N1 + y0) * N1 * H;
         DLPD_FOR_TASKS(t, (H / JG) * VP, NT) {
