@@ -146,16 +146,21 @@ __global__ void __launch_bounds__(K::NT, K::MINB) dlpd_cluster_kernel(const __gr
 #pragma unroll
     for (int r = 0; r < K::CL; ++r) slabs[r] = cl.map_shared_rank(reinterpret_cast<cpx*>(smem), r);
     const bool exch = K::exchanges(p);     // uniform over the grid
+    bool pending = false;
     for (int cid = (int)(blockIdx.x / K::CL); cid < n_items; cid += step) {
-        K::phase_a(p, cid, rank, smem, cid + step < n_items ? cid + step : -1);
+        K::phase_a(p, cid, rank, smem, cid + step < n_items ? cid + step : -1, pending);
         if (exch) {
             cl.sync();
             K::phase_b(p, cid, rank, slabs, smem);
-            cl.sync();                     // nobody re-fills (or leaves) while its shared memory is still being read
+            // nobody re-fills (or leaves) while its shared memory is still being read: arrive now, wait inside the next
+            // item's phase A (after its prefetches) or before leaving
+            cluster_arrive();
+            pending = true;
         } else {
             __syncthreads();
         }
     }
+    if (pending) cluster_wait();
 }
 template <class K> static int launch_cluster(unsigned clusters, const typename K::Params& p, dlpd_stream_t st) {
     static bool configured[64] = {};

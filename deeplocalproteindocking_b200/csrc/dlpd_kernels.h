@@ -645,6 +645,12 @@ DLPD_XPLAN(64, 8, 8)
 #ifndef DLPD_PLANEX_NT
 #define DLPD_PLANEX_NT 256
 #endif
+#ifndef DLPD_PLANEX_NT_CL8
+#define DLPD_PLANEX_NT_CL8 256
+#endif
+#ifndef DLPD_PLANEX_MINB_CL8
+#define DLPD_PLANEX_MINB_CL8 3
+#endif
 #ifndef DLPD_PLANEX_NT_BIG
 #define DLPD_PLANEX_NT_BIG 512
 #endif
@@ -655,13 +661,13 @@ template <int L_, int CL_> struct PlaneX {
     static constexpr int XA = XPlan<M>::XA, XB = XPlan<M>::XB;
     // 8-CTA clusters hold N/8 rows each (68 KB at N = 256): three CTAs = three planes in flight per SM instead of one, which
     // is what the latency-bound passes of this kernel need; 256 threads each so that the register file still fits them
-    static constexpr int NT = (CL_ == 8 && N > 160) ? 256 : ((N > 160) ? DLPD_PLANEX_NT_BIG : ((N >= 128) ? DLPD_PLANEX_NT : 128));
+    static constexpr int NT = (CL_ == 8 && N > 160) ? DLPD_PLANEX_NT_CL8 : ((N > 160) ? DLPD_PLANEX_NT_BIG : ((N >= 128) ? DLPD_PLANEX_NT : 128));
     static constexpr int SMEM = (M * NP + N) * (int)sizeof(cpx);
     static_assert((CL_ == 4 || CL_ == 8) && N % CL_ == 0 && M % 2 == 0 && N % XB == 0, "cluster shape");
     // the S1 plane (L x L) can be staged in the slab (M x N) up to CL = 4; larger clusters fold straight from global memory
     static constexpr bool STAGE = (L * L <= M * N);
 
-    static constexpr int MINB = (SMEM <= 56 * 1024) ? 4 : ((SMEM <= 75 * 1024) ? 3 : 1);   // resident CTAs per SM the register budget is cut for
+    static constexpr int MINB = (SMEM <= 56 * 1024) ? 4 : ((SMEM <= 75 * 1024) ? DLPD_PLANEX_MINB_CL8 : 1);   // resident CTAs per SM the register budget is cut for
     struct FoldS1 {          // element e = j of column l = y of slab q: w_N^{q j} (x[j] + i^q x[j + M])
         const cpx* pl;       // staged S1 plane: pl[j][y] = x[j][y], pl[j][L + y] = x[j + M][y]   (j < M, y < L)
         const cpx* tw;
@@ -693,11 +699,14 @@ template <int L_, int CL_> struct PlaneX {
 
     // everything up to the partial inverse along x: local to the slab
     // cid_next: the work item this cluster handles next (-1: none) -- its S1 plane is pulled into L2 meanwhile
-    static DLPD_DEV void phase_a(const Params& p, int cid, int q, char* smem, int cid_next) {
+    // pending: the cluster barrier that ended the previous item's phase B has been arrived at but not waited for -- the wait
+    // is placed after this item's prefetches, right before the slab is written again
+    static DLPD_DEV void phase_a(const Params& p, int cid, int q, char* smem, int cid_next, bool pending = false) {
         cpx* pl = reinterpret_cast<cpx*>(smem);        // [M local rows kx'][y], pitch NP
         cpx* tw = pl + M * NP;
         const int pair = cid % p.P, kz = (cid / p.P) % N, c = cid / (p.P * N);
         const long plane = ((long)pair * p.C + c) * N + kz;
+        if (STAGE && pending) cluster_wait();
         // stage the whole S1 plane (L x L, read by all CL CTAs of the cluster) in the still empty slab with asynchronous
         // copies -- every load is in flight at once instead of one dependent round trip per butterfly task: row j < M
         // holds x = j in its left half (columns y < L) and x = j + M in its right half, which the y transform only
@@ -720,6 +729,7 @@ template <int L_, int CL_> struct PlaneX {
             const char* s1n = reinterpret_cast<const char*>(p.in + plane2 * L * L) + (long)q * (L * L * (int)sizeof(cpx) / CL);
             DLPD_FOR_TASKS(t, L * L * (int)sizeof(cpx) / CL / 128, NT) prefetch_l2(s1n + 128 * t);
         }
+        if (!STAGE && pending) cluster_wait();
         DLPD_FOR_TASKS(t, N, NT) tw[t] = p.tw[t];
         cp_async_wait_all();
         DLPD_SYNC();

@@ -44,6 +44,8 @@
   static inline void named_barrier_sync(int, int) {}
   static inline void named_barrier_arrive(int, int) {}
   static inline void store_cpx2(float2* dst, float2 a, float2 b) { dst[0] = a; dst[1] = b; }
+  static inline void cluster_arrive() {}
+  static inline void cluster_wait() {}
   static inline unsigned int atomic_inc_u32(unsigned int* p) { return (*p)++; }
   static inline void atomic_add_f32(float* p, float v) { *p += v; }
   #define DLPD_UNROLL
@@ -89,6 +91,10 @@
   DLPD_DEV void store_cpx2(float2* dst, float2 a, float2 b) {       // 16-byte aligned destination
       *reinterpret_cast<float4*>(dst) = make_float4(a.x, a.y, b.x, b.y);
   }
+  // split cluster barrier: arrive (release) when this CTA no longer reads its peers' shared memory, wait (acquire) only
+  // right before it overwrites its own
+  DLPD_DEV void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+  DLPD_DEV void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
   DLPD_DEV unsigned int atomic_inc_u32(unsigned int* p) { return atomicAdd(p, 1u); }
   DLPD_DEV void atomic_add_f32(float* p, float v) { atomicAdd(p, v); }
   typedef cudaStream_t dlpd_stream_t;
