@@ -120,7 +120,7 @@ int dlpd_project_clash(const double* coords, const double* R, int nat, int n, in
 
 /* ---- tuning / test switches (process-wide) -------------------------------------------------------------
  * DLPD_OPT_PLANE_MODE     which kernel runs the per-(channel, kz) plane stage: AUTO = one CTA per plane when the plane
- *                         fits an SM's shared memory (N <= 160), else a 4-CTA cluster with distributed shared memory;
+ *                         fits an SM's shared memory (N <= 160), else a thread-block cluster (8 CTAs at N = 256, 4 elsewhere) with distributed shared memory;
  *                         SINGLE forces the former (fails if the plane does not fit), CLUSTER prefers the latter wherever it is
  *                         compiled (box sizes 8, 16, 20, 40, 64, 80, 128).  The receptor spectra of
  *                         a plan are laid out for the mode in force at dlpd_set_receptor time: do not switch between
