@@ -30,10 +30,10 @@ for s in $STAGES; do
         python bench.py --steps 1 --warmup 0 --cpu-rotations 0 --rot-batch 32 --max-rot 32 > $OUT/ncu_run.log 2>&1 ;;
     sanitize)
       timeout 900 compute-sanitizer --tool memcheck python -m pytest tests/test_gpu_parity.py -q -x \
-        -k "(small and 8-4) or ties or (cluster_plane_search_small and 16-4) or (pipelined_epilogue_small and 8-4) or project_clash or (tensor_filter_small and 8-16)" \
+        -k "(small and 8-4) or ties or (cluster_plane_search_small and 16-4) or (pipelined_epilogue_small and 8-4) or project_clash or (tensor_filter_small and 8-16) or volume_convolution_128 or test_search_full_size_80_matches" \
         > $OUT/memcheck.log 2>&1
       timeout 900 compute-sanitizer --tool racecheck python -m pytest tests/test_gpu_parity.py -q -x \
-        -k "(search_small_matches_oracle and 8-4) or (cluster_plane_search_small and 16-4) or (pipelined_epilogue_small and 8-4) or (tensor_filter_small and 8-16)" \
+        -k "(search_small_matches_oracle and 8-4) or (cluster_plane_search_small and 16-4) or (pipelined_epilogue_small and 8-4) or (tensor_filter_small and 8-16) or volume_convolution_128 or test_search_full_size_80_matches" \
         > $OUT/racecheck.log 2>&1 ;;
     cfg5)
       timeout 600 python bench.py --config 5 --steps 4 --warmup 3 --cpu-rotations 0 --rot-batch 32 --max-rot 32 > $OUT/bench_cfg5.log 2>&1; echo "rc=$?" >> $OUT/bench_cfg5.log ;;
