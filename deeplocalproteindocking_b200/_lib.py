@@ -41,7 +41,7 @@ SIGNATURES = {
 
 CENTER_MODES = {"box": 0, "grid": 1}
 OPTIONS = {"plane_mode": 1, "epilogue_tile": 2, "epilogue_kind": 3, "filter_kind": 4}      # DLPD_OPT_* of include/dlpd.h
-EPILOGUE_KINDS = {"auto": 0, "classic": 1, "pipelined": 2, "duo": 3}
+EPILOGUE_KINDS = {"auto": 0, "classic": 1, "pipelined": 2, "duo": 3, "fused": 4}
 PLANE_MODES = {"auto": 0, "single": 1, "cluster": 2}
 FILTER_KINDS = {"auto": 0, "fp32": 1, "tensor": 2}
 
@@ -82,7 +82,7 @@ def get_lib() -> ctypes.CDLL:
 
 def set_option(name: str, value) -> None:
     """Process-wide kernel selection switches (`dlpd_set_option`): plane_mode = auto | single | cluster,
-    epilogue_tile = 0 (auto) | 1 | 2, epilogue_kind = auto | classic | pipelined | duo, filter_kind = auto | fp32 | tensor
+    epilogue_tile = 0 (auto) | 1 | 2, epilogue_kind = auto | classic | pipelined | duo | fused, filter_kind = auto | fp32 | tensor
     (first filter layer as packed FFMA or as fp16-split mma.sync).  Tuning and tests only; the defaults are what ships."""
     lib = get_lib()
     if name == "plane_mode" and isinstance(value, str):

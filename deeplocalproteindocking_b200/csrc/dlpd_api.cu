@@ -279,6 +279,9 @@ static int g_filter_kind = DLPD_FILTER_AUTO;
 #ifndef DLPD_EPILOGUE_DEFAULT_DUO
 #define DLPD_EPILOGUE_DEFAULT_DUO 0
 #endif
+#ifndef DLPD_EPILOGUE_DEFAULT_FUSED
+#define DLPD_EPILOGUE_DEFAULT_FUSED 0
+#endif
 #ifndef DLPD_EPILOGUE_DEFAULT_PIPELINED
 #define DLPD_EPILOGUE_DEFAULT_PIPELINED 0
 #endif
@@ -672,6 +675,23 @@ static int launch_epilogue_pipe(dlpd_plan* p, int n, int P, float tau, float* ou
     }
 }
 template <int L, int C0, int C1, int H>
+static int launch_epilogue_fused(dlpd_plan* p, int n, int P, float tau, float* out_scores, const CandArgs& ca, dlpd_stream_t st) {
+    typedef EpilogueFused<L, C0, C1, H> K;
+    if constexpr (K::SMEM <= SMEM_MAX) {
+        typename K::Params e;
+        e.s2_0 = p->s2_0; e.h1 = p->h1; e.best = p->best; e.score_out = out_scores;
+        e.tw0 = p->tw0; e.n_rot = n; e.tau = tau;
+        e.cand = ca.cand; e.cand_count = ca.count; e.cand_cap = ca.cap; e.cand_key = ca.key; e.rot_base = ca.rot_base;
+        e.n_tiles = P * L * L;                      // 2x2 groups
+        e.mlp = nullptr;
+        e.grid = e.n_tiles < p->sm_count ? e.n_tiles : p->sm_count;
+        fill_filter(p, e.filt);
+        return launch<K>(dim3(e.grid), e, st);
+    } else {
+        return fail(DLPD_EINVAL, "the fused epilogue does not fit shared memory at this box size");
+    }
+}
+template <int L, int C0, int C1, int H>
 static int launch_epilogue_duo(dlpd_plan* p, int n, int P, float tau, float* out_scores, const CandArgs& ca, dlpd_stream_t st) {
     typedef EpilogueDuo<L, C0, C1, H> K;
     if constexpr (2 * (K::SMEM + 1024) <= 228 * 1024) {
@@ -697,6 +717,9 @@ static int launch_epilogue(dlpd_plan* p, int n, int P, float tau, float* out_sco
     const bool duo_fits = 2 * (EpilogueDuo<L, C0, C1, H>::SMEM + 1024) <= 228 * 1024;
     if (g_epi_kind == DLPD_EPILOGUE_DUO || (g_epi_kind == DLPD_EPILOGUE_AUTO && DLPD_EPILOGUE_DEFAULT_DUO && duo_fits && !g_epi_tile))
         return launch_epilogue_duo<L, C0, C1, H>(p, n, P, tau, out_scores, ca, st);
+    const bool fused_fits = EpilogueFused<L, C0, C1, H>::SMEM <= SMEM_MAX;
+    if (g_epi_kind == DLPD_EPILOGUE_FUSED || (g_epi_kind == DLPD_EPILOGUE_AUTO && DLPD_EPILOGUE_DEFAULT_FUSED && fused_fits && !g_epi_tile))
+        return launch_epilogue_fused<L, C0, C1, H>(p, n, P, tau, out_scores, ca, st);
     const bool pipe_fits = EpiloguePipe<L, C0, C1, H>::SMEM <= SMEM_MAX;
     if (g_epi_kind == DLPD_EPILOGUE_PIPELINED || (g_epi_kind == DLPD_EPILOGUE_AUTO && DLPD_EPILOGUE_DEFAULT_PIPELINED && pipe_fits && !g_epi_tile))
         return launch_epilogue_pipe<L, C0, C1, H>(p, n, P, tau, out_scores, ca, st);
@@ -865,7 +888,7 @@ extern "C" int dlpd_set_option(int key, int value) {
             g_plane_mode = value;
             return 0;
         case DLPD_OPT_EPILOGUE_KIND:
-            if (value < DLPD_EPILOGUE_AUTO || value > DLPD_EPILOGUE_DUO) return fail(DLPD_EINVAL, "bad epilogue kind");
+            if (value < DLPD_EPILOGUE_AUTO || value > DLPD_EPILOGUE_FUSED) return fail(DLPD_EINVAL, "bad epilogue kind");
             g_epi_kind = value;
             return 0;
         case DLPD_OPT_EPILOGUE_TILE:

@@ -390,6 +390,24 @@ DLPD_DEV void fft_pass(cpx* s, const cpx* tw, LineOff off, In in = In(), Out out
     fft_pass_team<KIND, RA, RB, NLINES, LEN, NB, TWN, ES>(CtaTeam<NT>(), s, tw, off, in, out, mul);
 }
 
+// ONE task of a plain in-place pass (no hooks, no loop, no barrier): lets a caller put a butterfly task and unrelated
+// register-only work into the same basic block so that the scheduler interleaves them (EpilogueFused)
+template <int KIND, int RA, int RB, int NLINES, int LEN, int NB, int TWN, int ES, class LineOff>
+DLPD_DEV void fft_one_task(cpx* s, const cpx* tw, LineOff off, int t) {
+    typedef FftTask<KIND, RA, RB, LEN, NB, TWN, ES> T;
+    constexpr int M = T::M, M2 = T::M2;
+    const int l = t % NLINES, b = t / NLINES, blk = b / M2, j = b - blk * M2, e0 = blk * NB + j;
+    cpx* p = s + off(l) + e0 * ES;
+    cpx a[RA][RB];
+    NoHook none;
+    T::run(a, p, tw, l, e0, j, none, none);
+    DLPD_UNROLL
+    for (int i = 0; i < RA; ++i) {
+        DLPD_UNROLL
+        for (int k = 0; k < RB; ++k) p[(i * M + k * M2) * ES] = a[i][k];
+    }
+}
+
 // Pruned forward head whose inputs were fetched into registers ahead of time (persistent kernels: the next work item's
 // global loads are issued while the current one finishes).  Thread `tid` owns tasks tid, tid + NT, ...: exactly NPRE each.
 template <int RB, int NLINES, int LEN, int TWN, int ES, int NPRE, class TM, class LineOff>

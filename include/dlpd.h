@@ -126,7 +126,7 @@ int dlpd_project_clash(const double* coords, const double* R, int nat, int n, in
  *                         a plan are laid out for the mode in force at dlpd_set_receptor time: do not switch between
  *                         dlpd_set_receptor and dlpd_search.
  * DLPD_OPT_EPILOGUE_TILE  0 = automatic, 1 = 2x1, 2 = 2x2 (x,y) columns per epilogue tile (classic epilogue)
- * DLPD_OPT_EPILOGUE_KIND  AUTO / CLASSIC / PIPELINED, see below
+ * DLPD_OPT_EPILOGUE_KIND  AUTO / CLASSIC / PIPELINED / DUO / FUSED, see below
  * DLPD_OPT_FILTER_KIND    how the classic epilogue evaluates the level-0 half of SimpleFilter's first layer
  *                         (DockingModels.py:29, 16 -> H): FP32 = packed FFMA chain; TENSOR = mma.sync m16n8k16 on fp16
  *                         operands split hi + lo (three products per term, fp32 accumulation: agrees with the FFMA
@@ -142,6 +142,8 @@ int dlpd_project_clash(const double* coords, const double* R, int nat, int n, in
 #define DLPD_EPILOGUE_CLASSIC 1     /* one consumer team: transform then filter, next tile prefetched            */
 #define DLPD_EPILOGUE_PIPELINED 2   /* load / transform / filter of consecutive half-tiles overlap (N <= 160)    */
 #define DLPD_EPILOGUE_DUO 3         /* two independent half-tile CTAs per SM (N <= 160)                          */
+#define DLPD_EPILOGUE_FUSED 4       /* half-tile ring; every thread interleaves a butterfly task of half-tile i
+                                       with the filter of its voxel of half-tile i - 1 (N <= 160)                */
 #define DLPD_PLANE_AUTO 0
 #define DLPD_PLANE_SINGLE 1
 #define DLPD_PLANE_CLUSTER 2

@@ -106,7 +106,7 @@ class EmuPlan:
 
 
 OPT_PLANE_MODE, OPT_EPILOGUE_TILE, OPT_EPILOGUE_KIND = 1, 2, 3
-EPILOGUE_AUTO, EPILOGUE_CLASSIC, EPILOGUE_PIPELINED, EPILOGUE_DUO = 0, 1, 2, 3
+EPILOGUE_AUTO, EPILOGUE_CLASSIC, EPILOGUE_PIPELINED, EPILOGUE_DUO, EPILOGUE_FUSED = 0, 1, 2, 3, 4
 PLANE_AUTO, PLANE_SINGLE, PLANE_CLUSTER = 0, 1, 2
 
 

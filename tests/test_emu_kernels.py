@@ -249,3 +249,20 @@ def test_emu_duo_epilogue_matches_oracle(L, C0, C1, H, n, duo_epilogue):
 
 def test_emu_duo_epilogue_candidates(duo_epilogue):
     test_emu_candidates_are_exactly_the_translations_below_the_threshold()
+
+
+# ---- fused epilogue (butterfly task of half-tile i interleaved with the filter of half-tile i - 1) -------------------
+@pytest.fixture
+def fused_epilogue():
+    emu.set_option(emu.OPT_EPILOGUE_KIND, emu.EPILOGUE_FUSED)
+    yield
+    emu.set_option(emu.OPT_EPILOGUE_KIND, emu.EPILOGUE_AUTO)
+
+
+@pytest.mark.parametrize("L,C0,C1,H,n", [(8, 4, 6, 5, 3), (20, 4, 6, 5, 3), (16, 16, 32, 24, 2)])
+def test_emu_fused_epilogue_matches_oracle(L, C0, C1, H, n, fused_epilogue):
+    test_emu_search_matches_oracle(L, C0, C1, H, n)
+
+
+def test_emu_fused_epilogue_candidates(fused_epilogue):
+    test_emu_candidates_are_exactly_the_translations_below_the_threshold()

@@ -363,22 +363,40 @@ def test_duo_epilogue_80_matches_oracle(duo_epilogue):
     test_search_full_size_80_matches_oracle()
 
 
+# ---- fused epilogue -------------------------------------------------------------------------------------------------
+@pytest.fixture
+def fused_epilogue():
+    _lib.set_option("epilogue_kind", "fused")
+    yield
+    _lib.set_option("epilogue_kind", "auto")
+
+
+@pytest.mark.parametrize("L,C0,C1,H,n", [(8, 4, 6, 5, 5), (16, 4, 6, 5, 4), (20, 4, 6, 5, 3), (8, 16, 32, 24, 3),
+                                         (16, 16, 32, 24, 2), (20, 16, 32, 24, 5)])
+def test_fused_epilogue_small_matches_oracle(L, C0, C1, H, n, fused_epilogue):
+    test_search_small_matches_oracle(L, C0, C1, H, n)
+
+
+def test_fused_epilogue_80_matches_oracle(fused_epilogue):
+    test_search_full_size_80_matches_oracle()
+
+
 def test_epilogue_kinds_80_many_rotations_identical():
-    """33 rotations (17 pairs, odd tail) at L=80 through all three epilogues: identical best poses and scores."""
+    """33 rotations (17 pairs, odd tail) at L=80 through all four epilogues: identical best poses and scores."""
     L, C0, C1 = 80, 16, 32
     rec, rec_clash = synthetic.learned_volumes(L, (C0, C1), seed=31)
     lig, lig_clash = synthetic.learned_volumes(L, (C0, C1), seed=32)
     filt = O.FilterWeights.random(C0 + C1, seed=33)
     Rs = R20[torch.arange(33) * 53 + 2]
     out = []
-    for kind in ("classic", "pipelined", "duo"):
+    for kind in ("classic", "pipelined", "duo", "fused"):
         _lib.set_option("epilogue_kind", kind)
         eng = DockingSearch(L, (C0, C1), max_rot=16, device=DEV)
         eng.set_receptor(rec, rec_clash); eng.set_ligand(lig, lig_clash); eng.set_filter((filt.W1, filt.b1, filt.W2, filt.b2))
         out.append(eng.search(Rs, 30.0)[0].cpu())
         eng.close()
     _lib.set_option("epilogue_kind", "auto")
-    assert torch.equal(out[0], out[1]) and torch.equal(out[0], out[2])
+    assert torch.equal(out[0], out[1]) and torch.equal(out[0], out[2]) and torch.equal(out[0], out[3])
 
 
 # ---- first filter layer: packed FFMA chain vs fp16-split mma.sync -------------------------------------------------
