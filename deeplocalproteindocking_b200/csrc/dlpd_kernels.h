@@ -1657,7 +1657,7 @@ template <int L_, int C0, int C1, int H> struct EpiloguePipe {
 #define DLPD_FUSED_NC 352
 #endif
 #ifndef DLPD_FUSED_NPROD
-#define DLPD_FUSED_NPROD 64
+#define DLPD_FUSED_NPROD DLPD_PIPE_NPROD
 #endif
 template <int L_, int C0, int C1, int H> struct EpilogueFused {
     typedef Epilogue<L_, C0, C1, H, 1> E;            // half-tile geometry and scoring code
@@ -1678,6 +1678,7 @@ template <int L_, int C0, int C1, int H> struct EpilogueFused {
     static constexpr int NHEAD = NL0 * (N / (2 * LP::R0));
     static constexpr int NVOX = XY * N, CA = C0 / 2;
     static_assert(2 + 2 * NB <= 16 && PW % 32 == 0 && NC % 32 == 0 && HB % 2 == 0 && C0 >= 2, "pipeline shape");
+    static_assert(PW == PP::PW, "the producers run EpiloguePipe::issue_loads, which strides by its own group width");
 
     static DLPD_DEV void tail_task(cpx* DLPD_RESTRICT b, const cpx* DLPD_RESTRICT tw, int t) {
         if constexpr (LP::TAIL > 1) fft_one_task<PASS_DIT, LP::TA, LP::TB, NL0, N, LP::TAIL, N, NL0>(b, tw, LineMul<1>(), t);
