@@ -264,7 +264,7 @@ template <int L> static int launch_fwdzc_t(const FwdZCParams& p, int P, dlpd_str
     typedef FwdZC<L, Tile<L>::CL_CG, Tile<L>::CL_YT> K;
     return launch_mb<K, false>(dim3(L * K::YTILES, p.C / K::CG, P), p, st);
 }
-// Plane<L> needs the whole N x N plane in one SM's shared memory; PlaneX<L, 4> spreads it over a cluster of 4 CTAs.
+// Plane<L> needs the whole N x N plane in one SM's shared memory; PlaneX<L, CL> spreads it over a cluster of CL = 4 or 8 CTAs.
 static constexpr int SMEM_MAX = 227 * 1024;
 #ifndef DLPD_PLANE_WAVES
 #define DLPD_PLANE_WAVES 1      // look-ahead distance of Plane's S1 prefetch in grid waves

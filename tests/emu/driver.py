@@ -19,12 +19,27 @@ SRC = os.path.join(ROOT, "deeplocalproteindocking_b200", "csrc")
 SO = os.path.join(HERE, "libdlpd_emu.so")
 
 
-def build(force=False):
+def build(force=False, flags=(), so=None):
+    """flags / so: a second build of the emulation with other -D switches (e.g. the 8-CTA cluster code at L = 16)."""
+    so = so or SO
     srcs = [os.path.join(SRC, f) for f in os.listdir(SRC)] + [os.path.join(ROOT, "include", "dlpd.h")]
-    if force or not os.path.exists(SO) or any(os.path.getmtime(s) > os.path.getmtime(SO) for s in srcs):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-DDLPD_EMU", "-x", "c++", "-fPIC", "-shared",
-                               "-o", SO, os.path.join(SRC, "dlpd_api.cu")])
-    return SO
+    if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-DDLPD_EMU", *flags, "-x", "c++", "-fPIC", "-shared",
+                               "-o", so, os.path.join(SRC, "dlpd_api.cu")])
+    return so
+
+
+def use_variant(flags, tag):
+    """Load a variant build as THE emulation library of this process; returns the previous one (pass it to `restore`)."""
+    global _emu
+    prev = _emu
+    _emu = _lib.bind_signatures(ctypes.CDLL(build(flags=flags, so=os.path.join(HERE, "libdlpd_emu_%s.so" % tag))))
+    return prev
+
+
+def restore(prev):
+    global _emu
+    _emu = prev
 
 
 _emu = None

@@ -125,7 +125,7 @@ def test_emu_unsupported_configuration_fails_loudly():
 
 @pytest.fixture
 def cluster_mode():
-    """Force the 4-CTA cluster plane kernel (PlaneX) and the 2x1 epilogue tile -- the kernels the 128^3 configuration uses."""
+    """Force the cluster plane kernel (PlaneX, 4 CTAs at these sizes) and the 2x1 epilogue tile -- the kernels the 128^3 configuration uses."""
     emu.set_option(emu.OPT_PLANE_MODE, emu.PLANE_CLUSTER)
     emu.set_option(emu.OPT_EPILOGUE_TILE, 1)
     yield
@@ -146,6 +146,29 @@ def test_emu_cluster_plane_correlate_matches_oracle(L, cluster_mode):
 @pytest.mark.parametrize("L,C0,C1,H,n", [(8, 4, 6, 5, 3), (16, 4, 6, 5, 2), (20, 16, 32, 24, 3)])
 def test_emu_cluster_plane_search_matches_oracle(L, C0, C1, H, n, cluster_mode):
     test_emu_search_matches_oracle(L, C0, C1, H, n)
+
+
+@pytest.fixture
+def cluster8_mode():
+    """The 8-CTA cluster form of PlaneX (what N = 256 runs: S1 folded straight from global memory, radix-8 exchange), compiled
+    for L = 16 so that the emulation can afford it (-DDLPD_PLANEX_CL_16=8)."""
+    prev = emu.use_variant(["-DDLPD_PLANEX_CL_16=8"], "cl8")
+    emu.set_option(emu.OPT_PLANE_MODE, emu.PLANE_CLUSTER)
+    emu.set_option(emu.OPT_EPILOGUE_TILE, 1)
+    yield
+    emu.set_option(emu.OPT_PLANE_MODE, emu.PLANE_AUTO)
+    emu.set_option(emu.OPT_EPILOGUE_TILE, 0)
+    emu.restore(prev)
+
+
+def test_emu_cluster8_plane_correlate_and_search_match_oracle(cluster8_mode):
+    g = torch.Generator().manual_seed(16)
+    v1 = torch.randn(1, 2, 16, 16, 16, generator=g)
+    v2 = torch.randn(1, 2, 16, 16, 16, generator=g)
+    want = O.correlate(v1.double(), v2.double())
+    assert (emu.volume_correlate(v1, v2).double() - want).abs().max() <= 2e-5 * want.abs().max()
+    test_emu_search_matches_oracle(16, 4, 6, 5, 2)
+    test_emu_search_matches_oracle(16, 16, 32, 24, 2)
 
 
 def test_emu_candidates_are_exactly_the_translations_below_the_threshold():

@@ -243,7 +243,7 @@ def test_errors_are_loud():
         out.sum().backward()
 
 
-# ---- the kernels of the 128^3 configuration: 4-CTA cluster plane (distributed shared memory) + 2x1 epilogue tile ----
+# ---- the kernels of the 128^3 configuration: cluster plane (distributed shared memory; 8 CTAs at 128^3, 4 below) + 2x1 epilogue tile ----
 @pytest.fixture
 def cluster_mode():
     _lib.set_option("plane_mode", "cluster")
