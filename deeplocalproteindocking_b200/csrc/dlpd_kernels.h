@@ -57,6 +57,9 @@
 #ifndef DLPD_PLANE_PERSISTENT
 #define DLPD_PLANE_PERSISTENT 1
 #endif
+#ifndef DLPD_PLANE_COLBLOCKS
+#define DLPD_PLANE_COLBLOCKS 1       // inverse-x column ownership that makes the barrier between planes unnecessary
+#endif
 #ifndef DLPD_PLANE_PREFETCH
 #define DLPD_PLANE_PREFETCH 2
 #endif
@@ -477,6 +480,30 @@ template <int L_> struct Plane {
 #endif
         }
     };
+    // Column ownership of the inverse-x passes in the team path: team g takes the two blocks of L/G columns that start at
+    // y = g L/G and y = L + g L/G.  The first block is exactly the set of columns the same team fills in the forward-x
+    // passes of the NEXT plane, so a persistent CTA needs no CTA-wide barrier between planes: nobody else reads them.
+    static constexpr int CB = (G > 1) ? L / G : 1;
+    struct ColBlocks {       // local line l in [0, 2 CB) -> column offset from the team's first column
+        DLPD_DEV int operator()(int l) const { return l < CB ? l : l + (L - CB); }
+    };
+    struct StoreS2TiledPairCB {  // StoreS2TiledPair for a team's two column blocks; y0 = g CB
+        cpx* out;
+        int y0;
+        DLPD_DEV void operator()(int l, int e, cpx v0, cpx v1) const {
+            const int y = y0 + (l < CB ? l : l + (L - CB));
+#if defined(DLPD_ABLATE_PLANE_STORE)
+            if (v0.x == 1.2345e30f) out[y] = v1;
+#else
+            store_cpx2(out + ((((e >> 1) * L) + (y >> 1)) << 2) + ((y & 1) << 1), v0, v1);
+#endif
+        }
+    };
+    struct StoreS2CB {
+        cpx* out;
+        int y0;
+        DLPD_DEV void operator()(int l, int e, cpx v) const { out[e * N + y0 + (l < CB ? l : l + (L - CB))] = v; }
+    };
     // grid: x = P * N * C  with the pair index fastest (CTAs that share a receptor plane run together -> L2 reuse)
     static DLPD_DEV void body(const Params& p, int bx, int, int, char* smem) {
         cpx* pl = reinterpret_cast<cpx*>(smem);        // [x][y], pitch NP
@@ -535,7 +562,14 @@ template <int L_> struct Plane {
                     DLPD_SYNC();
                     DLPD_FOR_TEAMS(g, G, TNT) {
                         const Team tm{DLPD_TEAM_TID(TNT), g + 1};
+#if DLPD_PLANE_COLBLOCKS
+                        cpx* cols = pl + g * CB;
+                        typedef ColBlocks InvOff;
+                        static_assert(N / G == 2 * CB && CB % 2 == 0, "two column blocks per team");
+#else
                         cpx* cols = pl + g * (N / G);
+                        typedef LineMul<1> InvOff;
+#endif
 #if !defined(DLPD_EMU)
                         if constexpr (PRE) {
                             have = b + stride < total;
@@ -546,17 +580,29 @@ template <int L_> struct Plane {
                             }
                         }
 #endif
-                        team_inv_tail<N, N / G, NP, PP>(tm, cols, tw, LineMul<1>());                        // inverse x
+                        team_inv_tail<N, N / G, NP, PP>(tm, cols, tw, InvOff());                            // inverse x
+                        static_assert((N / G) % 2 == 0 && (N / 2 / PP::R0) % 2 == 0, "tiled pair stores");
+#if DLPD_PLANE_COLBLOCKS
                         if (p.tiled) {
-                            static_assert((N / G) % 2 == 0 && (N / 2 / PP::R0) % 2 == 0, "tiled pair stores");
+                            GlobalOutPair<StoreS2TiledPairCB> out{StoreS2TiledPairCB{p.out + plane_b * N * N, g * CB}};
+                            team_inv_head<N, N / G, NP, PP>(tm, cols, tw, InvOff(), out);
+                        } else {
+                            GlobalOut<StoreS2CB> out{StoreS2CB{p.out + plane_b * N * N, g * CB}};
+                            team_inv_head<N, N / G, NP, PP>(tm, cols, tw, InvOff(), out);
+                        }
+#else
+                        if (p.tiled) {
                             GlobalOutPair<StoreS2TiledPair> out{StoreS2TiledPair{p.out + plane_b * N * N + g * (N / G / 2) * 4}};
-                            team_inv_head<N, N / G, NP, PP>(tm, cols, tw, LineMul<1>(), out);
+                            team_inv_head<N, N / G, NP, PP>(tm, cols, tw, InvOff(), out);
                         } else {
                             GlobalOut<StoreS2> out{StoreS2{p.out + plane_b * N * N + g * (N / G)}};
-                            team_inv_head<N, N / G, NP, PP>(tm, cols, tw, LineMul<1>(), out);
+                            team_inv_head<N, N / G, NP, PP>(tm, cols, tw, InvOff(), out);
                         }
+#endif
                     }
+#if !DLPD_PLANE_COLBLOCKS
                     if (b + stride < total) DLPD_SYNC();      // the next plane's first pass overwrites columns other teams still read
+#endif
                 }
                 return;
             }
