@@ -548,7 +548,7 @@ template <int L_> struct Plane {
 #endif
                         if (!first_done) team_fwd_head<N, L / G, NP, PP>(tm, pl + g * (L / G), tw, LineMul<1>(), in);
                         if (g == 0) prefetch(p, b, spec_b);
-                        team_fwd_tail<N, L / G, NP, PP>(tm, pl + g * (L / G), tw, LineMul<1>());
+                        team_fwd_tail<N, L / G, NP, PP>(NoSyncTeam<Team>{tm}, pl + g * (L / G), tw, LineMul<1>());     // CTA barrier next
                     }
                     DLPD_SYNC();
                     DLPD_FOR_TEAMS(g, G, TNT) {
@@ -557,7 +557,7 @@ template <int L_> struct Plane {
                         PointMul<MulSpec> mul{MulSpec{spec_b + g * (N / G)}};
                         team_fwd_head<N, N / G, 1, PP>(tm, rows, tw, LineMul<NP>());                        // along y, rows kx'
                         team_mid<N, N / G, 1, PP>(tm, rows, tw, LineMul<NP>(), mul);                        // y tail . multiply . inverse y tail
-                        team_inv_head<N, N / G, 1, PP>(tm, rows, tw, LineMul<NP>());                        // inverse y
+                        team_inv_head<N, N / G, 1, PP>(NoSyncTeam<Team>{tm}, rows, tw, LineMul<NP>());      // inverse y; CTA barrier next
                     }
                     DLPD_SYNC();
                     DLPD_FOR_TEAMS(g, G, TNT) {

@@ -123,6 +123,14 @@ template <int NT_, bool DUAL_ = false> struct SubTeam {
     DLPD_DEV int tid() const { return tid_; }
     DLPD_DEV void sync() const { named_barrier_sync(bar_, NT_); }
 };
+// the same team for a pass whose closing barrier is subsumed by a wider one that follows immediately
+template <class TM> struct NoSyncTeam {
+    static constexpr int NT = TM::NT;
+    static constexpr bool DUAL = TM::DUAL;
+    TM tm;
+    DLPD_DEV int tid() const { return tm.tid(); }
+    DLPD_DEV void sync() const {}
+};
 #if defined(DLPD_EMU)
   #define DLPD_TEAM_TASKS(tm, t, n) for (int t = 0; t < (n); ++t)
   // pairs (t, t + NT): the emulated thread plays every team thread of the even rounds
