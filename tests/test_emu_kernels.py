@@ -289,3 +289,37 @@ def test_emu_fused_epilogue_matches_oracle(L, C0, C1, H, n, fused_epilogue):
 
 def test_emu_fused_epilogue_candidates(fused_epilogue):
     test_emu_candidates_are_exactly_the_translations_below_the_threshold()
+
+
+def test_emu_correlate_80_team_plane_matches_oracle():
+    """L = 80 is the one size whose plane kernel runs the TEAM path (5 teams, per-team barriers, inverse-x teams owning two
+    interleaved column blocks): one channel through the standalone correlation checks its index maps on the CPU."""
+    g = torch.Generator().manual_seed(80)
+    v1 = torch.randn(1, 1, 80, 80, 80, generator=g)
+    v2 = torch.randn(1, 1, 80, 80, 80, generator=g)
+    got = emu.volume_correlate(v1, v2)
+    want = O.correlate(v1.double(), v2.double())
+    assert (got.double() - want).abs().max() <= 2e-5 * want.abs().max()
+
+
+def test_emu_search_80_one_rotation_matches_oracle():
+    """The BASELINE shape (L = 80, 16 + 32 channels) through the emulated kernels for ONE rotation: covers the persistent team
+    path of the plane kernel with the tiled pair stores, the 2x2-tile epilogue and HiddenL1 at full size on the CPU."""
+    from deeplocalproteindocking_b200 import synthetic
+    L, C0, C1, H = 80, 16, 32, 24
+    rec, rec_clash = synthetic.learned_volumes(L, (C0, C1), seed=1)
+    lig, lig_clash = synthetic.learned_volumes(L, (C0, C1), seed=2)
+    filt = O.FilterWeights.random(C0 + C1, seed=3)
+    Rs = R20[[316]]
+    plan = emu.EmuPlan(L, C0, C1, H, max_rot=2)
+    try:
+        plan.set_receptor(rec[0], rec[1], rec_clash)
+        plan.set_ligand(lig[0], lig[1], lig_clash)
+        plan.set_filter(filt.W1, filt.b1, filt.W2, filt.b2)
+        best, _ = plan.search(Rs, 30.0)
+    finally:
+        plan.close()
+    want, _ = O.dock([v[None].double() for v in rec], rec_clash[None, None].double(), [v[None].double() for v in lig],
+                     lig_clash.double(), Rs, filt.to(torch.float64), 30.0, K=0)
+    assert torch.equal(best[:, 1:].double(), want[:, 1:])
+    assert torch.allclose(best[:, 0].double(), want[:, 0], rtol=1e-4, atol=1e-6)
