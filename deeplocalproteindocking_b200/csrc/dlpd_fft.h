@@ -187,7 +187,9 @@ enum PassKind {
 // One fused pass over NLINES lines of LEN elements held in shared memory `s` (element stride ES, line offsets `off`).
 //   NB   block size of the outer radix (LEN % NB == 0);  TWN size of the twiddle table tw[k] = e^{+2 pi i k/TWN}
 //   In / Out / Mul: NoHook or the hook structs above
-template <int KIND, int RA, int RB, int LEN, int NB, int TWN, int ES> struct FftTask {
+// PK: `tw` is a PACKED twiddle table for this (2, RB) head pass -- entry [j][0..RB) = w_NB^(j + k M2), [j][RB..2RB-1) = w_M^(j k)
+// (k = 1..RB-1), one zero pad -- read with RB 16-byte loads instead of 2 RB - 1 8-byte ones (see pack_head_twiddles)
+template <int KIND, int RA, int RB, int LEN, int NB, int TWN, int ES, bool PK = false> struct FftTask {
     static constexpr int M = NB / RA;             // outer sub-block
     static constexpr int M2 = M / RB;             // inner sub-block: range of the butterfly index j
     static constexpr int TPL = LEN / (RA * RB);   // tasks per line
@@ -198,6 +200,16 @@ template <int KIND, int RA, int RB, int LEN, int NB, int TWN, int ES> struct Fft
     static_assert(KIND != PASS_DIF_PRUNED || RA == 2, "pruned pass is the outermost radix-2 step");
     // innermost pass (one butterfly per block, j == 0): every twiddle is a compile-time power of w_NB, NB | 16
     static constexpr bool CONST_TW = (M2 == 1) && (16 % NB == 0 || NB == 20);
+    static_assert(!PK || (RA == 2 && M2 > 1 && !CONST_TW), "packed twiddles are for the (2, R0) head passes");
+    static DLPD_DEV void load_packed(cpx (&w)[2 * RB], const cpx* tw, int j) {
+        const float4* q = reinterpret_cast<const float4*>(tw + j * 2 * RB);
+        DLPD_UNROLL
+        for (int u = 0; u < RB; ++u) {
+            const float4 v = q[u];
+            w[2 * u] = make_float2(v.x, v.y);
+            w[2 * u + 1] = make_float2(v.z, v.w);
+        }
+    }
 
     // load the RA x RB values of the task whose first element is e0 = blk*NB + j (line l at `p`) and transform them
     template <class In, class Mul>
@@ -251,6 +263,8 @@ template <int KIND, int RA, int RB, int LEN, int NB, int TWN, int ES> struct Fft
     }
     static DLPD_DEV void compute_fwd(cpx (&a)[RA][RB], const cpx* tw, int j) {
         if (FWD) {
+            cpx w[2 * RB];
+            if constexpr (PK) load_packed(w, tw, j);
             // outer DFT over i for each k, then twiddle w_NB^{(j + k*M2) * pa}
             DLPD_UNROLL
             for (int k = 0; k < RB; ++k) {
@@ -267,6 +281,7 @@ template <int KIND, int RA, int RB, int LEN, int NB, int TWN, int ES> struct Fft
                 DLPD_UNROLL
                 for (int i = 1; i < RA; ++i) {
                     if constexpr (CONST_TW) a[i][k] = mul_wconst<NB>(c[i], k * i);
+                    else if constexpr (PK) a[i][k] = cmul(c[i], w[k]);
                     else a[i][k] = cmul(c[i], tw[TWO * (j + k * M2) * i]);
                 }
             }
@@ -276,19 +291,21 @@ template <int KIND, int RA, int RB, int LEN, int NB, int TWN, int ES> struct Fft
                 Dft<RB>::run(a[i]);
                 if constexpr (M2 > 1) {
                     DLPD_UNROLL
-                    for (int k = 1; k < RB; ++k) a[i][k] = cmul(a[i][k], tw[TWI * j * k]);
+                    for (int k = 1; k < RB; ++k) a[i][k] = cmul(a[i][k], PK ? w[RB + k - 1] : tw[TWI * j * k]);
                 }
             }
         }
     }
     static DLPD_DEV void compute_inv(cpx (&a)[RA][RB], const cpx* tw, int j) {
         if (INV) {
+            cpx w[2 * RB];
+            if constexpr (PK) load_packed(w, tw, j);
             // inner: twiddle w_M^{j * s}, DFT over s for each pa
             DLPD_UNROLL
             for (int i = 0; i < RA; ++i) {
                 if constexpr (M2 > 1) {
                     DLPD_UNROLL
-                    for (int k = 1; k < RB; ++k) a[i][k] = cmul(a[i][k], tw[TWI * j * k]);
+                    for (int k = 1; k < RB; ++k) a[i][k] = cmul(a[i][k], PK ? w[RB + k - 1] : tw[TWI * j * k]);
                 }
                 Dft<RB>::run(a[i]);
             }
@@ -300,6 +317,7 @@ template <int KIND, int RA, int RB, int LEN, int NB, int TWN, int ES> struct Fft
                 DLPD_UNROLL
                 for (int i = 1; i < RA; ++i) {
                     if constexpr (CONST_TW) c[i] = mul_wconst<NB>(a[i][k], k * i);
+                    else if constexpr (PK) c[i] = cmul(a[i][k], w[k]);
                     else c[i] = cmul(a[i][k], tw[TWO * (j + k * M2) * i]);
                 }
                 Dft<RA>::run(c);
@@ -310,10 +328,10 @@ template <int KIND, int RA, int RB, int LEN, int NB, int TWN, int ES> struct Fft
     }
 };
 
-template <int KIND, int RA, int RB, int NLINES, int LEN, int NB, int TWN, int ES, class TM, class LineOff,
+template <int KIND, int RA, int RB, int NLINES, int LEN, int NB, int TWN, int ES, bool PK = false, class TM, class LineOff,
           class In = NoHook, class Out = NoHook, class Mul = NoHook>
 DLPD_DEV void fft_pass_team(const TM& tm, cpx* s, const cpx* tw, LineOff off, In in = In(), Out out = Out(), Mul mul = Mul()) {
-    typedef FftTask<KIND, RA, RB, LEN, NB, TWN, ES> T;
+    typedef FftTask<KIND, RA, RB, LEN, NB, TWN, ES, PK> T;
     constexpr int M = T::M, M2 = T::M2, TPL = T::TPL;
     if constexpr (is_pair_out<Out>::value) {
         // two neighbouring butterflies (elements e, e+1) per task: the hook stores 16-byte pairs
@@ -388,6 +406,15 @@ template <int KIND, int RA, int RB, int NLINES, int LEN, int NB, int TWN, int ES
           class In = NoHook, class Out = NoHook, class Mul = NoHook>
 DLPD_DEV void fft_pass(cpx* s, const cpx* tw, LineOff off, In in = In(), Out out = Out(), Mul mul = Mul()) {
     fft_pass_team<KIND, RA, RB, NLINES, LEN, NB, TWN, ES>(CtaTeam<NT>(), s, tw, off, in, out, mul);
+}
+
+// packed twiddles of the (2, R0) head pass of a length-N line (N entries): see FftTask<..., PK = true>
+template <int N, int R0> DLPD_DEV cpx packed_head_twiddle(const cpx* tw, int t) {
+    constexpr int M2 = N / (2 * R0);
+    const int j = t / (2 * R0), k = t % (2 * R0);
+    if (k < R0) return tw[j + k * M2];                      // w_N^(j + k M2)
+    if (k < 2 * R0 - 1) return tw[(2 * j * (k - R0 + 1)) % N];  // w_(N/2)^(j k'),  k' = k - R0 + 1
+    return make_float2(0.f, 0.f);
 }
 
 // ONE task of a plain in-place pass (no hooks, no loop, no barrier): lets a caller put a butterfly task and unrelated
@@ -471,9 +498,9 @@ DLPD_DEV void fft_inv_head(cpx* s, const cpx* tw, LineOff off, Out out = Out()) 
 }
 
 // ---- the same helpers for an explicit team (SubTeam / CtaTeam) ------------------------------------------------
-template <int N, int NLINES, int ES, class P = LinePlan<N>, class TM, class LineOff, class In = NoHook>
+template <int N, int NLINES, int ES, class P = LinePlan<N>, bool PK = false, class TM, class LineOff, class In = NoHook>
 DLPD_DEV void team_fwd_head(const TM& tm, cpx* s, const cpx* tw, LineOff off, In in = In()) {
-    fft_pass_team<PASS_DIF_PRUNED, 2, P::R0, NLINES, N, N, N, ES>(tm, s, tw, off, in);
+    fft_pass_team<PASS_DIF_PRUNED, 2, P::R0, NLINES, N, N, N, ES, PK>(tm, s, tw, off, in);
 }
 template <int N, int NLINES, int ES, class P = LinePlan<N>, class TM, class LineOff>
 DLPD_DEV void team_fwd_tail(const TM& tm, cpx* s, const cpx* tw, LineOff off) {
@@ -488,7 +515,7 @@ DLPD_DEV void team_inv_tail(const TM& tm, cpx* s, const cpx* tw, LineOff off, In
     if constexpr (P::TAIL > 1 || !std::is_same<In, NoHook>::value)
         fft_pass_team<PASS_DIT, P::TA, P::TB, NLINES, N, P::TAIL, N, ES>(tm, s, tw, off, in);
 }
-template <int N, int NLINES, int ES, class P = LinePlan<N>, class TM, class LineOff, class Out = NoHook>
+template <int N, int NLINES, int ES, class P = LinePlan<N>, bool PK = false, class TM, class LineOff, class Out = NoHook>
 DLPD_DEV void team_inv_head(const TM& tm, cpx* s, const cpx* tw, LineOff off, Out out = Out()) {
-    fft_pass_team<PASS_DIT, 2, P::R0, NLINES, N, N, N, ES>(tm, s, tw, off, NoHook(), out);
+    fft_pass_team<PASS_DIT, 2, P::R0, NLINES, N, N, N, ES, PK>(tm, s, tw, off, NoHook(), out);
 }
