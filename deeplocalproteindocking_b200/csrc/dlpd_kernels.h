@@ -60,6 +60,15 @@
 #ifndef DLPD_PLANE_COLBLOCKS
 #define DLPD_PLANE_COLBLOCKS 1       // inverse-x column ownership that makes the barrier between planes unnecessary
 #endif
+#ifndef DLPD_EPI_PACKED_TW
+#define DLPD_EPI_PACKED_TW 0          // the same for the epilogue's inverse head pass (classic kernel) -- prepared, not measured yet
+#endif
+#ifndef DLPD_FWDZ_PACKED_TW
+#define DLPD_FWDZ_PACKED_TW 0         // ... FwdZC's forward head pass
+#endif
+#ifndef DLPD_HID_PACKED_TW
+#define DLPD_HID_PACKED_TW 0          // ... HiddenL1's inverse head pass
+#endif
 #ifndef DLPD_PLANE_PACKED_TW
 #define DLPD_PLANE_PACKED_TW 1        // head-pass twiddles from a packed table with 16-byte loads (5.11 -> 5.04 ms)
 #endif
@@ -366,7 +375,8 @@ template <int L_, int CG_, int YT_> struct FwdZC {
     static constexpr int L = L_, N = 2 * L_, CG = CG_, YT = YT_, YTILES = L_ / YT_, CQ = CG_ / 4;
     static constexpr int CS = N * YT + 8;          // per-channel stride: +8 keeps 4 channel groups of a warp on distinct banks
     static constexpr int NT = (L_ >= 80 && YT_ >= 8) ? 2 * DLPD_FWDZC_NT : DLPD_FWDZC_NT;   // 512 at L = 80: 1.51 vs 1.62 ms; worse at L = 40
-    static constexpr int SMEM = (CG * CS + N) * (int)sizeof(cpx);
+    static constexpr bool PKT = DLPD_FWDZ_PACKED_TW && (N / (2 * LinePlan<N>::R0) > 1);
+    static constexpr int SMEM = (CG * CS + N + (PKT ? N : 0)) * (int)sizeof(cpx);
     static constexpr int MINB = 1024 / NT;         // resident CTAs the register budget is cut for (64 registers per thread)
     static_assert(L_ % YT_ == 0 && CG_ % 4 == 0, "tile shape");
     struct Lines {
@@ -385,6 +395,12 @@ template <int L_, int CG_, int YT_> struct FwdZC {
             rb[i] = hasB ? p.R[9 * rotB + i] : 0.0f;
         }
         DLPD_FOR_TASKS(t, N, NT) tw[t] = p.tw[t];
+        const cpx* htw = tw;
+        if constexpr (PKT) {
+            cpx* pk = tw + N;
+            DLPD_FOR_TASKS(t, N, NT) pk[t] = packed_head_twiddle<N, LinePlan<N>::R0>(p.tw, t);
+            htw = pk;
+        }
         const float* src = p.src + (long)by * L * L * L * CG;       // this CTA's channel group
         DLPD_FOR_TASKS(t, CQ * YT * L, NT) {
             const int cq = t % CQ, yl = (t / CQ) % YT, z = t / (CQ * YT), y = y0 + yl;
@@ -404,7 +420,7 @@ template <int L_, int CG_, int YT_> struct FwdZC {
         }
         DLPD_SYNC();
         const CtaTeam<NT, true> tm;
-        team_fwd_head<N, CG * YT, YT>(tm, buf, tw, Lines());
+        team_fwd_head<N, CG * YT, YT, LinePlan<N>, PKT>(tm, buf, htw, Lines());
         team_fwd_tail<N, CG * YT, YT>(tm, buf, tw, Lines());
         cpx* out = p.out + ((((long)pair * p.Ctot + c0) * N) * L + x) * L + y0;
         DLPD_FOR_TASKS(t, CG * N * YT, NT) {
@@ -1104,7 +1120,8 @@ template <int L_, int C0, int C1, int H> struct HiddenL1 {
     static constexpr int JG = (H % 8 == 0) ? 8 : H;          // hidden units per task
     static constexpr int VP = (YT * N1 + 31) / 32 * 32;      // (yl, z1) padded to whole warps (warp-uniform hidden group)
     static constexpr int NT = (N1 >= 64) ? DLPD_HID_NT : 128;
-    static constexpr int SMEM = (N1 * P1 + N1) * (int)sizeof(cpx);
+    static constexpr bool PKT = DLPD_HID_PACKED_TW && (N1 / (2 * LinePlan<N1>::R0) > 1);
+    static constexpr int SMEM = (N1 * P1 + N1 + (PKT ? N1 : 0)) * (int)sizeof(cpx);
     static_assert(N1 % YT == 0, "level-1 y tile");
     struct LoadS2 {          // element e = kz' of line l = c*YT + yl
         const cpx* s;
@@ -1116,6 +1133,12 @@ template <int L_, int C0, int C1, int H> struct HiddenL1 {
         cpx* tw1 = b1 + N1 * P1;
         const int y0 = YT * bx, x1 = by, pair = bz;
         DLPD_FOR_TASKS(t, N1, NT) tw1[t] = p.tw1[t];
+        const cpx* htw1 = tw1;
+        if constexpr (PKT) {
+            cpx* pk = tw1 + N1;
+            DLPD_FOR_TASKS(t, N1, NT) pk[t] = packed_head_twiddle<N1, LinePlan<N1>::R0>(p.tw1, t);
+            htw1 = pk;
+        }
         const CtaTeam<NT, true> tm;
 #if DLPD_HID_DIRECT
         {
@@ -1160,7 +1183,7 @@ template <int L_, int C0, int C1, int H> struct HiddenL1 {
         DLPD_SYNC();
         team_inv_tail<N1, NL, P1>(tm, b1, tw1, LineMul<1>());
 #endif
-        team_inv_head<N1, NL, P1>(tm, b1, tw1, LineMul<1>());
+        team_inv_head<N1, NL, P1, LinePlan<N1>, PKT>(tm, b1, htw1, LineMul<1>());
         cpx* h1 = p.h1 + (((long)pair * N1 + x1) * N1 + y0) * N1 * H;
         DLPD_FOR_TASKS(t, (H / JG) * VP, NT) {
             const int v = t % VP, jg = t / VP;
@@ -1219,7 +1242,8 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, bool TC_ = false> struct E
     static constexpr int NPROD = (N >= 128) ? DLPD_EPI_NPROD : 32, NC = NT - NPROD;
     static constexpr int BUF = N * NL0, HB = N1 * H;
     static constexpr int MLP_BYTES = TC_ ? ((int)sizeof(MlpDev<C0, H>) + 15) / 16 * 16 : 0;      // shared-memory copy of the MMA fragments
-    static constexpr int SMEM = (2 * BUF + 2 * HB + N) * (int)sizeof(cpx) + 64 * 8 + MLP_BYTES;
+    static constexpr bool PKT = DLPD_EPI_PACKED_TW && (N / (2 * LinePlan<N>::R0) > 1);      // packed twiddles of the inverse head pass
+    static constexpr int SMEM = (2 * BUF + 2 * HB + N + (PKT ? N : 0)) * (int)sizeof(cpx) + 64 * 8 + MLP_BYTES;
     static constexpr int QPT = NPROD / TY;         // (c, kz) rows covered per sweep of the producer threads
     static constexpr int TILES = T * TPR;          // tiles per pair
     static_assert(HB % 2 == 0 && NPROD % 32 == 0 && NC % 32 == 0 && (TY_ == 1 || TY_ == 2), "team shapes");
@@ -1280,7 +1304,8 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, bool TC_ = false> struct E
     template <class TM>
     static DLPD_DEV void score_tile(const Params& p, const TM& tm, cpx* b0, const cpx* h1, const cpx* tw0, const MlpDev<C0, H>* ms,
                                     int pair, int x0, int y0, unsigned long long& bestA, unsigned long long& bestB) {
-        transform_tile(tm, b0, tw0);
+        if constexpr (PKT) transform_tile_pk(tm, b0, tw0, tw0 + N);
+        else transform_tile(tm, b0, tw0);
 #if !defined(DLPD_EMU)
         if constexpr (MMA_OK) {
             if (p.mlp != nullptr) {
@@ -1426,6 +1451,13 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, bool TC_ = false> struct E
         team_inv_head<N, NL0, NL0>(tm, b0, tw0, LineMul<1>());
 #endif
     }
+    // the same with the head pass reading its twiddles from the packed table htw (classic kernel, PKT)
+    template <class TM> static DLPD_DEV void transform_tile_pk(const TM& tm, cpx* b0, const cpx* tw0, const cpx* htw) {
+#if !defined(DLPD_ABLATE_EPI_FFT)
+        team_inv_tail<N, NL0, NL0>(tm, b0, tw0, LineMul<1>());
+        team_inv_head<N, NL0, NL0, LinePlan<N>, PKT>(tm, b0, htw, LineMul<1>());
+#endif
+    }
 
     // filter, clash mask and running argmin over the XY * N voxels of a transformed tile
     template <class TM>
@@ -1477,9 +1509,12 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, bool TC_ = false> struct E
         cpx* bufs = reinterpret_cast<cpx*>(smem);      // [2][kz][NL0]
         cpx* hbufs = bufs + 2 * BUF;                   // [2][z'][H]  (rotA, rotB): b1 + level-1 part of the hidden layer
         cpx* tw0 = hbufs + 2 * HB;
-        unsigned long long* red = reinterpret_cast<unsigned long long*>(tw0 + N);
+        unsigned long long* red = reinterpret_cast<unsigned long long*>(tw0 + N + (PKT ? N : 0));
         MlpDev<C0, H>* ms = reinterpret_cast<MlpDev<C0, H>*>(red + 64);
         DLPD_FOR_TASKS(t, N, NT) tw0[t] = p.tw0[t];
+        if constexpr (PKT) {
+            DLPD_FOR_TASKS(t, N, NT) tw0[N + t] = packed_head_twiddle<N, LinePlan<N>::R0>(p.tw0, t);
+        }
         if (MMA_OK && p.mlp != nullptr) {
             DLPD_FOR_TASKS(t, (int)sizeof(MlpDev<C0, H>) / 4, NT)
                 reinterpret_cast<unsigned int*>(ms)[t] = reinterpret_cast<const unsigned int*>(p.mlp)[t];
