@@ -481,21 +481,29 @@ def main():
         if world == 1 and args.torch_gpu_rotations > 0 and cfg["source"] == "atoms":
             eng.close()
             torch.cuda.empty_cache()
-            Rt = Rall[:args.torch_gpu_rotations + 1]
-            cl = clash_volumes(lig_dev, Rt.to(device), device)
-            line["gpu_torch_baseline"] = {
-                "unit": "rotations/s", "kind": "port",
-                "what": "the reference's loop body as plain PyTorch library calls on the same GPU (grid_sample, cuFFT "
-                        "rfftn/irfftn, interpolate, Linear, min): same-GPU comparator, SURVEY.md 8(d)",
-                "receptor_retransformed_each_call": torch_gpu_baseline(rec_vols, rec_clash, lig_vols, cl, Rt, filt,
-                                                                       args.torch_gpu_rotations, False, device),
-                "receptor_spectra_precomputed": torch_gpu_baseline(rec_vols, rec_clash, lig_vols, cl, Rt, filt,
-                                                                   args.torch_gpu_rotations, True, device),
-                "sample": "%d rotations of oim10 after 1 warm-up, one rotation per call" % args.torch_gpu_rotations}
+            try:
+                line["gpu_torch_baseline"] = _torch_gpu_line(args, rec_vols, rec_clash, lig_vols, lig_dev, Rall, filt, device)
+            except Exception as e:                       # a comparator must never cost the bench line
+                line["gpu_torch_baseline"] = {"error": "%s: %s" % (type(e).__name__, e)}
         print(json.dumps(line), flush=True)
     eng.close()
     if world > 1:
         dist.destroy_process_group()
+
+
+def _torch_gpu_line(args, rec_vols, rec_clash, lig_vols, lig_dev, Rall, filt, device):
+    """`gpu_torch_baseline` of the bench line: torch_loop_body timed on the same GPU, receptor re-transformed per call
+    (faithful to VolumeConvolution) and with precomputed receptor spectra."""
+    Rt = Rall[:args.torch_gpu_rotations + 1]
+    cl = clash_volumes(lig_dev, Rt.to(device), device)
+    n = args.torch_gpu_rotations
+    return {
+        "unit": "rotations/s", "kind": "port",
+        "what": "the reference's loop body as plain PyTorch library calls on the same GPU (grid_sample, cuFFT "
+                "rfftn/irfftn, interpolate, Linear, min): same-GPU comparator, SURVEY.md 8(d)",
+        "receptor_retransformed_each_call": torch_gpu_baseline(rec_vols, rec_clash, lig_vols, cl, Rt, filt, n, False, device),
+        "receptor_spectra_precomputed": torch_gpu_baseline(rec_vols, rec_clash, lig_vols, cl, Rt, filt, n, True, device),
+        "sample": "%d rotations of oim10 after 1 warm-up, one rotation per call" % n}
 
 
 if __name__ == "__main__":
