@@ -125,3 +125,82 @@ def test_bench_torch_loop_body_matches_oracle():
         N = 2 * L
         assert int(idx) == (x * N + y) * N + z
         assert abs(float(best) - s) <= 1e-4 * max(abs(s), 1e-3 * float(V.abs().max()))
+
+
+def test_tpl_module_surface_is_import_compatible(tmp_path):
+    """deeplocalproteindocking_b200.tpl.install() makes the reference's own import lines resolve (Docker.py:8-10,
+    VolumeViz.py:10) and the FullAtomModel stand-ins follow the call-site conventions (r' = R r, real atoms only)."""
+    import importlib
+    import sys
+    from deeplocalproteindocking_b200 import tpl
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "_Volume" or k.startswith("TorchProteinLibrary")}
+    try:
+        tpl.install()
+        from TorchProteinLibrary.FullAtomModel import CoordsTransform                                  # Docker.py:8
+        from TorchProteinLibrary.Volume import TypedCoords2Volume, VolumeConvolution, VolumeRotation    # Docker.py:9
+        from TorchProteinLibrary.FullAtomModel import (PDB2CoordsUnordered, Coords2TypedCoords, CoordsTranslate,   # Docker.py:10
+                                                       getBBox, getRandomRotation)
+        import _Volume                                                                                   # VolumeViz.py:10
+        assert VolumeRotation is importlib.import_module("deeplocalproteindocking_b200").VolumeRotation
+        assert VolumeConvolution(clip=5.0) is not None and TypedCoords2Volume(8, 1.0) is not None
+        g = torch.Generator().manual_seed(3)
+        coords = torch.zeros(2, 3 * 5, dtype=torch.float64)
+        coords[0, :12] = torch.randn(12, generator=g, dtype=torch.float64)      # 4 real atoms + 1 padding atom
+        coords[1, :9] = torch.randn(9, generator=g, dtype=torch.float64)        # 3 real atoms + 2 padding atoms
+        nat = torch.tensor([4, 3], dtype=torch.int32)
+        R = getRandomRotation(2)
+        assert R.dtype == torch.float64 and torch.allclose(R @ R.transpose(1, 2), torch.eye(3, dtype=torch.float64).expand(2, 3, 3), atol=1e-12)
+        assert torch.allclose(torch.linalg.det(R), torch.ones(2, dtype=torch.float64))
+        rot = CoordsTransform.CoordsRotate()(coords, R, nat)
+        assert torch.allclose(rot[0, :3], R[0] @ coords[0, :3]) and torch.equal(rot[0, 12:], coords[0, 12:])
+        T = torch.tensor([[1.0, 2.0, 3.0], [-1.0, 0.5, 0.0]], dtype=torch.float64)
+        tr = CoordsTranslate()(coords, T, nat)
+        assert torch.allclose(tr[1, 3:6], coords[1, 3:6] + T[1]) and torch.equal(tr[1, 9:], coords[1, 9:])     # padding untouched
+        a, b = getBBox(coords, nat)
+        xyz0 = coords[0, :12].reshape(4, 3)
+        assert torch.equal(a[0], xyz0.min(0).values) and torch.equal(b[0], xyz0.max(0).values)
+        with pytest.raises(NotImplementedError):
+            PDB2CoordsUnordered()(["x.pdb"])
+        with pytest.raises(NotImplementedError):
+            Coords2TypedCoords()(coords, None, None, nat)
+        out = tmp_path / "v.xplor"
+        _Volume.Volume2Xplor(torch.arange(27, dtype=torch.float32).reshape(3, 3, 3), str(out), 1.25)
+        text = out.read_text().splitlines()
+        assert "ZYX" in text and text[-2].strip() == "-9999"
+    finally:
+        for k in [k for k in sys.modules if k == "_Volume" or k.startswith("TorchProteinLibrary")]:
+            del sys.modules[k]
+        for k, m in saved.items():
+            if m is not None:
+                sys.modules[k] = m
+
+
+def test_reference_docker_module_imports_against_the_stand_ins(tmp_path):
+    """With tpl.install() the reference's UNMODIFIED src/Docker/Docker.py imports and binds our operators (authoring
+    container only: the reference tree is absent on the GPU box)."""
+    import importlib
+    import sys
+    from oracle import ref_shims
+    if not ref_shims.reference_available():
+        pytest.skip("reference tree not present")
+    from deeplocalproteindocking_b200 import tpl
+    from deeplocalproteindocking_b200.rotations import write_eul, soi_euler_angles
+    (tmp_path / "data").mkdir()
+    write_eul(str(tmp_path / "data" / "oim20.eul"), soi_euler_angles(20))
+    saved = dict(sys.modules)
+    try:
+        ref_shims.install(str(tmp_path))                 # fake `src` package + se3cnn stubs (test infrastructure)
+        tpl.install()                                    # the product's TorchProteinLibrary stand-ins replace the oracle's
+        for k in [k for k in sys.modules if k.startswith("src.Docker") or k.startswith("src.Models")]:
+            del sys.modules[k]
+        mod = importlib.import_module("src.Docker.Docker")
+        assert mod.VolumeRotation.__module__ == "deeplocalproteindocking_b200.volume"
+        assert mod.VolumeConvolution.__module__ == "deeplocalproteindocking_b200.volume"
+        assert mod.getBBox.__module__ == "deeplocalproteindocking_b200.tpl"
+        assert mod.CoordsTransform.CoordsRotate.__module__ == "deeplocalproteindocking_b200.tpl"
+        models = importlib.import_module("src.Models.DockingModels")
+        assert models.VolumeConvolution.__module__ == "deeplocalproteindocking_b200.volume"
+    finally:
+        for k in [k for k in sys.modules if k not in saved]:
+            del sys.modules[k]
+        sys.modules.update(saved)
