@@ -5,7 +5,7 @@ from .search import DockingSearch  # noqa: F401
 from .volume import VolumeRotation, VolumeConvolution, TypedCoords2Volume  # noqa: F401
 from .models import SimpleFilter, GlobalDockingModel, E3MultiResRepr4x4  # noqa: F401
 from .docker import Docker, Atoms  # noqa: F401
-from . import rotations, synthetic, distributed, tpl  # noqa: F401
+from . import rotations, synthetic, distributed, tpl, poses  # noqa: F401
 from ._lib import set_option  # noqa: F401
 
 __all__ = ["Rotations", "DockingSearch", "VolumeRotation", "VolumeConvolution", "TypedCoords2Volume", "SimpleFilter",

@@ -204,3 +204,32 @@ def test_reference_docker_module_imports_against_the_stand_ins(tmp_path):
         for k in [k for k in sys.modules if k not in saved]:
             del sys.modules[k]
         sys.modules.update(saved)
+
+
+def test_pose_file_round_trip_and_application(tmp_path):
+    """Docker.write_conformations -> poses.parse_output gives back rotation, translation and score of every pose; the
+    reference reader's int() truncation is available behind a flag; transform_ligand = rotate then translate."""
+    from deeplocalproteindocking_b200 import Docker, poses
+    dk = Docker(docking_model=None, angle_inc=20, box_size=80, resolution=1.25, max_conf=5, device="cpu")
+    dk.top_list = [(7, 3, 157, 80, -2.5), (1853, 0, 79, 159, -1.25), (100, 81, 1, 2, 0.0)]
+    path = str(tmp_path / "target.dat")
+    assert dk.new_log(path, rewrite=True)
+    dk.write_conformations()
+    dk.cleanup()
+    got = poses.parse_output(path)
+    assert poses.parse_output(str(tmp_path / "missing.dat")) is None
+    assert len(got) == 3
+    for entry, (R, t, score) in zip(dk.top_list, got):
+        r_want, t_want, s_want = dk.conformation(entry)
+        assert torch.allclose(R[0], r_want, atol=1e-6) and torch.allclose(t[0], t_want, atol=1e-6) and abs(score - s_want) < 1e-6
+    # circular index -> signed shift times the resolution (Docker.py:112-122)
+    assert torch.allclose(got[0][1][0], torch.tensor([3 * 1.25, -3 * 1.25, -80 * 1.25], dtype=torch.float64))
+    trunc = poses.parse_output(path, truncate_translation=True)
+    assert torch.equal(trunc[0][1][0], torch.tensor([3.0, -3.0, -100.0], dtype=torch.float64))          # int(3.75), int(-3.75), int(-100.0)
+    coords = torch.tensor([[1.0, 0.0, 0.0, 0.0, 2.0, 0.0, 9.0, 9.0, 9.0]], dtype=torch.float64)          # 2 real atoms + padding
+    nat = torch.tensor([2], dtype=torch.int32)
+    centred = poses.centre_on_bbox(coords, nat)
+    assert torch.allclose(centred[0, :6], torch.tensor([0.5, -1.0, 0.0, -0.5, 1.0, 0.0], dtype=torch.float64))
+    out = poses.transform_ligand(centred, nat, got[1])
+    R, t, _ = got[1]
+    assert torch.allclose(out[0, :3], R[0] @ centred[0, :3] + t[0]) and torch.equal(out[0, 6:], coords[0, 6:])
