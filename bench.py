@@ -299,7 +299,7 @@ def main():
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config (1-based); 2 is the bench line")
     ap.add_argument("--plane-mode", default="auto", choices=["auto", "single", "cluster"], help="plane-stage kernel (tuning)")
     ap.add_argument("--epilogue-kind", default="auto", choices=["auto", "classic", "pipelined", "duo", "fused"], help="epilogue kernel (tuning)")
-    ap.add_argument("--filter-kind", default="auto", choices=["auto", "fp32", "tensor"], help="first filter layer: FFMA chain or fp16-split mma.sync (tuning)")
+    ap.add_argument("--filter-kind", default="auto", choices=["auto", "fp32", "tensor", "tcgen05"], help="first filter layer: FFMA chain or fp16-split mma.sync (tuning)")
     ap.add_argument("--epilogue-tile", type=int, default=0, choices=[0, 1, 2], help="epilogue tile shape (tuning)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

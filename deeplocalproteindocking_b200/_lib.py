@@ -30,6 +30,15 @@ SIGNATURES = {
                                        c_void_p, c_void_p]),
     "dlpd_search_prerotated": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
     "dlpd_search_host": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
+    "dlpd_set_ligand_atoms": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p]),
+    "dlpd_search_atoms": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p, c_void_p]),
+    "dlpd_search_candidates_atoms": (c_int, [c_void_p, c_void_p, c_int, c_float, c_float, c_void_p, c_void_p, c_int, c_void_p,
+                                             c_void_p]),
+    "dlpd_search_host_atoms": (c_int, [c_void_p, c_void_p, c_int, c_float, c_void_p, c_void_p]),
+    "dlpd_project_typed": (c_int, [c_void_p, c_void_p, c_void_p, c_int, c_int, c_int, c_int, c_float, c_void_p, c_void_p]),
+    "dlpd_plan_set_option": (c_int, [c_void_p, c_int, c_int]),
+    "dlpd_build_flags": (c_int, []),
+    "dlpd_release_workspace": (c_int, []),
     "dlpd_profile_enable": (c_int, [c_void_p, c_int]),
     "dlpd_profile_read": (c_int, [c_void_p, POINTER(ctypes.c_double), POINTER(c_int), c_void_p]),
     "dlpd_launch_count": (c_longlong, []),
@@ -43,7 +52,8 @@ CENTER_MODES = {"box": 0, "grid": 1}
 OPTIONS = {"plane_mode": 1, "epilogue_tile": 2, "epilogue_kind": 3, "filter_kind": 4}      # DLPD_OPT_* of include/dlpd.h
 EPILOGUE_KINDS = {"auto": 0, "classic": 1, "pipelined": 2, "duo": 3, "fused": 4}
 PLANE_MODES = {"auto": 0, "single": 1, "cluster": 2}
-FILTER_KINDS = {"auto": 0, "fp32": 1, "tensor": 2}
+FILTER_KINDS = {"auto": 0, "fp32": 1, "tensor": 2, "tcgen05": 3}
+BUILD_EXPERIMENTAL, BUILD_EMULATION = 1, 2
 
 
 class DlpdError(RuntimeError):
@@ -80,15 +90,25 @@ def get_lib() -> ctypes.CDLL:
     return _lib
 
 
-def set_option(name: str, value) -> None:
-    """Process-wide kernel selection switches (`dlpd_set_option`): plane_mode = auto | single | cluster,
-    epilogue_tile = 0 (auto) | 1 | 2, epilogue_kind = auto | classic | pipelined | duo | fused, filter_kind = auto | fp32 | tensor
-    (first filter layer as packed FFMA or as fp16-split mma.sync).  Tuning and tests only; the defaults are what ships."""
-    lib = get_lib()
+def option_value(name: str, value) -> int:
     if name == "plane_mode" and isinstance(value, str):
         value = PLANE_MODES[value]
     if name == "epilogue_kind" and isinstance(value, str):
         value = EPILOGUE_KINDS[value]
     if name == "filter_kind" and isinstance(value, str):
         value = FILTER_KINDS[value]
-    check(lib, lib.dlpd_set_option(OPTIONS[name], int(value)))
+    return int(value)
+
+
+def set_option(name: str, value) -> None:
+    """DEFAULT kernel-selection options that plans created afterwards start from (`dlpd_set_option`; a live plan is changed
+    with `DockingSearch.set_option`): plane_mode = auto | single | cluster, epilogue_tile = 0 (auto) | 1 | 2,
+    epilogue_kind = auto | classic (| pipelined | duo | fused in DLPD_EXPERIMENTAL builds), filter_kind = auto | fp32 | tcgen05
+    (| tensor in experimental builds).  Tuning and tests only; the defaults are what ships."""
+    lib = get_lib()
+    check(lib, lib.dlpd_set_option(OPTIONS[name], option_value(name, value)))
+
+
+def has_experimental() -> bool:
+    """True if this libdlpd.so was built with -DDLPD_EXPERIMENTAL=1 (rejected epilogue variants, mma.sync filter)."""
+    return bool(get_lib().dlpd_build_flags() & BUILD_EXPERIMENTAL)

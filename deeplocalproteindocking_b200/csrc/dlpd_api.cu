@@ -9,7 +9,9 @@
 
 #include <stdio.h>
 #include <stdlib.h>
+#include <atomic>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -21,7 +23,7 @@
 // runtime shim
 // ------------------------------------------------------------------------------------------------------
 static thread_local std::string g_err;
-static long long g_launches = 0;     // kernels launched by this library (bench.py reports it as gpu_launches)
+static std::atomic<long long> g_launches{0};     // kernels launched by this library (bench.py reports it as gpu_launches)
 static int fail(int code, const std::string& msg) {
     g_err = msg;
     return code;
@@ -269,12 +271,19 @@ static constexpr int SMEM_MAX = 227 * 1024;
 #ifndef DLPD_PLANE_WAVES
 #define DLPD_PLANE_WAVES 1      // look-ahead distance of Plane's S1 prefetch in grid waves
 #endif
-static int g_plane_mode = DLPD_PLANE_AUTO;
-static int g_epi_tile = 0;               // 0 = automatic, 1 / 2 = force 2x1 / 2x2 tiles in the epilogue
-static int g_epi_kind = DLPD_EPILOGUE_AUTO;
-static int g_filter_kind = DLPD_FILTER_AUTO;
-#ifndef DLPD_FILTER_DEFAULT_TENSOR
-#define DLPD_FILTER_DEFAULT_TENSOR 0      // measured on B200: 4.40 ms vs 3.74 ms for the FFMA chain
+// Kernel-selection options.  A plan carries its own copy (dlpd_plan_set_option), initialised from the process-wide defaults
+// below at dlpd_plan_create; dlpd_set_option changes the defaults (plans created afterwards, and the plan-less standalone
+// operators).  Nothing a running plan depends on lives in a global.
+struct Options {
+    int plane_mode = DLPD_PLANE_AUTO;
+    int epi_tile = 0;                    // 0 = automatic, 1 / 2 = force 2x1 / 2x2 tiles in the epilogue
+    int epi_kind = DLPD_EPILOGUE_AUTO;
+    int filter_kind = DLPD_FILTER_AUTO;
+};
+static Options g_defaults;
+static std::mutex g_mutex;               // guards g_defaults and the standalone operators' workspaces
+#ifndef DLPD_FILTER_DEFAULT
+#define DLPD_FILTER_DEFAULT DLPD_FILTER_TCGEN05      // what DLPD_FILTER_AUTO means where the tcgen05 kernel exists (else FP32)
 #endif
 #ifndef DLPD_EPILOGUE_DEFAULT_DUO
 #define DLPD_EPILOGUE_DEFAULT_DUO 0
@@ -295,10 +304,15 @@ template <int L> struct HasPlaneX { static constexpr bool value = (L == 8 || L =
 #endif
 template <int L> struct PlaneXCL { static constexpr int value = (L == 128) ? DLPD_PLANEX_CL_BIG : ((L == 16) ? DLPD_PLANEX_CL_16 : 4); };
 template <int L> struct HasPlane { static constexpr bool value = ((2 * L) * (2 * L + 1) + 2 * L) * 8 <= SMEM_MAX; };
-template <int L> static int launch_plane_t(const PlaneParams& p, dlpd_stream_t st) {
+// which plane kernel `mode` selects at box size L (the receptor spectra are laid out for it)
+template <int L> static bool plane_is_cluster_t(int mode) {
     bool cluster = !HasPlane<L>::value;
-    if (g_plane_mode == DLPD_PLANE_CLUSTER && HasPlaneX<L>::value) cluster = true;
-    if (g_plane_mode == DLPD_PLANE_SINGLE) cluster = false;
+    if (mode == DLPD_PLANE_CLUSTER && HasPlaneX<L>::value) cluster = true;
+    if (mode == DLPD_PLANE_SINGLE) cluster = false;
+    return cluster;
+}
+template <int L> static int launch_plane_t(const PlaneParams& p, int mode, dlpd_stream_t st) {
+    const bool cluster = plane_is_cluster_t<L>(mode);
     if (cluster) {
         if constexpr (HasPlaneX<L>::value) return launch_cluster<PlaneX<L, PlaneXCL<L>::value> >((unsigned)(p.P * 2 * L * p.C), p, st);
         else return fail(DLPD_EINVAL, "the cluster plane kernel is not compiled for this box size");
@@ -347,13 +361,21 @@ static int cl_group(int L) {
     }
     return 8;
 }     // multiple of every Tile<L>::CL_CG in use
-static int launch_plane(int L, const PlaneParams& p, dlpd_stream_t st) {
+static int launch_plane(int L, const PlaneParams& p, int mode, dlpd_stream_t st) {
     switch (L) {
-#define X(L_) case L_: return launch_plane_t<L_>(p, st);
+#define X(L_) case L_: return launch_plane_t<L_>(p, mode, st);
         DLPD_OP_SIZES(X)
 #undef X
     }
     return fail(DLPD_EINVAL, "unsupported box size");
+}
+static int plane_is_cluster(int L, int mode) {
+    switch (L) {
+#define X(L_) case L_: return plane_is_cluster_t<L_>(mode) ? 1 : 0;
+        DLPD_OP_SIZES(X)
+#undef X
+    }
+    return 0;
 }
 static int launch_invz(int L, const InvZParams& p, int Q, dlpd_stream_t st) {
     switch (L) {
@@ -386,6 +408,15 @@ struct dlpd_plan {
     std::vector<float> W1, b1, W2;
     float b2;
     bool has_receptor, has_ligand, lig_has_clash, has_filter;
+    Options opt;                 // kernel selection of THIS plan
+    int rspec_cluster[2];        // plane kernel the receptor spectra of level 0 / 1 were laid out for (-1: none yet)
+    // ligand atoms for the in-loop clash re-projection inside the library (dlpd_set_ligand_atoms)
+    double* atoms;               // [nat][3] bbox-centred coordinates
+    int nat;
+    float resolution;
+    float* clash_rot;            // [max_rot][L^3] re-projected clash volumes of the current chunk
+    float* R32;                  // [max_rot][9] fp32 copies of the chunk's rotation matrices
+    double* dev_R64;             // staging of dlpd_search_host_atoms
     long long bytes;
     // optional per-kernel timing with CUDA events on the launching stream (dlpd_profile_*)
     bool profile;
@@ -448,7 +479,12 @@ extern "C" long long dlpd_plan_bytes(const dlpd_plan* p) { return p ? p->bytes :
 
 extern "C" int dlpd_plan_destroy(dlpd_plan* p) {
     if (!p) return 0;
+    int prev_dev = -1;
+#if !defined(DLPD_EMU)
+    if (cudaGetDevice(&prev_dev) != cudaSuccess) prev_dev = -1;
+#endif
     rt_set_device(p->device);
+    rt_free(p->atoms); rt_free(p->clash_rot); rt_free(p->R32); rt_free(p->dev_R64);
     rt_free(p->tw0); rt_free(p->tw1); rt_free(p->tw2);
     rt_free(p->lig0); rt_free(p->lig1); rt_free(p->lig0_cl); rt_free(p->lig1_cl); rt_free(p->rspec0); rt_free(p->rspec1);
     rt_free(p->s1_0); rt_free(p->s1_1); rt_free(p->s2_0); rt_free(p->s2_1); rt_free(p->h1);
@@ -460,6 +496,7 @@ extern "C" int dlpd_plan_destroy(dlpd_plan* p) {
     for (auto& e : p->pool) cudaEventDestroy(e);
 #endif
     delete p;
+    if (prev_dev >= 0) rt_set_device(prev_dev);     // leave the caller's current device as it was
     return 0;
 }
 
@@ -484,6 +521,12 @@ extern "C" int dlpd_plan_create(dlpd_plan** out, int L, int C0, int C1, int H, i
     p->sm_count = rt_sm_count(device);
     p->pin_R = p->pin_best = p->dev_R = p->dev_best = nullptr; p->host_cap = 0;
     p->has_receptor = p->has_ligand = p->lig_has_clash = p->has_filter = false;
+    {
+        std::lock_guard<std::mutex> lk(g_mutex);
+        p->opt = g_defaults;
+    }
+    p->rspec_cluster[0] = p->rspec_cluster[1] = -1;
+    p->atoms = nullptr; p->nat = 0; p->resolution = 0.f; p->clash_rot = nullptr; p->R32 = nullptr; p->dev_R64 = nullptr;
     p->b2 = 0.f;
     p->profile = false;
     for (int i = 0; i < DLPD_PROFILE_KINDS; ++i) { p->prof_ms[i] = 0.0; p->prof_n[i] = 0; }
@@ -505,6 +548,7 @@ extern "C" int dlpd_plan_create(dlpd_plan** out, int L, int C0, int C1, int H, i
         {(void**)&p->rec_ss, sizeof(float) * C0},
         {(void**)&p->lig_ss, sizeof(float) * C0},
         {(void**)&p->mlp, 8192},
+        {(void**)&p->R32, sizeof(float) * 9 * (size_t)max_rot},
     };
     p->bytes = 0;
     for (auto& a : allocs) {
@@ -521,7 +565,7 @@ extern "C" int dlpd_plan_create(dlpd_plan** out, int L, int C0, int C1, int H, i
 }
 
 // forward transform of `C` real volumes (R = nullptr) into spectra: FwdZ (identity) + Plane (spectrum mode)
-static int real_spectra(int L, const float* vols, int C, cpx* s1, cpx* spec, const cpx* tw, dlpd_stream_t st) {
+static int real_spectra(int L, const float* vols, int C, cpx* s1, cpx* spec, const cpx* tw, int plane_mode, dlpd_stream_t st) {
     const int N = 2 * L;
     FwdZParams f;
     f.src = vols; f.src_pair_stride = 0; f.src_rot = nullptr; f.R = nullptr; f.out = s1; f.tw = tw;
@@ -530,13 +574,17 @@ static int real_spectra(int L, const float* vols, int C, cpx* s1, cpx* spec, con
     PlaneParams q;
     q.in = s1; q.out = spec; q.spec = nullptr; q.spec_pair_stride = 0; q.tw = tw; q.C = C; q.P = 1; q.tiled = 0; q.wave = 1 << 30; q.grid = 0;
     q.scale = (float)(1.0 / ((double)N * N * N));
-    TRY(launch_plane(L, q, st));
+    TRY(launch_plane(L, q, plane_mode, st));
     return 0;
 }
 
-static bool filter_tensor_wanted() {
-    return g_filter_kind == DLPD_FILTER_TENSOR || (g_filter_kind == DLPD_FILTER_AUTO && DLPD_FILTER_DEFAULT_TENSOR);
+// how this plan evaluates the first filter layer: FP32 / TENSOR (mma.sync, experimental builds) / TCGEN05
+static int filter_kind_of(const dlpd_plan* p) {
+    const int k = p->opt.filter_kind;
+    return k == DLPD_FILTER_AUTO ? DLPD_FILTER_DEFAULT : k;
 }
+#if DLPD_EXPERIMENTAL
+static bool filter_tensor_wanted(const dlpd_plan* p) { return filter_kind_of(p) == DLPD_FILTER_TENSOR; }
 // squared L2 norm per level-0 feature channel (max over the n volume sets): bounds the correlations for the fp16-split filter
 static int channel_sumsq(const float* vols, int C, int V, int n, float* out, dlpd_stream_t st) {
     TRY(rt_memset(out, 0, sizeof(float) * C, st));
@@ -544,6 +592,7 @@ static int channel_sumsq(const float* vols, int C, int V, int n, float* out, dlp
     q.v = vols; q.out = out; q.C = C; q.V = V;
     return launch<SumSq>(dim3(C, n), q, st);
 }
+#endif
 
 extern "C" int dlpd_set_receptor(dlpd_plan* p, const float* vol0, const float* vol1, const float* clash, void* stream) {
     if (!p || !vol0 || !vol1 || !clash) return fail(DLPD_EINVAL, "dlpd_set_receptor: NULL argument");
@@ -553,9 +602,13 @@ extern "C" int dlpd_set_receptor(dlpd_plan* p, const float* vol0, const float* v
     // stage [C0 feature volumes | clash] contiguously in the (not yet needed) ligand buffer
     TRY(rt_copy(p->lig0, vol0, sizeof(float) * p->C0 * n3(L), D2D, st));
     TRY(rt_copy(p->lig0 + p->C0 * n3(L), clash, sizeof(float) * n3(L), D2D, st));
-    TRY(real_spectra(L, p->lig0, p->C0 + 1, p->s1_0, p->rspec0, p->tw0, st));
+    TRY(real_spectra(L, p->lig0, p->C0 + 1, p->s1_0, p->rspec0, p->tw0, p->opt.plane_mode, st));
+#if DLPD_EXPERIMENTAL
     TRY(channel_sumsq(vol0, p->C0, (int)n3(L), 1, p->rec_ss, st));
-    TRY(real_spectra(L1, vol1, p->C1, p->s1_1, p->rspec1, p->tw1, st));
+#endif
+    TRY(real_spectra(L1, vol1, p->C1, p->s1_1, p->rspec1, p->tw1, p->opt.plane_mode, st));
+    p->rspec_cluster[0] = plane_is_cluster(L, p->opt.plane_mode);
+    p->rspec_cluster[1] = plane_is_cluster(L1, p->opt.plane_mode);
     p->has_receptor = true;
     p->has_ligand = false;      // lig0 was used as staging
     return 0;
@@ -570,7 +623,9 @@ extern "C" int dlpd_set_ligand(dlpd_plan* p, const float* vol0, const float* vol
     if (clash) TRY(rt_copy(p->lig0 + p->C0 * n3(L), clash, sizeof(float) * n3(L), D2D, st));
     else TRY(rt_memset(p->lig0 + p->C0 * n3(L), 0, sizeof(float) * n3(L), st));
     TRY(rt_copy(p->lig1, vol1, sizeof(float) * p->C1 * n3(L1), D2D, st));
+#if DLPD_EXPERIMENTAL
     TRY(channel_sumsq(vol0, p->C0, (int)n3(L), 1, p->lig_ss, st));
+#endif
     ChannelLastParams cl;
     cl.in = p->lig0; cl.out = p->lig0_cl; cl.C = p->C0; cl.V = (int)n3(L); cl.G = cl_group(L);
     TRY(launch<ToChannelLast>(dim3((cl.V + ToChannelLast::VOX_PER_CTA - 1) / ToChannelLast::VOX_PER_CTA), cl, st));
@@ -614,14 +669,8 @@ struct CandArgs {
     unsigned int cap = 0, key = 0;
     int rot_base = 0;
 };
+#if DLPD_EXPERIMENTAL
 // tensor-core filter: on unless switched off, wherever the epilogue kernel has the path (C0 = 16, H % 8 = 0)
-template <int L, int C0, int C1, int H> static bool filter_tensor() {
-#if defined(DLPD_EMU)
-    return false;
-#else
-    return filter_tensor_wanted() && C0 == 16 && H % 8 == 0;
-#endif
-}
 template <int L, int C0, int C1, int H> static int launch_filter_prep(dlpd_plan* p, dlpd_stream_t st) {
 #if !defined(DLPD_EMU)
     if constexpr (C0 == 16 && H % 8 == 0) {
@@ -636,9 +685,10 @@ template <int L, int C0, int C1, int H> static int launch_filter_prep(dlpd_plan*
     (void)p; (void)st;
     return 0;
 }
-template <int L, int C0, int C1, int H, int TY, bool TC = false>
+#endif   // DLPD_EXPERIMENTAL
+template <int L, int C0, int C1, int H, int TY, int FK = 0>
 static int launch_epilogue_t(dlpd_plan* p, int n, int P, float tau, float* out_scores, const CandArgs& ca, dlpd_stream_t st) {
-    typedef Epilogue<L, C0, C1, H, TY, TC> K;
+    typedef Epilogue<L, C0, C1, H, TY, FK> K;
     if constexpr (K::SMEM <= SMEM_MAX) {
         typename K::Params e;
         e.s2_0 = p->s2_0; e.h1 = p->h1; e.best = p->best; e.score_out = out_scores;
@@ -648,15 +698,18 @@ static int launch_epilogue_t(dlpd_plan* p, int n, int P, float tau, float* out_s
         e.grid = e.n_tiles < p->sm_count ? e.n_tiles : p->sm_count;
         fill_filter(p, e.filt);
         e.mlp = nullptr;
+#if DLPD_EXPERIMENTAL
         if constexpr (K::MMA_OK) {
             TRY((launch_filter_prep<L, C0, C1, H>(p, st)));
             e.mlp = (const MlpDev<C0, H>*)p->mlp;
         }
+#endif
         return launch<K>(dim3(e.grid), e, st);
     } else {
         return fail(DLPD_EINVAL, "epilogue tile does not fit shared memory");
     }
 }
+#if DLPD_EXPERIMENTAL
 template <int L, int C0, int C1, int H>
 static int launch_epilogue_pipe(dlpd_plan* p, int n, int P, float tau, float* out_scores, const CandArgs& ca, dlpd_stream_t st) {
     typedef EpiloguePipe<L, C0, C1, H> K;
@@ -712,25 +765,45 @@ static int launch_epilogue_duo(dlpd_plan* p, int n, int P, float tau, float* out
         return fail(DLPD_EINVAL, "two epilogue CTAs per SM do not fit shared memory at this box size");
     }
 }
+#endif   // DLPD_EXPERIMENTAL
 template <int L, int C0, int C1, int H>
 static int launch_epilogue(dlpd_plan* p, int n, int P, float tau, float* out_scores, const CandArgs& ca, dlpd_stream_t st) {
+#if DLPD_EXPERIMENTAL
+    const int ek = p->opt.epi_kind, et = p->opt.epi_tile;
     const bool duo_fits = 2 * (EpilogueDuo<L, C0, C1, H>::SMEM + 1024) <= 228 * 1024;
-    if (g_epi_kind == DLPD_EPILOGUE_DUO || (g_epi_kind == DLPD_EPILOGUE_AUTO && DLPD_EPILOGUE_DEFAULT_DUO && duo_fits && !g_epi_tile))
+    if (ek == DLPD_EPILOGUE_DUO || (ek == DLPD_EPILOGUE_AUTO && DLPD_EPILOGUE_DEFAULT_DUO && duo_fits && !et))
         return launch_epilogue_duo<L, C0, C1, H>(p, n, P, tau, out_scores, ca, st);
     const bool fused_fits = EpilogueFused<L, C0, C1, H>::SMEM <= SMEM_MAX;
-    if (g_epi_kind == DLPD_EPILOGUE_FUSED || (g_epi_kind == DLPD_EPILOGUE_AUTO && DLPD_EPILOGUE_DEFAULT_FUSED && fused_fits && !g_epi_tile))
+    if (ek == DLPD_EPILOGUE_FUSED || (ek == DLPD_EPILOGUE_AUTO && DLPD_EPILOGUE_DEFAULT_FUSED && fused_fits && !et))
         return launch_epilogue_fused<L, C0, C1, H>(p, n, P, tau, out_scores, ca, st);
     const bool pipe_fits = EpiloguePipe<L, C0, C1, H>::SMEM <= SMEM_MAX;
-    if (g_epi_kind == DLPD_EPILOGUE_PIPELINED || (g_epi_kind == DLPD_EPILOGUE_AUTO && DLPD_EPILOGUE_DEFAULT_PIPELINED && pipe_fits && !g_epi_tile))
+    if (ek == DLPD_EPILOGUE_PIPELINED || (ek == DLPD_EPILOGUE_AUTO && DLPD_EPILOGUE_DEFAULT_PIPELINED && pipe_fits && !et))
         return launch_epilogue_pipe<L, C0, C1, H>(p, n, P, tau, out_scores, ca, st);
+#endif
     const bool fits2 = Epilogue<L, C0, C1, H, 2>::SMEM <= SMEM_MAX;
-    const int ty = g_epi_tile ? g_epi_tile : (fits2 ? 2 : 1);
+    const int ty = p->opt.epi_tile ? p->opt.epi_tile : (fits2 ? 2 : 1);
 #if !defined(DLPD_EMU)
-    if constexpr (C0 == 16 && H % 8 == 0) {
-        if (filter_tensor<L, C0, C1, H>())
-            return ty == 2 ? launch_epilogue_t<L, C0, C1, H, 2, true>(p, n, P, tau, out_scores, ca, st)
-                           : launch_epilogue_t<L, C0, C1, H, 1, true>(p, n, P, tau, out_scores, ca, st);
+    // first filter layer on tcgen05 / TMEM wherever the kernel has the path (C0 % 8 == 0, H % 8 == 0, the tile's
+    // warpgroups fit the 512 TMEM columns) unless the plan asks for the FP32 chain
+    const int fk = filter_kind_of(p);
+    if (fk == DLPD_FILTER_TCGEN05) {
+        if (ty == 2) {
+            if constexpr (Epilogue<L, C0, C1, H, 2, 2>::TC_OK && Epilogue<L, C0, C1, H, 2, 2>::SMEM <= SMEM_MAX)
+                return launch_epilogue_t<L, C0, C1, H, 2, 2>(p, n, P, tau, out_scores, ca, st);
+        } else {
+            if constexpr (Epilogue<L, C0, C1, H, 1, 2>::TC_OK && Epilogue<L, C0, C1, H, 1, 2>::SMEM <= SMEM_MAX)
+                return launch_epilogue_t<L, C0, C1, H, 1, 2>(p, n, P, tau, out_scores, ca, st);
+        }
+        if (p->opt.filter_kind == DLPD_FILTER_TCGEN05)
+            return fail(DLPD_EINVAL, "the tcgen05 filter is not available for this configuration (needs C0 % 8 == 0, H % 8 == 0)");
     }
+#if DLPD_EXPERIMENTAL
+    if constexpr (C0 == 16 && H % 8 == 0) {
+        if (fk == DLPD_FILTER_TENSOR)
+            return ty == 2 ? launch_epilogue_t<L, C0, C1, H, 2, 1>(p, n, P, tau, out_scores, ca, st)
+                           : launch_epilogue_t<L, C0, C1, H, 1, 1>(p, n, P, tau, out_scores, ca, st);
+    }
+#endif
 #endif
     return ty == 2 ? launch_epilogue_t<L, C0, C1, H, 2>(p, n, P, tau, out_scores, ca, st)
                    : launch_epilogue_t<L, C0, C1, H, 1>(p, n, P, tau, out_scores, ca, st);
@@ -749,7 +822,9 @@ static int search_chunk(dlpd_plan* p, const float* R, const float* clash_rot, co
         f.src_pair_stride = 0; f.R = R; f.out = p->s1_0; f.tw = p->tw0; f.Ctot = p->C0 + 1; f.n_rot = n; f.ext_all = 0;
         f.center = center_of(L, p->center_mode);
         if (lig0_rot) {
-            if (filter_tensor_wanted()) TRY(channel_sumsq(lig0_rot, p->C0, (int)n3(L), n, p->lig_ss, st));
+#if DLPD_EXPERIMENTAL
+            if (filter_tensor_wanted(p)) TRY(channel_sumsq(lig0_rot, p->C0, (int)n3(L), n, p->lig_ss, st));
+#endif
             f.src = p->lig0; f.src_rot = lig0_rot; f.C = p->C0; f.c_out0 = 0; f.c_ext = -1; f.ext_all = 1;
             TRY(launch_fwdz(L, f, P, st));
             f.ext_all = 0;
@@ -787,9 +862,9 @@ static int search_chunk(dlpd_plan* p, const float* R, const float* clash_rot, co
     PlaneParams q;
     q.in = p->s1_0; q.out = p->s2_0; q.spec = p->rspec0; q.spec_pair_stride = 0; q.tw = p->tw0; q.C = p->C0 + 1; q.P = P;
     q.scale = 1.f; q.tiled = 1; q.wave = DLPD_PLANE_WAVES * p->sm_count; q.grid = 0;
-    { ProfScope ps(p, DLPD_PROFILE_PLANE0, st); TRY(launch_plane(L, q, st)); }
+    { ProfScope ps(p, DLPD_PROFILE_PLANE0, st); TRY(launch_plane(L, q, p->opt.plane_mode, st)); }
     q.in = p->s1_1; q.out = p->s2_1; q.spec = p->rspec1; q.tw = p->tw1; q.C = p->C1; q.tiled = 0; q.wave = 2 * p->sm_count;
-    { ProfScope ps(p, DLPD_PROFILE_PLANE1, st); TRY(launch_plane(L1, q, st)); }
+    { ProfScope ps(p, DLPD_PROFILE_PLANE1, st); TRY(launch_plane(L1, q, p->opt.plane_mode, st)); }
     int rc = DLPD_EINVAL;
     {
         ProfScope ps(p, DLPD_PROFILE_HIDDEN1, st);
@@ -812,14 +887,24 @@ static int search_chunk(dlpd_plan* p, const float* R, const float* clash_rot, co
     return 0;
 }
 
-static int search_all(dlpd_plan* p, const float* R, const float* lig_clash_rot, const float* lig0_rot, const float* lig1_rot,
-                      int n, float tau, float* out_best, float* out_scores, CandArgs ca, void* stream) {
+static int project_clash_launch(const double* coords, const double* R, int nat, int n, int L, float resolution, float* out,
+                                dlpd_stream_t st);
+
+// R64 != nullptr: float64 rotation matrices; the ligand clash volume of every rotation is re-projected from the plan's
+// atoms (dlpd_set_ligand_atoms) chunk by chunk, exactly as Docker.py:221-224 does per rotation
+static int search_all(dlpd_plan* p, const float* R, const double* R64, const float* lig_clash_rot, const float* lig0_rot,
+                      const float* lig1_rot, int n, float tau, float* out_best, float* out_scores, CandArgs ca, void* stream) {
     const bool prerot = lig0_rot != nullptr;
-    if (!p || !out_best || n < 1 || (!prerot && !R)) return fail(DLPD_EINVAL, "dlpd_search: bad argument");
+    if (!p || !out_best || n < 1 || (!prerot && !R && !R64)) return fail(DLPD_EINVAL, "dlpd_search: bad argument");
     if (!p->has_receptor || !p->has_filter || (!prerot && !p->has_ligand))
         return fail(DLPD_ESTATE, "dlpd_search: set_receptor, set_ligand and set_filter must be called first");
-    if (!lig_clash_rot && !p->lig_has_clash)
+    if (R64 && (!p->atoms || !p->clash_rot))
+        return fail(DLPD_ESTATE, "dlpd_search_atoms: dlpd_set_ligand_atoms must be called first");
+    if (!R64 && !lig_clash_rot && !p->lig_has_clash)
         return fail(DLPD_ESTATE, "dlpd_search: no ligand clash volume (pass one to set_ligand or per rotation)");
+    if (plane_is_cluster(p->L, p->opt.plane_mode) != p->rspec_cluster[0] || plane_is_cluster(p->L / 2, p->opt.plane_mode) != p->rspec_cluster[1])
+        return fail(DLPD_ESTATE, "dlpd_search: the plane mode was changed after dlpd_set_receptor -- the receptor spectra are laid "
+                                 "out for the other plane kernel; call dlpd_set_receptor again");
     dlpd_stream_t st = (dlpd_stream_t)stream;
     TRY(rt_set_device(p->device));
     const size_t L3 = n3(p->L), N3 = n3(2 * p->L);
@@ -827,6 +912,15 @@ static int search_all(dlpd_plan* p, const float* R, const float* lig_clash_rot, 
         const int m = n - i0 < p->max_rot ? n - i0 : p->max_rot;
         ca.rot_base = i0;
         const size_t L13 = n3(p->L / 2);
+        if (R64) {
+            CastParams cp;
+            cp.in = R64 + 9 * (size_t)i0; cp.out = p->R32; cp.n = 9 * m;
+            TRY(launch<CastF64F32>(dim3((cp.n + CastF64F32::NT - 1) / CastF64F32::NT), cp, st));
+            TRY(project_clash_launch(p->atoms, R64 + 9 * (size_t)i0, p->nat, m, p->L, p->resolution, p->clash_rot, st));
+            TRY(search_chunk(p, p->R32, p->clash_rot, nullptr, nullptr, m, tau, out_best + 4 * (size_t)i0,
+                             out_scores ? out_scores + N3 * i0 : nullptr, ca, st));
+            continue;
+        }
         TRY(search_chunk(p, R ? R + 9 * (size_t)i0 : nullptr, lig_clash_rot ? lig_clash_rot + L3 * i0 : nullptr,
                          prerot ? lig0_rot + L3 * p->C0 * i0 : nullptr, prerot ? lig1_rot + L13 * p->C1 * i0 : nullptr, m, tau,
                          out_best + 4 * (size_t)i0, out_scores ? out_scores + N3 * i0 : nullptr, ca, st));
@@ -836,40 +930,82 @@ static int search_all(dlpd_plan* p, const float* R, const float* lig_clash_rot, 
 
 extern "C" int dlpd_search(dlpd_plan* p, const float* R, const float* lig_clash_rot, int n, float tau, float* out_best,
                            float* out_scores, void* stream) {
-    return search_all(p, R, lig_clash_rot, nullptr, nullptr, n, tau, out_best, out_scores, CandArgs(), stream);
+    return search_all(p, R, nullptr, lig_clash_rot, nullptr, nullptr, n, tau, out_best, out_scores, CandArgs(), stream);
+}
+
+extern "C" int dlpd_set_ligand_atoms(dlpd_plan* p, const double* coords, int nat, float resolution, void* stream) {
+    if (!p || !coords || nat < 1 || !(resolution > 0.f)) return fail(DLPD_EINVAL, "dlpd_set_ligand_atoms: bad argument");
+    dlpd_stream_t st = (dlpd_stream_t)stream;
+    TRY(rt_set_device(p->device));
+    if (nat > p->nat) {
+        TRY(rt_sync(st));
+        rt_free(p->atoms);
+        p->atoms = nullptr; p->nat = 0;
+        TRY(rt_malloc((void**)&p->atoms, sizeof(double) * 3 * (size_t)nat));
+    }
+    if (!p->clash_rot) {
+        TRY(rt_malloc((void**)&p->clash_rot, sizeof(float) * n3(p->L) * (size_t)p->max_rot));
+        p->bytes += (long long)(sizeof(float) * n3(p->L) * (size_t)p->max_rot);
+    }
+    TRY(rt_copy(p->atoms, coords, sizeof(double) * 3 * (size_t)nat, D2D, st));
+    p->nat = nat;
+    p->resolution = resolution;
+    return 0;
+}
+
+extern "C" int dlpd_search_atoms(dlpd_plan* p, const double* R64, int n, float tau, float* out_best, float* out_scores, void* stream) {
+    if (!R64) return fail(DLPD_EINVAL, "dlpd_search_atoms: NULL rotation matrices");
+    return search_all(p, nullptr, R64, nullptr, nullptr, nullptr, n, tau, out_best, out_scores, CandArgs(), stream);
 }
 
 extern "C" int dlpd_search_prerotated(dlpd_plan* p, const float* lig0_rot, const float* lig1_rot, const float* lig_clash_rot,
                                       int n, float tau, float* out_best, float* out_scores, void* stream) {
     if (!lig0_rot || !lig1_rot || !lig_clash_rot) return fail(DLPD_EINVAL, "dlpd_search_prerotated: NULL volume pointer");
-    return search_all(p, nullptr, lig_clash_rot, lig0_rot, lig1_rot, n, tau, out_best, out_scores, CandArgs(), stream);
+    return search_all(p, nullptr, nullptr, lig_clash_rot, lig0_rot, lig1_rot, n, tau, out_best, out_scores, CandArgs(), stream);
 }
 
-extern "C" int dlpd_search_candidates(dlpd_plan* p, const float* R, const float* lig_clash_rot, int n, float tau,
-                                      float score_max, float* out_best, int* cand, int cand_cap, unsigned int* cand_count,
-                                      void* stream) {
+static int search_candidates_impl(dlpd_plan* p, const float* R, const double* R64, const float* lig_clash_rot, int n, float tau,
+                                  float score_max, float* out_best, int* cand, int cand_cap, unsigned int* cand_count, void* stream) {
     if (!cand || !cand_count || cand_cap < 1) return fail(DLPD_EINVAL, "dlpd_search_candidates: bad candidate buffer");
     if (score_max != score_max) return fail(DLPD_EINVAL, "dlpd_search_candidates: score_max is NaN");
+    if (!p) return fail(DLPD_EINVAL, "dlpd_search_candidates: NULL plan");
+    TRY(rt_set_device(p->device));
     TRY(rt_memset(cand_count, 0, sizeof(unsigned int), (dlpd_stream_t)stream));
     CandArgs ca;
     ca.cand = cand; ca.count = cand_count; ca.cap = (unsigned int)cand_cap; ca.key = score_key(score_max);
-    return search_all(p, R, lig_clash_rot, nullptr, nullptr, n, tau, out_best, nullptr, ca, stream);
+    return search_all(p, R, R64, lig_clash_rot, nullptr, nullptr, n, tau, out_best, nullptr, ca, stream);
+}
+extern "C" int dlpd_search_candidates(dlpd_plan* p, const float* R, const float* lig_clash_rot, int n, float tau,
+                                      float score_max, float* out_best, int* cand, int cand_cap, unsigned int* cand_count,
+                                      void* stream) {
+    return search_candidates_impl(p, R, nullptr, lig_clash_rot, n, tau, score_max, out_best, cand, cand_cap, cand_count, stream);
+}
+extern "C" int dlpd_search_candidates_atoms(dlpd_plan* p, const double* R64, int n, float tau, float score_max, float* out_best,
+                                            int* cand, int cand_cap, unsigned int* cand_count, void* stream) {
+    if (!R64) return fail(DLPD_EINVAL, "dlpd_search_candidates_atoms: NULL rotation matrices");
+    return search_candidates_impl(p, nullptr, R64, nullptr, n, tau, score_max, out_best, cand, cand_cap, cand_count, stream);
+}
+
+// pinned / device staging of the host-buffer entry points, grown on demand
+static int host_staging(dlpd_plan* p, int n) {
+    if (n <= p->host_cap) return 0;
+    rt_free_host(p->pin_R); rt_free_host(p->pin_best); rt_free(p->dev_R); rt_free(p->dev_best); rt_free(p->dev_R64);
+    p->pin_R = p->pin_best = p->dev_R = p->dev_best = nullptr; p->dev_R64 = nullptr;
+    p->host_cap = 0;
+    TRY(rt_malloc_host((void**)&p->pin_R, sizeof(double) * 9 * n));      // holds fp32 or fp64 matrices
+    TRY(rt_malloc_host((void**)&p->pin_best, sizeof(float) * 4 * n));
+    TRY(rt_malloc((void**)&p->dev_R, sizeof(float) * 9 * n));
+    TRY(rt_malloc((void**)&p->dev_R64, sizeof(double) * 9 * n));
+    TRY(rt_malloc((void**)&p->dev_best, sizeof(float) * 4 * n));
+    p->host_cap = n;
+    return 0;
 }
 
 extern "C" int dlpd_search_host(dlpd_plan* p, const float* R_host, int n, float tau, float* best_host, void* stream) {
     if (!p || !R_host || !best_host || n < 1) return fail(DLPD_EINVAL, "dlpd_search_host: bad argument");
     dlpd_stream_t st = (dlpd_stream_t)stream;
     TRY(rt_set_device(p->device));
-    if (n > p->host_cap) {
-        rt_free_host(p->pin_R); rt_free_host(p->pin_best); rt_free(p->dev_R); rt_free(p->dev_best);
-        p->pin_R = p->pin_best = p->dev_R = p->dev_best = nullptr;
-        p->host_cap = 0;
-        TRY(rt_malloc_host((void**)&p->pin_R, sizeof(float) * 9 * n));
-        TRY(rt_malloc_host((void**)&p->pin_best, sizeof(float) * 4 * n));
-        TRY(rt_malloc((void**)&p->dev_R, sizeof(float) * 9 * n));
-        TRY(rt_malloc((void**)&p->dev_best, sizeof(float) * 4 * n));
-        p->host_cap = n;
-    }
+    TRY(host_staging(p, n));
     memcpy(p->pin_R, R_host, sizeof(float) * 9 * n);
     TRY(rt_copy(p->dev_R, p->pin_R, sizeof(float) * 9 * n, H2D, st));
     TRY(dlpd_search(p, p->dev_R, nullptr, n, tau, p->dev_best, nullptr, stream));
@@ -879,28 +1015,74 @@ extern "C" int dlpd_search_host(dlpd_plan* p, const float* R_host, int n, float 
     return 0;
 }
 
-extern "C" long long dlpd_launch_count(void) { return g_launches; }
+extern "C" int dlpd_search_host_atoms(dlpd_plan* p, const double* R_host, int n, float tau, float* best_host, void* stream) {
+    if (!p || !R_host || !best_host || n < 1) return fail(DLPD_EINVAL, "dlpd_search_host_atoms: bad argument");
+    dlpd_stream_t st = (dlpd_stream_t)stream;
+    TRY(rt_set_device(p->device));
+    TRY(host_staging(p, n));
+    memcpy(p->pin_R, R_host, sizeof(double) * 9 * n);
+    TRY(rt_copy(p->dev_R64, p->pin_R, sizeof(double) * 9 * n, H2D, st));
+    TRY(dlpd_search_atoms(p, p->dev_R64, n, tau, p->dev_best, nullptr, stream));
+    TRY(rt_copy(p->pin_best, p->dev_best, sizeof(float) * 4 * n, D2H, st));
+    TRY(rt_sync(st));
+    memcpy(best_host, p->pin_best, sizeof(float) * 4 * n);
+    return 0;
+}
 
-extern "C" int dlpd_set_option(int key, int value) {
+extern "C" long long dlpd_launch_count(void) { return g_launches.load(); }
+
+static int apply_option(Options& o, int key, int value) {
     switch (key) {
         case DLPD_OPT_PLANE_MODE:
             if (value < DLPD_PLANE_AUTO || value > DLPD_PLANE_CLUSTER) return fail(DLPD_EINVAL, "bad plane mode");
-            g_plane_mode = value;
+            o.plane_mode = value;
             return 0;
         case DLPD_OPT_EPILOGUE_KIND:
             if (value < DLPD_EPILOGUE_AUTO || value > DLPD_EPILOGUE_FUSED) return fail(DLPD_EINVAL, "bad epilogue kind");
-            g_epi_kind = value;
+#if !DLPD_EXPERIMENTAL
+            if (value > DLPD_EPILOGUE_CLASSIC)
+                return fail(DLPD_EINVAL, "this epilogue variant is only compiled with -DDLPD_EXPERIMENTAL=1 (see dlpd_build_flags)");
+#endif
+            o.epi_kind = value;
             return 0;
         case DLPD_OPT_EPILOGUE_TILE:
             if (value < 0 || value > 2) return fail(DLPD_EINVAL, "epilogue tile must be 0 (auto), 1 (2x1) or 2 (2x2)");
-            g_epi_tile = value;
+            o.epi_tile = value;
             return 0;
         case DLPD_OPT_FILTER_KIND:
-            if (value < DLPD_FILTER_AUTO || value > DLPD_FILTER_TENSOR) return fail(DLPD_EINVAL, "bad filter kind");
-            g_filter_kind = value;
+            if (value < DLPD_FILTER_AUTO || value > DLPD_FILTER_TCGEN05) return fail(DLPD_EINVAL, "bad filter kind");
+#if !DLPD_EXPERIMENTAL
+            if (value == DLPD_FILTER_TENSOR)
+                return fail(DLPD_EINVAL, "the mma.sync filter is only compiled with -DDLPD_EXPERIMENTAL=1 (see dlpd_build_flags)");
+#endif
+#if defined(DLPD_EMU)
+            if (value == DLPD_FILTER_TCGEN05) return fail(DLPD_EINVAL, "the tcgen05 filter needs the device");
+#endif
+            o.filter_kind = value;
             return 0;
     }
     return fail(DLPD_EINVAL, "unknown option");
+}
+
+extern "C" int dlpd_set_option(int key, int value) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    return apply_option(g_defaults, key, value);
+}
+
+extern "C" int dlpd_plan_set_option(dlpd_plan* p, int key, int value) {
+    if (!p) return fail(DLPD_EINVAL, "dlpd_plan_set_option: NULL plan");
+    return apply_option(p->opt, key, value);
+}
+
+extern "C" int dlpd_build_flags(void) {
+    int f = 0;
+#if DLPD_EXPERIMENTAL
+    f |= DLPD_BUILD_EXPERIMENTAL;
+#endif
+#if defined(DLPD_EMU)
+    f |= DLPD_BUILD_EMULATION;
+#endif
+    return f;
 }
 
 extern "C" int dlpd_profile_enable(dlpd_plan* p, int on) {
@@ -933,11 +1115,8 @@ extern "C" int dlpd_volume_rotate(const float* vol, const float* R, float* out, 
     return launch<RotateVolume>(dim3(gx, C, B), p, (dlpd_stream_t)stream);
 }
 
-extern "C" int dlpd_project_clash(const double* coords, const double* R, int nat, int n, int L, float resolution, float* out,
-                                  void* stream) {
-    if (!coords || !R || !out || nat < 1 || n < 1 || L < 1 || !(resolution > 0.f))
-        return fail(DLPD_EINVAL, "dlpd_project_clash: bad argument");
-    dlpd_stream_t st = (dlpd_stream_t)stream;
+static int project_clash_launch(const double* coords, const double* R, int nat, int n, int L, float resolution, float* out,
+                                dlpd_stream_t st) {
     TRY(rt_memset(out, 0, sizeof(float) * n3(L) * (size_t)n, st));
     ProjectParams p;
     p.coords = coords; p.R = R; p.out = out; p.nat = nat; p.n = n; p.L = L; p.res = resolution;
@@ -945,11 +1124,48 @@ extern "C" int dlpd_project_clash(const double* coords, const double* R, int nat
     return launch<ProjectClash>(dim3((nat + ProjectClash::NT - 1) / ProjectClash::NT, n), p, st);
 }
 
+extern "C" int dlpd_project_clash(const double* coords, const double* R, int nat, int n, int L, float resolution, float* out,
+                                  void* stream) {
+    if (!coords || !R || !out || nat < 1 || n < 1 || L < 1 || !(resolution > 0.f))
+        return fail(DLPD_EINVAL, "dlpd_project_clash: bad argument");
+    return project_clash_launch(coords, R, nat, n, L, resolution, out, (dlpd_stream_t)stream);
+}
+
+extern "C" int dlpd_project_typed(const float* coords, const int* num_atoms_of_type, const int* offsets, int B, int T, int nmax,
+                                  int L, float resolution, float* out, void* stream) {
+    if (!coords || !num_atoms_of_type || !offsets || !out || B < 1 || T < 1 || nmax < 1 || L < 1 || !(resolution > 0.f))
+        return fail(DLPD_EINVAL, "dlpd_project_typed: bad argument");
+    dlpd_stream_t st = (dlpd_stream_t)stream;
+    TRY(rt_memset(out, 0, sizeof(float) * n3(L) * (size_t)B * (size_t)T, st));
+    ProjectTypedParams p;
+    p.coords = coords; p.num = num_atoms_of_type; p.off = offsets; p.out = out; p.B = B; p.T = T; p.nmax = nmax; p.L = L;
+    p.res = resolution;
+    return launch<ProjectTyped>(dim3((nmax + ProjectTyped::NT - 1) / ProjectTyped::NT, B), p, st);
+}
+
 struct OpWorkspace {
     cpx *tw = nullptr, *s1 = nullptr, *spec = nullptr, *s2 = nullptr;
     int L = 0, Q = 0;
 };
-static std::map<int, OpWorkspace> g_ws;     // per device
+static std::map<int, OpWorkspace> g_ws;     // per device; guarded by g_mutex (held for the whole call: launches on one
+                                            // workspace must not interleave with another thread's)
+extern "C" int dlpd_release_workspace(void) {
+    std::lock_guard<std::mutex> lk(g_mutex);
+    int prev = -1;
+#if !defined(DLPD_EMU)
+    if (cudaGetDevice(&prev) != cudaSuccess) prev = -1;
+#endif
+    for (auto& kv : g_ws) {
+        rt_set_device(kv.first);
+#if !defined(DLPD_EMU)
+        cudaDeviceSynchronize();
+#endif
+        rt_free(kv.second.tw); rt_free(kv.second.s1); rt_free(kv.second.spec); rt_free(kv.second.s2);
+    }
+    g_ws.clear();
+    if (prev >= 0) rt_set_device(prev);
+    return 0;
+}
 
 extern "C" int dlpd_volume_correlate(const float* v1, const float* v2, float* out, int B, int C, int L, void* stream) {
     if (!v1 || !v2 || !out || B < 1 || C < 1) return fail(DLPD_EINVAL, "dlpd_volume_correlate: bad argument");
@@ -965,6 +1181,8 @@ extern "C" int dlpd_volume_correlate(const float* v1, const float* v2, float* ou
     int Q = (int)((size_t)1536 * 1024 * 1024 / per_item);
     if (Q < 1) Q = 1;
     if (Q > items) Q = items;
+    std::lock_guard<std::mutex> lk(g_mutex);
+    const int mode = g_defaults.plane_mode;
     OpWorkspace& w = g_ws[dev];
     if (w.L != L || w.Q < Q) {
         TRY(rt_sync(st));
@@ -985,14 +1203,16 @@ extern "C" int dlpd_volume_correlate(const float* v1, const float* v2, float* ou
         PlaneParams pl;
         pl.in = w.s1; pl.out = w.spec; pl.spec = nullptr; pl.spec_pair_stride = 0; pl.tw = w.tw; pl.C = 1; pl.P = q; pl.tiled = 0; pl.wave = 1 << 30; pl.grid = 0;
         pl.scale = (float)(1.0 / ((double)N * N * N));
-        TRY(launch_plane(L, pl, st));
+        TRY(launch_plane(L, pl, mode, st));
         f.src = v2 + n3(L) * i0;
         TRY(launch_fwdz(L, f, q, st));
         pl.out = w.s2; pl.spec = w.spec; pl.spec_pair_stride = (long)n3(N); pl.scale = 1.f;
-        TRY(launch_plane(L, pl, st));
+        TRY(launch_plane(L, pl, mode, st));
         InvZParams iz;
         iz.in = w.s2; iz.out = out + n3(N) * i0; iz.tw = w.tw;
         TRY(launch_invz(L, iz, q, st));
     }
+    // two host threads may use different streams: the next caller must not overwrite the workspace under this call
+    TRY(rt_sync(st));
     return 0;
 }

@@ -102,7 +102,7 @@ def top_conformations(V: torch.Tensor, K: int) -> List[Tuple[int, int, int, floa
 
 class Docker:
     def __init__(self, docking_model, angle_inc=15.0, box_size=80, resolution=1.25, max_conf=1000, randomize_rot=False,
-                 rot_batch: int = 16, center: str = "box", clash_source: str = "project",
+                 rot_batch: int = 16, center: str = "grid", clash_source: str = "project",
                  pdb_loader: Optional[Callable[[str], Atoms]] = None, device=None, generator=None, verbose=False):
         """Reference arguments first (Docker.py:18); then: `rot_batch` rotations per fused call, rotation `center`
         convention, `clash_source` = 'project' (re-project rotated atoms, Docker.py:221-224) or 'rotate' (rotate the

@@ -41,10 +41,13 @@ class DockingSearch:
     box_size L, channel counts (C0 @ L, C1 @ L/2) and hidden width H select a compiled kernel
     configuration (`dlpd_search_supported`); anything else raises -- there is no fallback path.
     `max_rot` rotations are processed per internal batch (two rotations share one complex transform).
+    `center` is the rotation centre of the ligand feature volumes: 'grid' = (L-1)/2, what `affine_grid` + `grid_sample`
+    (the construction TorchProteinLibrary's VolumeRotation is built on) does -- the default wherever drop-in parity is
+    claimed; 'box' = L/2, consistent with voxel i at i * resolution and atoms centred at box_length / 2 (opt-in).
     """
 
     def __init__(self, box_size: int, channels: Sequence[int] = (16, 32), hidden: Optional[int] = None,
-                 max_rot: int = 16, center: str = "box", device=None):
+                 max_rot: int = 16, center: str = "grid", device=None):
         if not torch.cuda.is_available():
             raise _lib.DlpdError("DockingSearch needs a CUDA device (sm_100a); there is no CPU fallback")
         self.lib = _lib.get_lib()
@@ -64,8 +67,13 @@ class DockingSearch:
     # -- lifetime ---------------------------------------------------------------------------------
     def close(self):
         if getattr(self, "_h", None):
-            self.lib.dlpd_plan_destroy(self._h)
+            self.lib.dlpd_plan_destroy(self._h)     # restores the caller's current device itself
             self._h = ctypes.c_void_p()
+
+    def set_option(self, name: str, value) -> None:
+        """Kernel selection of THIS plan (`dlpd_plan_set_option`): see `_lib.set_option` for the names.  Changing the plane
+        mode after `set_receptor` makes the next search fail with DLPD_ESTATE until the receptor is set again."""
+        _lib.check(self.lib, self.lib.dlpd_plan_set_option(self._h, _lib.OPTIONS[name], _lib.option_value(name, value)))
 
     def __del__(self):
         try:
@@ -107,6 +115,15 @@ class DockingSearch:
             _lib.check(self.lib, self.lib.dlpd_set_ligand(self._h, _ptr(v0), _ptr(v1), _ptr(f), _stream_ptr(self.device)))
         self._keep["lig"] = (v0, v1, f)
 
+    def set_ligand_atoms(self, coords: torch.Tensor, resolution: float):
+        """Bbox-centred ligand atoms [Nat,3] (float64, Angstrom) for the in-loop clash re-projection inside the library
+        (Docker.py:221-224): `search_atoms` / `search_host_atoms` then need nothing but the float64 rotation matrices."""
+        c = coords.detach().to(device=self.device, dtype=torch.float64).contiguous().reshape(-1, 3)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib, self.lib.dlpd_set_ligand_atoms(self._h, _ptr(c), c.shape[0], float(resolution),
+                                                               _stream_ptr(self.device)))
+        self._keep["atoms"] = c
+
     def set_filter(self, filt):
         """`filt`: a SimpleFilter-like module (`.fc[0]`, `.fc[2]` Linear layers, DockingModels.py:28-32) or (W1,b1,W2,b2)."""
         if isinstance(filt, (tuple, list)):
@@ -140,14 +157,43 @@ class DockingSearch:
                                                      _stream_ptr(self.device)))
         return best, scores
 
+    def search_atoms(self, R64: torch.Tensor, threshold_clash: Optional[float] = None, return_scores: bool = False
+                     ) -> Tuple[torch.Tensor, Optional[torch.Tensor]]:
+        """`search` with the reference's own per-rotation clash volumes: R64 [n,3,3] float64 (the table's matrices,
+        Docker.py:214); the library casts them to fp32 for the volume rotation (Docker.py:215) and re-projects the rotated
+        atoms given to `set_ligand_atoms` chunk by chunk (Docker.py:221-224)."""
+        tau = self.threshold_clash if threshold_clash is None else float(threshold_clash)
+        Rd = R64.detach().to(device=self.device, dtype=torch.float64).contiguous().reshape(-1, 9)
+        n, N = Rd.shape[0], 2 * self.L
+        best = torch.empty(n, 4, device=self.device, dtype=torch.float32)
+        scores = torch.empty(n, N, N, N, device=self.device, dtype=torch.float32) if return_scores else None
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib, self.lib.dlpd_search_atoms(self._h, _ptr(Rd), n, tau, _ptr(best), _ptr(scores),
+                                                           _stream_ptr(self.device)))
+        return best, scores
+
+    def search_host_atoms(self, R64_host: torch.Tensor, threshold_clash: Optional[float] = None) -> torch.Tensor:
+        """End to end with HOST buffers: R64 [n,3,3] CPU float64 in, best [n,4] CPU float32 out; H2D, clash re-projection,
+        fused search, D2H and a stream synchronisation inside the library (`dlpd_search_host_atoms`)."""
+        tau = self.threshold_clash if threshold_clash is None else float(threshold_clash)
+        Rh = R64_host.detach().to("cpu", torch.float64).contiguous().reshape(-1, 9)
+        out = torch.empty(Rh.shape[0], 4, dtype=torch.float32)
+        with torch.cuda.device(self.device):
+            _lib.check(self.lib, self.lib.dlpd_search_host_atoms(self._h, _ptr(Rh), Rh.shape[0], tau, _ptr(out),
+                                                                _stream_ptr(self.device)))
+        return out
+
     def search_candidates(self, R: torch.Tensor, score_max: float, threshold_clash: Optional[float] = None,
-                          ligand_forbidden_rotated: Optional[torch.Tensor] = None, capacity: int = 1 << 16
-                          ) -> Tuple[torch.Tensor, torch.Tensor, int]:
+                          ligand_forbidden_rotated: Optional[torch.Tensor] = None, capacity: int = 1 << 16,
+                          use_atoms: bool = False) -> Tuple[torch.Tensor, torch.Tensor, int]:
         """`search` that also lists every translation with masked score <= `score_max` (the caller's current K-th best,
         Docker.py:100-105).  Returns (best [n,4], candidates [m,3] float64 = (score, rotation index in R, linear index),
         total) -- if total > m == capacity the list is truncated and the caller must redo this batch exactly."""
         tau = self.threshold_clash if threshold_clash is None else float(threshold_clash)
-        Rd = _dev_f32(R, self.device, "R").reshape(-1, 9)
+        if use_atoms:        # R float64: clash volumes re-projected inside the library from the atoms of set_ligand_atoms
+            Rd = R.detach().to(device=self.device, dtype=torch.float64).contiguous().reshape(-1, 9)
+        else:
+            Rd = _dev_f32(R, self.device, "R").reshape(-1, 9)
         n = Rd.shape[0]
         best = torch.empty(n, 4, device=self.device, dtype=torch.float32)
         cand = torch.empty(int(capacity), 4, device=self.device, dtype=torch.int32)
@@ -156,8 +202,14 @@ class DockingSearch:
         if ligand_forbidden_rotated is not None:
             cr = _dev_f32(ligand_forbidden_rotated, self.device, "ligand_forbidden_rotated").reshape(n, self.L, self.L, self.L)
         with torch.cuda.device(self.device):
-            _lib.check(self.lib, self.lib.dlpd_search_candidates(self._h, _ptr(Rd), _ptr(cr), n, tau, float(score_max), _ptr(best),
-                                                                _ptr(cand), int(capacity), _ptr(count), _stream_ptr(self.device)))
+            if use_atoms:
+                _lib.check(self.lib, self.lib.dlpd_search_candidates_atoms(self._h, _ptr(Rd), n, tau, float(score_max), _ptr(best),
+                                                                          _ptr(cand), int(capacity), _ptr(count),
+                                                                          _stream_ptr(self.device)))
+            else:
+                _lib.check(self.lib, self.lib.dlpd_search_candidates(self._h, _ptr(Rd), _ptr(cr), n, tau, float(score_max),
+                                                                    _ptr(best), _ptr(cand), int(capacity), _ptr(count),
+                                                                    _stream_ptr(self.device)))
         total = int(count.item())
         c = cand[:min(total, int(capacity))]
         out = torch.stack([c[:, 0].contiguous().view(torch.float32).double(), c[:, 1].double(), c[:, 2].double()], dim=1)

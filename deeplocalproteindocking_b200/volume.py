@@ -3,8 +3,9 @@
 
 `VolumeRotation` and `VolumeConvolution` call the hand-written CUDA kernels in libdlpd.so through
 `torch.autograd.Function`s (forward only: the search runs under `torch.no_grad()`,
-`/root/reference/src/local_test.py:67`; asking for a gradient raises).  `TypedCoords2Volume` stays plain
-PyTorch (it sits outside the fused search; BASELINE.json north_star).
+`/root/reference/src/local_test.py:67`; asking for a gradient raises).  `TypedCoords2Volume` runs the CUDA projector
+(`dlpd_project_typed`) for float32 CUDA inputs -- the receptor / ligand set-up and the per-rotation projection of the
+`dockE3` loop (Docker.py:164,204,208) -- and keeps a plain-PyTorch form for CPU tensors (host-side tests only).
 """
 from __future__ import annotations
 
@@ -50,10 +51,11 @@ class VolumeRotationFunction(_NoBackward, torch.autograd.Function):
 class VolumeRotation(nn.Module):
     """`TorchProteinLibrary.Volume.VolumeRotation` (Docker.py:40,218): `forward(volume[B,C,L,L,L], R[B,3,3])`.
 
-    out[b,c,p] = trilinear(volume[b,c], ctr + R_b^T (p - ctr)), zeros outside; ctr = L/2 ('box', default)
-    or (L-1)/2 ('grid')."""
+    out[b,c,p] = trilinear(volume[b,c], ctr + R_b^T (p - ctr)), zeros outside; ctr = (L-1)/2 ('grid', default: what
+    `affine_grid` + `grid_sample` -- the construction TorchProteinLibrary's operator is built on -- does, see
+    tests/test_host_logic.py) or L/2 ('box', opt-in)."""
 
-    def __init__(self, center: str = "box"):
+    def __init__(self, center: str = "grid"):
         super().__init__()
         self.center_mode = _lib.CENTER_MODES[center]
 
@@ -102,6 +104,27 @@ class TypedCoords2Volume(nn.Module):
 
     def forward(self, input_coords_cpu, num_atoms_of_type, offsets):
         coords = input_coords_cpu
+        B, T = num_atoms_of_type.shape
+        L, res = self.box_size, self.resolution
+        if coords.is_cuda and coords.dtype == torch.float32:
+            return self._forward_cuda(coords, num_atoms_of_type, offsets)
+        return self._forward_torch(coords, num_atoms_of_type, offsets)
+
+    def _forward_cuda(self, coords, num_atoms_of_type, offsets):
+        """One launch of the `ProjectTyped` kernel: one thread per atom slot, atomic scatter of the 5^3 stencil."""
+        B, T = num_atoms_of_type.shape
+        L = self.box_size
+        c = coords.contiguous()
+        nat = num_atoms_of_type.to(device=c.device, dtype=torch.int32).contiguous()
+        off = offsets.to(device=c.device, dtype=torch.int32).contiguous()
+        out = torch.empty(B, T, L, L, L, device=c.device, dtype=torch.float32)
+        lib = _lib.get_lib()
+        with torch.cuda.device(c.device):
+            _lib.check(lib, lib.dlpd_project_typed(_ptr(c), _ptr(nat), _ptr(off), B, T, c.shape[1] // 3, L, self.resolution,
+                                                  _ptr(out), _stream_ptr(c.device)))
+        return out
+
+    def _forward_torch(self, coords, num_atoms_of_type, offsets):
         B, T = num_atoms_of_type.shape
         L, res = self.box_size, self.resolution
         out = torch.zeros(B, T, L * L * L, device=coords.device, dtype=coords.dtype)

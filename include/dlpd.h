@@ -13,7 +13,9 @@
  *     stated otherwise;
  *   - return value 0 = success, otherwise a DLPD_E* code; dlpd_last_error() returns the message of the last
  *     failure on the calling thread;
- *   - a plan is not thread-safe; distinct plans are independent;
+ *   - a plan is not thread-safe; distinct plans are independent (every kernel-selection option, workspace and profile
+ *     counter lives in the plan; the only process-wide state is the table of DEFAULT options new plans start from and
+ *     the mutex-guarded workspace of the plan-less standalone operators);
  *   - there is no CPU fallback: every entry point fails with DLPD_ECUDA if no device is usable.
  */
 #ifndef DLPD_H
@@ -28,8 +30,9 @@ extern "C" {
 #define DLPD_ECUDA 2       /* CUDA runtime error (message in dlpd_last_error)       */
 #define DLPD_ESTATE 3      /* call order violated (e.g. search before set_receptor) */
 
-#define DLPD_CENTER_BOX 0  /* rotation centre L/2     (default; SURVEY 8c choice 2) */
-#define DLPD_CENTER_GRID 1 /* rotation centre (L-1)/2 (literal torch-1.1 affine_grid) */
+#define DLPD_CENTER_BOX 0  /* rotation centre L/2     (voxel i at i * resolution; SURVEY 8c choice 2)               */
+#define DLPD_CENTER_GRID 1 /* rotation centre (L-1)/2 (literal affine_grid / grid_sample, align_corners = True:
+                              what TorchProteinLibrary's VolumeRotation most plausibly does -- the Python default) */
 
 typedef struct dlpd_plan dlpd_plan;
 
@@ -93,8 +96,24 @@ int dlpd_search_prerotated(dlpd_plan* plan, const float* lig0_rot, const float* 
                            float tau, float* out_best, float* out_scores, void* stream);
 
 /* Same with HOST buffers (R_host [n][9] in, best_host [n][4] out): stages through pinned memory, copies inside,
- * and synchronises the stream before returning.  This is the end-to-end call bench.py times. */
+ * and synchronises the stream before returning.  The ligand clash volume given to dlpd_set_ligand is rotated. */
 int dlpd_search_host(dlpd_plan* plan, const float* R_host, int n, float tau, float* best_host, void* stream);
+
+/* ---- the reference's own per-rotation clash volumes, inside the library (Docker.py:214-224) -------------------------
+ * dlpd_set_ligand_atoms keeps the ligand's bbox-centred atom coordinates (device [nat][3] float64, Angstrom; the typed
+ * layout does not matter once summed over types) and the voxel size.  The *_atoms searches then take the float64
+ * rotation matrices of the table (r_batch_cpu, Docker.py:214) and, chunk by chunk: cast them to fp32 for the volume
+ * rotation (Docker.py:215), rotate + translate the atoms in float64, cast, project and sum over types (Docker.py:221-224,
+ * = dlpd_project_clash) and run the fused search on the result.  Nothing per rotation crosses the host boundary.
+ *   dlpd_search_atoms            R64 device [n][9] float64; otherwise as dlpd_search
+ *   dlpd_search_candidates_atoms as dlpd_search_candidates
+ *   dlpd_search_host_atoms       R_host [n][9] float64 and best_host [n][4] are HOST buffers: H2D, search, D2H and a stream
+ *                                synchronisation inside -- the end-to-end call bench.py times (`e2e`). */
+int dlpd_set_ligand_atoms(dlpd_plan* plan, const double* coords, int nat, float resolution, void* stream);
+int dlpd_search_atoms(dlpd_plan* plan, const double* R64, int n, float tau, float* out_best, float* out_scores, void* stream);
+int dlpd_search_candidates_atoms(dlpd_plan* plan, const double* R64, int n, float tau, float score_max, float* out_best,
+                                 int* cand, int cand_cap, unsigned int* cand_count, void* stream);
+int dlpd_search_host_atoms(dlpd_plan* plan, const double* R_host, int n, float tau, float* best_host, void* stream);
 
 /* ---- measurement hooks (bench.py) ----------------------------------------------------------------------
  * Per-kernel device time with CUDA events recorded on the launching stream around every launch of dlpd_search. */
@@ -118,19 +137,30 @@ long long dlpd_launch_count(void);
 int dlpd_project_clash(const double* coords, const double* R, int nat, int n, int L, float resolution, float* out,
                        void* stream);
 
-/* ---- tuning / test switches (process-wide) -------------------------------------------------------------
+/* TorchProteinLibrary.Volume.TypedCoords2Volume(box_size, resolution).forward(coords, num_atoms_of_type, offsets)
+ * (Docker.py:31,204,208; per rotation in dockE3, Docker.py:164): coords device [B][3 nmax] fp32 in the typed layout (atoms
+ * of type t of structure b at slots offsets[b][t] .. + num_atoms_of_type[b][t] - 1), both int tables device [B][T];
+ * out device [B][T][L^3] fp32 (overwritten): every atom adds exp(-r^2 / 2) to the 5^3 voxels around floor(x / res). */
+int dlpd_project_typed(const float* coords, const int* num_atoms_of_type, const int* offsets, int B, int T, int nmax, int L,
+                       float resolution, float* out, void* stream);
+
+/* ---- kernel-selection options ----------------------------------------------------------------------------
+ * Every plan owns its options: dlpd_plan_set_option changes ONE plan; dlpd_set_option changes the process-wide DEFAULTS that
+ * plans created afterwards start from (and that the plan-less standalone operators use).
  * DLPD_OPT_PLANE_MODE     which kernel runs the per-(channel, kz) plane stage: AUTO = one CTA per plane when the plane
  *                         fits an SM's shared memory (N <= 160), else a thread-block cluster (8 CTAs at N = 256, 4 elsewhere) with distributed shared memory;
  *                         SINGLE forces the former (fails if the plane does not fit), CLUSTER prefers the latter wherever it is
  *                         compiled (box sizes 8, 16, 20, 40, 64, 80, 128).  The receptor spectra of
- *                         a plan are laid out for the mode in force at dlpd_set_receptor time: do not switch between
- *                         dlpd_set_receptor and dlpd_search.
+ *                         a plan are laid out for the mode in force at dlpd_set_receptor time: a search after a switch
+ *                         that selects the other kernel fails with DLPD_ESTATE until dlpd_set_receptor is called again.
  * DLPD_OPT_EPILOGUE_TILE  0 = automatic, 1 = 2x1, 2 = 2x2 (x,y) columns per epilogue tile (classic epilogue)
- * DLPD_OPT_EPILOGUE_KIND  AUTO / CLASSIC / PIPELINED / DUO / FUSED, see below
- * DLPD_OPT_FILTER_KIND    how the classic epilogue evaluates the level-0 half of SimpleFilter's first layer
- *                         (DockingModels.py:29, 16 -> H): FP32 = packed FFMA chain; TENSOR = mma.sync m16n8k16 on fp16
- *                         operands split hi + lo (three products per term, fp32 accumulation: agrees with the FFMA
- *                         chain to fp32 rounding level; C0 = 16, H % 8 = 0 only); AUTO = FP32 (faster on B200) */
+ * DLPD_OPT_EPILOGUE_KIND  AUTO / CLASSIC; PIPELINED / DUO / FUSED are measured-and-rejected variants that exist only in builds
+ *                         with -DDLPD_EXPERIMENTAL=1 (dlpd_build_flags) -- elsewhere selecting them fails with DLPD_EINVAL
+ * DLPD_OPT_FILTER_KIND    how the epilogue evaluates the level-0 half of SimpleFilter's first layer (DockingModels.py:29,
+ *                         C0 -> H):  TCGEN05 = tcgen05.mma kind::tf32 with the operand and accumulators in TMEM, every
+ *                         factor split into TF32 hi + lo (three products per term, fp32 accumulation: agrees with the FP32
+ *                         chain to ~3e-7 of the score range; needs C0 % 8 == 0 and H % 8 == 0);  FP32 = packed FFMA2 chain;
+ *                         TENSOR = mma.sync fp16 split (experimental builds only);  AUTO = TCGEN05 where available, else FP32 */
 #define DLPD_OPT_PLANE_MODE 1
 #define DLPD_OPT_EPILOGUE_TILE 2
 #define DLPD_OPT_EPILOGUE_KIND 3
@@ -138,6 +168,7 @@ int dlpd_project_clash(const double* coords, const double* R, int nat, int n, in
 #define DLPD_FILTER_AUTO 0
 #define DLPD_FILTER_FP32 1
 #define DLPD_FILTER_TENSOR 2
+#define DLPD_FILTER_TCGEN05 3
 #define DLPD_EPILOGUE_AUTO 0
 #define DLPD_EPILOGUE_CLASSIC 1     /* one consumer team: transform then filter, next tile prefetched            */
 #define DLPD_EPILOGUE_PIPELINED 2   /* load / transform / filter of consecutive half-tiles overlap (N <= 160)    */
@@ -148,6 +179,13 @@ int dlpd_project_clash(const double* coords, const double* R, int nat, int n, in
 #define DLPD_PLANE_SINGLE 1
 #define DLPD_PLANE_CLUSTER 2
 int dlpd_set_option(int key, int value);
+int dlpd_plan_set_option(dlpd_plan* plan, int key, int value);
+/* what this build of the library contains */
+#define DLPD_BUILD_EXPERIMENTAL 1   /* the rejected epilogue variants and the mma.sync filter are compiled in */
+#define DLPD_BUILD_EMULATION 2      /* host emulation of the kernel bodies (tests/emu only; never shipped)      */
+int dlpd_build_flags(void);
+/* Frees the device workspace the standalone operators (dlpd_volume_correlate) keep per device. */
+int dlpd_release_workspace(void);
 
 /* ---- standalone operators (module-level drop-ins) --------------------------------------------------------
  * TorchProteinLibrary.Volume.VolumeRotation.forward(volume, R)   (Docker.py:40,218)

@@ -41,7 +41,7 @@ def euler_to_matrix(phi: float, theta: float, psi: float) -> torch.Tensor:
 # --------------------------------------------------------------------------------------
 # VolumeRotation  (Docker.py:40,218)   -- PARITY UNPINNED: centre & boundary are our choice
 # --------------------------------------------------------------------------------------
-def rotation_center(L: int, center: str = "box") -> float:
+def rotation_center(L: int, center: str = "grid") -> float:
     """'box': c = L/2 (voxel i sits at i*res and atoms are centred at box_length/2, Docker.py:34-35);
     'grid': c = (L-1)/2 (literal torch-1.1 affine_grid/grid_sample, align_corners=True)."""
     if center == "box":
@@ -51,7 +51,7 @@ def rotation_center(L: int, center: str = "box") -> float:
     raise ValueError(center)
 
 
-def rotate_volume(volume: torch.Tensor, R: torch.Tensor, center: str = "box") -> torch.Tensor:
+def rotate_volume(volume: torch.Tensor, R: torch.Tensor, center: str = "grid") -> torch.Tensor:
     """out[b,c,p] = trilinear(volume[b,c], ctr + R_b^T (p - ctr)), zero outside [0,L-1]^3.
 
     p = (x,y,z) = tensor dims (2,3,4).  volume [B,C,L,L,L]; R [B,3,3].  Computed in volume.dtype.
@@ -87,7 +87,7 @@ def rotate_volume(volume: torch.Tensor, R: torch.Tensor, center: str = "box") ->
     return out.reshape(B, C, L, L, L)
 
 
-def rotate_volume_grid_sample(volume: torch.Tensor, R: torch.Tensor, center: str = "box") -> torch.Tensor:
+def rotate_volume_grid_sample(volume: torch.Tensor, R: torch.Tensor, center: str = "grid") -> torch.Tensor:
     """Same operator through `F.grid_sample(mode='bilinear', padding_mode='zeros', align_corners=True)`."""
     B, C, L = volume.shape[0], volume.shape[1], volume.shape[2]
     dt = volume.dtype
@@ -327,7 +327,7 @@ class ReceptorSpectra:
 
 
 def score_rotation(spectra: ReceptorSpectra, ligand_volumes: List[torch.Tensor], ligand_forbidden: torch.Tensor,
-                   R: torch.Tensor, filt: FilterWeights, threshold: float, center: str = "box",
+                   R: torch.Tensor, filt: FilterWeights, threshold: float, center: str = "grid",
                    ligand_forbidden_is_rotated: bool = False) -> torch.Tensor:
     """Masked score volume V [2L,2L,2L] of ONE rotation (Docker.py:218-232) with precomputed receptor spectra.
 
@@ -352,7 +352,7 @@ def score_rotation(spectra: ReceptorSpectra, ligand_volumes: List[torch.Tensor],
 
 
 def dock(receptor_volumes, receptor_forbidden, ligand_volumes, ligand_forbidden, Rs, filt, threshold,
-         K: int = 1, center: str = "box", ligand_forbidden_rotated=None):
+         K: int = 1, center: str = "grid", ligand_forbidden_rotated=None):
     """Restatement of the dockSE3 loop over rotations `Rs [n,3,3]`.
 
     Returns (best [n,4] float64 rows (score,x,y,z), top_list of (rot,x,y,z,score) like Docker.top_list).

@@ -24,7 +24,8 @@ def build(force=False, flags=(), so=None):
     so = so or SO
     srcs = [os.path.join(SRC, f) for f in os.listdir(SRC)] + [os.path.join(ROOT, "include", "dlpd.h")]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
-        subprocess.check_call(["g++", "-std=c++17", "-O2", "-DDLPD_EMU", *flags, "-x", "c++", "-fPIC", "-shared",
+        # -DDLPD_EXPERIMENTAL=1: the emulation also covers the rejected epilogue variants the shipped library leaves out
+        subprocess.check_call(["g++", "-std=c++17", "-O2", "-DDLPD_EMU", "-DDLPD_EXPERIMENTAL=1", *flags, "-x", "c++", "-fPIC", "-shared",
                                "-o", so, os.path.join(SRC, "dlpd_api.cu")])
     return so
 
@@ -61,7 +62,7 @@ def fptr(t):
 
 
 class EmuPlan:
-    def __init__(self, L, C0, C1, H, max_rot=4, center="box"):
+    def __init__(self, L, C0, C1, H, max_rot=4, center="grid"):
         self.L, self.C0, self.C1, self.H = L, C0, C1, H
         self.h = ctypes.c_void_p()
         _lib.check(lib(), lib().dlpd_plan_create(ctypes.byref(self.h), L, C0, C1, H, max_rot, _lib.CENTER_MODES[center], 0))
@@ -119,6 +120,27 @@ class EmuPlan:
         _lib.check(lib(), lib().dlpd_search_host(self.h, ptr(R), R.shape[0], float(tau), ptr(best), None))
         return best
 
+    def set_option(self, key, value):
+        _lib.check(lib(), lib().dlpd_plan_set_option(self.h, key, value))
+
+    def set_ligand_atoms(self, coords, res):
+        coords = coords.contiguous().double().reshape(-1, 3)
+        _lib.check(lib(), lib().dlpd_set_ligand_atoms(self.h, ptr(coords), coords.shape[0], float(res), None))
+
+    def search_atoms(self, R64, tau, want_scores=False):
+        R64 = R64.contiguous().double().reshape(-1, 9)
+        n, N = R64.shape[0], 2 * self.L
+        best = torch.zeros(n, 4)
+        scores = torch.zeros(n, N, N, N) if want_scores else None
+        _lib.check(lib(), lib().dlpd_search_atoms(self.h, ptr(R64), n, float(tau), ptr(best), ptr(scores), None))
+        return best, scores
+
+    def search_host_atoms(self, R64, tau):
+        R64 = R64.contiguous().double().reshape(-1, 9)
+        best = torch.zeros(R64.shape[0], 4)
+        _lib.check(lib(), lib().dlpd_search_host_atoms(self.h, ptr(R64), R64.shape[0], float(tau), ptr(best), None))
+        return best
+
 
 OPT_PLANE_MODE, OPT_EPILOGUE_TILE, OPT_EPILOGUE_KIND = 1, 2, 3
 EPILOGUE_AUTO, EPILOGUE_CLASSIC, EPILOGUE_PIPELINED, EPILOGUE_DUO, EPILOGUE_FUSED = 0, 1, 2, 3, 4
@@ -129,7 +151,7 @@ def set_option(key, value):
     _lib.check(lib(), lib().dlpd_set_option(key, value))
 
 
-def volume_rotate(vol, R, center="box"):
+def volume_rotate(vol, R, center="grid"):
     vol, R = vol.contiguous().float(), R.contiguous().float()
     out = torch.empty_like(vol)
     B, C, L = vol.shape[:3]
@@ -142,6 +164,15 @@ def volume_correlate(v1, v2):
     B, C, L = v1.shape[:3]
     out = torch.empty(B, C, 2 * L, 2 * L, 2 * L)
     _lib.check(lib(), lib().dlpd_volume_correlate(ptr(v1), ptr(v2), ptr(out), B, C, L, None))
+    return out
+
+
+def project_typed(coords, nat, off, L, res):
+    coords = coords.contiguous().float()
+    nat, off = nat.contiguous().to(torch.int32), off.contiguous().to(torch.int32)
+    B, T = nat.shape
+    out = torch.empty(B, T, L, L, L)
+    _lib.check(lib(), lib().dlpd_project_typed(ptr(coords), ptr(nat), ptr(off), B, T, coords.shape[1] // 3, L, float(res), ptr(out), None))
     return out
 
 

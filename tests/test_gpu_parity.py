@@ -14,6 +14,12 @@ R20 = rotations.Rotations(20).R
 DEV = "cuda:0"
 
 
+def _need_experimental():
+    """The rejected epilogue variants and the mma.sync filter exist only in -DDLPD_EXPERIMENTAL=1 builds of libdlpd.so."""
+    if not _lib.has_experimental():
+        pytest.skip("libdlpd.so was built without -DDLPD_EXPERIMENTAL=1")
+
+
 def _d(t):
     return t.double()
 
@@ -330,6 +336,7 @@ def test_project_clash_matches_oracle():
 # ---- pipelined epilogue (load / transform / filter stages overlapped with named barriers) --------------------------
 @pytest.fixture
 def pipelined_epilogue():
+    _need_experimental()
     _lib.set_option("epilogue_kind", "pipelined")
     yield
     _lib.set_option("epilogue_kind", "auto")
@@ -348,6 +355,7 @@ def test_pipelined_epilogue_80_matches_oracle(pipelined_epilogue):
 # ---- two half-tile epilogue CTAs per SM --------------------------------------------------------------------------
 @pytest.fixture
 def duo_epilogue():
+    _need_experimental()
     _lib.set_option("epilogue_kind", "duo")
     yield
     _lib.set_option("epilogue_kind", "auto")
@@ -366,6 +374,7 @@ def test_duo_epilogue_80_matches_oracle(duo_epilogue):
 # ---- fused epilogue -------------------------------------------------------------------------------------------------
 @pytest.fixture
 def fused_epilogue():
+    _need_experimental()
     _lib.set_option("epilogue_kind", "fused")
     yield
     _lib.set_option("epilogue_kind", "auto")
@@ -383,6 +392,7 @@ def test_fused_epilogue_80_matches_oracle(fused_epilogue):
 
 def test_epilogue_kinds_80_many_rotations_identical():
     """33 rotations (17 pairs, odd tail) at L=80 through all four epilogues: identical best poses and scores."""
+    _need_experimental()
     L, C0, C1 = 80, 16, 32
     rec, rec_clash = synthetic.learned_volumes(L, (C0, C1), seed=31)
     lig, lig_clash = synthetic.learned_volumes(L, (C0, C1), seed=32)
@@ -391,17 +401,20 @@ def test_epilogue_kinds_80_many_rotations_identical():
     out = []
     for kind in ("classic", "pipelined", "duo", "fused"):
         _lib.set_option("epilogue_kind", kind)
+        _lib.set_option("filter_kind", "fp32")
         eng = DockingSearch(L, (C0, C1), max_rot=16, device=DEV)
         eng.set_receptor(rec, rec_clash); eng.set_ligand(lig, lig_clash); eng.set_filter((filt.W1, filt.b1, filt.W2, filt.b2))
         out.append(eng.search(Rs, 30.0)[0].cpu())
         eng.close()
     _lib.set_option("epilogue_kind", "auto")
+    _lib.set_option("filter_kind", "auto")
     assert torch.equal(out[0], out[1]) and torch.equal(out[0], out[2]) and torch.equal(out[0], out[3])
 
 
 # ---- first filter layer: packed FFMA chain vs fp16-split mma.sync -------------------------------------------------
 @pytest.fixture
 def tensor_filter():
+    _need_experimental()
     _lib.set_option("filter_kind", "tensor")
     yield
     _lib.set_option("filter_kind", "auto")
@@ -418,9 +431,10 @@ def test_tensor_filter_80_matches_oracle(tensor_filter):
 
 @pytest.mark.parametrize("scale", [1.0, 1e-3, 3e3])
 def test_filter_kinds_80_agree(scale):
-    """Tensor-core (fp16 hi+lo split, three products) vs FFMA first layer at L=80, 9 rotations, volumes scaled over six orders
-    of magnitude (the per-channel power-of-two scaling must keep fp16 in range): identical best translations, scores and the
-    whole masked score volume of one rotation within 1e-5 of the score range."""
+    """tcgen05 (3 x TF32 split, TMEM) vs FFMA2 first layer at L=80, 9 rotations, volumes scaled over six orders of magnitude
+    (TF32 keeps fp32's exponent range: no scaling needed) and channels of very different size: identical best
+    translations, scores and the whole masked score volume of one rotation within 1e-5 of the score range.  Experimental
+    builds also run the mma.sync fp16-split variant."""
     L, C0, C1 = 80, 16, 32
     rec, rec_clash = synthetic.learned_volumes(L, (C0, C1), seed=41)
     lig, lig_clash = synthetic.learned_volumes(L, (C0, C1), seed=42)
@@ -432,7 +446,8 @@ def test_filter_kinds_80_agree(scale):
     W1[:, :C0] /= scale                                 # keep the hidden pre-activations O(1)
     Rs = R20[torch.arange(9) * 201 + 5]
     out, vol = [], []
-    for kind in ("fp32", "tensor"):
+    kinds = ("fp32", "tcgen05") + (("tensor",) if _lib.has_experimental() else ())
+    for kind in kinds:
         _lib.set_option("filter_kind", kind)
         eng = DockingSearch(L, (C0, C1), max_rot=8, device=DEV)
         eng.set_receptor(rec, rec_clash); eng.set_ligand(lig, lig_clash); eng.set_filter((W1, filt.b1, filt.W2, filt.b2))
@@ -440,7 +455,35 @@ def test_filter_kinds_80_agree(scale):
         vol.append(eng.search(Rs[:1], 30.0, return_scores=True)[1].cpu())
         eng.close()
     _lib.set_option("filter_kind", "auto")
-    assert torch.equal(out[0][:, 1:], out[1][:, 1:])
     rng = float(vol[0].abs().max())
-    assert (out[0][:, 0] - out[1][:, 0]).abs().max() <= 1e-5 * rng
-    assert (vol[0] - vol[1]).abs().max() <= 1e-5 * rng
+    for k in range(1, len(kinds)):
+        assert torch.equal(out[0][:, 1:], out[k][:, 1:]), kinds[k]
+        assert (out[0][:, 0] - out[k][:, 0]).abs().max() <= 1e-5 * rng, kinds[k]
+        assert (vol[0] - vol[k]).abs().max() <= 1e-5 * rng, kinds[k]
+
+
+@pytest.fixture(params=["fp32", "tcgen05"])
+def filter_kind(request):
+    _lib.set_option("filter_kind", request.param)
+    yield request.param
+    _lib.set_option("filter_kind", "auto")
+
+
+@pytest.mark.parametrize("L,C0,C1,H,n", [(8, 16, 32, 24, 3), (16, 16, 32, 24, 2), (20, 16, 32, 24, 5)])
+def test_filter_kind_small_matches_oracle(L, C0, C1, H, n, filter_kind):
+    """Both shipped forms of the first filter layer at sizes with partly filled warpgroups (64 / 128 / 160 translations per tile)."""
+    test_search_small_matches_oracle(L, C0, C1, H, n)
+
+
+def test_filter_kind_80_matches_oracle(filter_kind):
+    test_search_full_size_80_matches_oracle()
+
+
+def test_filter_kind_2x1_tile_matches_oracle(filter_kind):
+    """The 2x1 epilogue tile (what 128^3 uses) at L = 20 and L = 80: 2 / 3 warpgroups of translations per tile."""
+    _lib.set_option("epilogue_tile", 1)
+    try:
+        test_search_small_matches_oracle(20, 16, 32, 24, 5)
+        test_search_full_size_80_matches_oracle()
+    finally:
+        _lib.set_option("epilogue_tile", 0)

@@ -31,7 +31,7 @@ def test_identity_rotation_is_identity():
 def test_rotation_direction_blob():
     """P4: a blob at c+u ends up at c+R.u (same direction as CoordsRotate r' = R r, Docker.py:218 vs :221)."""
     L = 32
-    c = L / 2.0
+    c = O.rotation_center(L)                       # centre of the default convention
     u = torch.tensor([6.0, -3.0, 4.0], dtype=torch.float64)
     ax = torch.arange(L, dtype=torch.float64)
     X, Y, Z = torch.meshgrid(ax, ax, ax, indexing="ij")
@@ -52,13 +52,33 @@ def test_rotated_projection_consistent_with_volume_rotation():
     atoms = (torch.rand(300, 3, generator=g, dtype=torch.float64) - 0.5) * 14.0
     R = _rand_rot(8)
     v0 = O.ligand_clash_volume(atoms, torch.eye(3, dtype=torch.float64), L, res)
-    v_rot = O.rotate_volume(v0[None, None].double(), R[None])[0, 0]
+    v_rot = O.rotate_volume(v0[None, None].double(), R[None], center="box")[0, 0]
     v_proj = O.ligand_clash_volume(atoms, R, L, res).double()
     sim = (v_rot * v_proj).sum() / torch.sqrt((v_rot ** 2).sum() * (v_proj ** 2).sum())
     assert sim > 0.97
     v_grid = O.rotate_volume(v0[None, None].double(), R[None], center="grid")[0, 0]
     sim_grid = (v_grid * v_proj).sum() / torch.sqrt((v_grid ** 2).sum() * (v_proj ** 2).sum())
     assert sim > sim_grid
+
+
+def test_default_rotation_is_affine_grid_plus_grid_sample():
+    """The default centre ('grid') is what `F.affine_grid` + `F.grid_sample` do -- the construction TorchProteinLibrary's
+    VolumeRotation is built on -- for BOTH align_corners settings (the centre is (L-1)/2 in index space either way):
+    theta = P R^T P with P the (x,y,z) <-> (z,y,x) axis swap of grid_sample's coordinate order."""
+    import torch.nn.functional as F
+    g = torch.Generator().manual_seed(3)
+    for L in (9, 12):
+        vol = torch.randn(2, 3, L, L, L, generator=g, dtype=torch.float64)
+        R = torch.stack([_rand_rot(11), _rand_rot(12)])
+        want = O.rotate_volume(vol, R)                                  # default centre
+        P = torch.tensor([[0., 0., 1.], [0., 1., 0.], [1., 0., 0.]], dtype=torch.float64)
+        theta = torch.zeros(2, 3, 4, dtype=torch.float64)
+        theta[:, :, :3] = P @ R.transpose(1, 2) @ P
+        for ac in (True, False):
+            grid = F.affine_grid(theta, list(vol.shape), align_corners=ac)
+            got = F.grid_sample(vol, grid, mode="bilinear", padding_mode="zeros", align_corners=ac)
+            assert (got - want).abs().max() < 1e-9, (L, ac)
+        assert (O.rotate_volume(vol, R, center="box") - want).abs().max() > 1e-3     # the opt-in convention differs
 
 
 def test_dock_small_end_to_end_fp32_vs_fp64():
