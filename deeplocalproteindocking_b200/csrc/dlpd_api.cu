@@ -4,6 +4,7 @@
 #include "../../include/dlpd.h"
 #if !defined(DLPD_EMU)
 #include <cooperative_groups.h>
+#include <cuda.h>               // CUtensorMap (types only: the encoder is fetched with cudaGetDriverEntryPoint, no libcuda link)
 #endif
 #include "dlpd_kernels.h"
 
@@ -94,7 +95,7 @@ static int rt_sync(dlpd_stream_t st) { CU(cudaStreamSynchronize(st)); return 0; 
 
 template <class K>
 __global__ void __launch_bounds__(K::NT) dlpd_kernel(const __grid_constant__ typename K::Params p) {
-    extern __shared__ __align__(16) char smem[];
+    extern __shared__ __align__(128) char smem[];
     K::body(p, blockIdx.x, blockIdx.y, blockIdx.z, smem);
 }
 template <class K> static int launch(dim3 g, const typename K::Params& p, dlpd_stream_t st) {
@@ -114,7 +115,7 @@ template <class K> static int launch(dim3 g, const typename K::Params& p, dlpd_s
 // same for kernels that state how many CTAs per SM their register budget is cut for (K::MINB)
 template <class K>
 __global__ void __launch_bounds__(K::NT, K::MINB) dlpd_kernel_mb(const __grid_constant__ typename K::Params p) {
-    extern __shared__ __align__(16) char smem[];
+    extern __shared__ __align__(128) char smem[];
     K::body(p, blockIdx.x, blockIdx.y, blockIdx.z, smem);
 }
 // CARVE: ask for the maximum shared-memory carve-out (kernels that live in shared memory); false for kernels whose
@@ -140,7 +141,7 @@ template <class K, bool CARVE = true> static int launch_mb(dim3 g, const typenam
 // persistent: the resident clusters walk over the work items cid0, cid0 + n_resident, ... (no cluster launch per item)
 template <class K>
 __global__ void __launch_bounds__(K::NT, K::MINB) dlpd_cluster_kernel(const __grid_constant__ typename K::Params p, int n_items) {
-    extern __shared__ __align__(16) char smem[];
+    extern __shared__ __align__(128) char smem[];
     namespace cg = cooperative_groups;
     cg::cluster_group cl = cg::this_cluster();
     const int rank = (int)cl.block_rank(), step = (int)(gridDim.x / K::CL);
@@ -686,6 +687,46 @@ template <int L, int C0, int C1, int H> static int launch_filter_prep(dlpd_plan*
     return 0;
 }
 #endif   // DLPD_EXPERIMENTAL
+#if !defined(DLPD_EMU)
+// TMA descriptor of the tiled level-0 S2 array [P][C0+1][N][T*T][8 floats] as a rank-5 fp32 tensor with the dimensions
+// ordered (payload, channel, kz', tile, pair): a box (8 | 4, C0+1, N, 1, 1) is one epilogue tile and lands in shared memory as
+// [kz'][channel][payload], the layout the transform passes work on.
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_tiled_fn() {
+    static std::atomic<void*> fn{nullptr};
+    void* f = fn.load();
+    if (!f) {
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &f, cudaEnableDefault, &q) != cudaSuccess || q != cudaDriverEntryPointSuccess)
+            f = nullptr;
+        fn.store(f);
+    }
+    return (EncodeTiledFn)f;
+}
+static int make_s2_tensor_map(const cpx* s2, int C, int N, int T, int P, int payload, unsigned long long (&out)[16]) {
+    EncodeTiledFn enc = encode_tiled_fn();
+    if (!enc) return fail(DLPD_ECUDA, "cuTensorMapEncodeTiled is not available from this driver");
+    static_assert(sizeof(CUtensorMap) == 128, "CUtensorMap size");
+    const cuuint64_t tile = 32;                                  // bytes of one 2x2 tile of one (c, kz') row
+    cuuint64_t dims[5] = {8, (cuuint64_t)C, (cuuint64_t)N, (cuuint64_t)T * T, (cuuint64_t)P};
+    cuuint64_t strides[4] = {(cuuint64_t)N * T * T * tile, (cuuint64_t)T * T * tile, tile, (cuuint64_t)C * N * T * T * tile};
+    cuuint32_t box[5] = {(cuuint32_t)payload, (cuuint32_t)C, (cuuint32_t)N, 1, 1};
+    cuuint32_t estr[5] = {1, 1, 1, 1, 1};
+    CUtensorMap m;
+    const CUresult r = enc(&m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 5, (void*)s2, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                           CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        char b[96];
+        snprintf(b, sizeof b, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return fail(DLPD_ECUDA, b);
+    }
+    memcpy(out, &m, 128);
+    return 0;
+}
+#endif
+
 template <int L, int C0, int C1, int H, int TY, int FK = 0>
 static int launch_epilogue_t(dlpd_plan* p, int n, int P, float tau, float* out_scores, const CandArgs& ca, dlpd_stream_t st) {
     typedef Epilogue<L, C0, C1, H, TY, FK> K;
@@ -698,6 +739,9 @@ static int launch_epilogue_t(dlpd_plan* p, int n, int P, float tau, float* out_s
         e.grid = e.n_tiles < p->sm_count ? e.n_tiles : p->sm_count;
         fill_filter(p, e.filt);
         e.mlp = nullptr;
+#if !defined(DLPD_EMU)
+        if constexpr (K::USE_TMA) TRY(make_s2_tensor_map(p->s2_0, C0 + 1, K::N, K::T, p->P, TY == 2 ? 8 : 4, e.tmap));
+#endif
 #if DLPD_EXPERIMENTAL
         if constexpr (K::MMA_OK) {
             TRY((launch_filter_prep<L, C0, C1, H>(p, st)));

@@ -83,6 +83,15 @@
 #ifndef DLPD_FWDZC_NT
 #define DLPD_FWDZC_NT 256
 #endif
+#ifndef DLPD_EPI_TMA
+#define DLPD_EPI_TMA 0               // tcgen05 epilogue: tiles arrive by TMA (one cp.async.bulk.tensor box + one bulk copy per tile,
+                                     // mbarrier) instead of the producer warps' cp.async.  Parity-green, measured on B200 and
+                                     // REJECTED: a tile is 2720 rows of 32 contiguous bytes and the TMA unit processes such short
+                                     // rows far below HBM speed -- epilogue 7.90 ms vs 3.48 ms per 32 rotations (profiles/r02e)
+#endif
+#ifndef DLPD_EPI_TC_EXTRA
+#define DLPD_EPI_TC_EXTRA 64         // tcgen05 epilogue: this many extra threads join the inverse-z transform passes (they do not score)
+#endif
 
 template <int S> struct LineMul {
     DLPD_DEV int operator()(int l) const { return l * S; }
@@ -1295,6 +1304,10 @@ template <int L_, int C0, int C1, int H> struct HiddenL1 {
 // second shared-memory buffer (cp.async) while the current tile is transformed and scored, so no load is exposed.
 // ------------------------------------------------------------------------------------------------------
 template <int C0, int C1, int H> struct EpiParams {
+    // TMA descriptor (CUtensorMap, 128 bytes) of the tiled S2 array viewed as a rank-5 fp32 tensor
+    //   (8 floats of a 2x2 tile, channel, kz', tile, pair): one box = all channels and kz' of one tile, landing in shared
+    // memory as [kz'][channel][8] -- exactly the line-interleaved layout the transform passes use.  Built by the host.
+    alignas(64) unsigned long long tmap[16];
     const cpx* s2_0;              // [P][C0+1][N][N/2][N/2][2][2]   (kz', x/2, y/2, y&1, x&1); channel C0 = clash
     const cpx* h1;                // [P][N1][N1][N1][H]
     unsigned long long* best;     // [n_rot] packed (score_key << 32 | linear index), pre-set to ~0
@@ -1333,9 +1346,13 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0> struct Epilog
     // warp specialisation: the last NPROD threads only issue the cp.async copies of the NEXT tile (each copy touches
     // its own cache line, so issuing them is slow -- but it now overlaps the transform of the current tile instead of
     // stalling every warp); the first NC threads transform and score
-    static constexpr int NPROD = (N >= 128) ? DLPD_EPI_NPROD : 32;
+    // USE_TMA (tcgen05 kernels): no producer threads at all -- thread 0 issues one tensor-map box load and one bulk copy per
+    // tile, completion is counted on an mbarrier; NX extra threads only help with the transform passes
+    static constexpr bool USE_TMA = TC_OK && (DLPD_EPI_TMA != 0);
+    static constexpr int NPROD = USE_TMA ? 0 : ((N >= 128) ? DLPD_EPI_NPROD : 32);
+    static constexpr int NX = (TC_OK && N >= 128) ? DLPD_EPI_TC_EXTRA : 0;
     static constexpr int NC = TC_OK ? 128 * NWG : ((N >= 128) ? DLPD_EPI_NT : 128) - NPROD;
-    static constexpr int NT = NC + NPROD;
+    static constexpr int NT = NC + NX + NPROD;
     static constexpr int BUF = N * NL0, HB = N1 * H;
 #if DLPD_EXPERIMENTAL
     static constexpr int MLP_BYTES = TC_ ? ((int)sizeof(MlpDev<C0, H>) + 15) / 16 * 16 : 0;      // shared-memory copy of the MMA fragments
@@ -1345,7 +1362,7 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0> struct Epilog
     // tcgen05: first-layer weights as the B operand, [hi | lo][C0 / 4 k-chunks][HP rows][4] TF32 (K-major, no swizzle),
     // then 2 mbarriers per warpgroup and the TMEM base address
     static constexpr int TC_BW = 2 * C0 * HP;                      // floats
-    static constexpr int TC_BYTES = TC_OK ? (TC_BW * 4 + 16 * 8 + 16) : 0;
+    static constexpr int TC_BYTES = TC_OK ? (TC_BW * 4 + 16 * 8 + 16) : 0;       // bars[0 .. 2 NWG) MMA, bars[14], bars[15] tile landed
     static constexpr bool PKT = DLPD_EPI_PACKED_TW && (N / (2 * LinePlan<N>::R0) > 1);      // packed twiddles of the inverse head pass
     static constexpr int SMEM = (2 * BUF + 2 * HB + N + (PKT ? N : 0)) * (int)sizeof(cpx) + 64 * 8 + MLP_BYTES + TC_BYTES;
     static constexpr int QPT = NPROD / TY;         // (c, kz) rows covered per sweep of the producer threads
@@ -1360,7 +1377,7 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0> struct Epilog
         const int pair = tile / TILES, r = tile % TILES;
         const int r4 = tile_xh(r) * T + (tile_y0(r) >> 1);              // 2x2 group (x/2) * T + (y/2) of the tiled S2
         const cpx* s = p.s2_0 + ((long)pair * (C0 + 1) * N * T * T + r4) * 4 + ((TY == 1) ? 2 * (tile_y0(r) & 1) : 0);
-        DLPD_FOR_TASKS_SUB(t, NPROD, NPROD, NC) {
+        DLPD_FOR_TASKS_SUB(t, NPROD, NPROD, NC + NX) {
             const int h = (TY == 2) ? (t & 1) : 0, q0 = t / TY;
             int c = q0 / N, kz = q0 % N;
             const cpx* src = s + ((long)q0 * (T * T) * 4 + 2 * h);      // q = c*N + kz: 16 TY contiguous bytes per row
@@ -1373,8 +1390,20 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0> struct Epilog
             }
         }
         const cpx* hs = p.h1 + ((long)pair * T * T + r4) * HB;          // level-1 column (x/2, y/2): N1*H contiguous
-        DLPD_FOR_TASKS_SUB(t, HB / 2, NPROD, NC) cp_async16(hb + 2 * t, hs + 2 * t);
+        DLPD_FOR_TASKS_SUB(t, HB / 2, NPROD, NC + NX) cp_async16(hb + 2 * t, hs + 2 * t);
     }
+
+#if !defined(DLPD_EMU)
+    // the same loads as ONE tensor-map box (all channels and kz' of the tile -> [kz'][c][8 floats]) and ONE bulk copy (the
+    // level-1 column), issued by a single thread; both complete on `bar`
+    static DLPD_DEV void issue_tma(const Params& p, int tile, cpx* b0, cpx* hb, uint64_t* bar) {
+        const int pair = tile / TILES, r = tile % TILES;
+        const int r4 = tile_xh(r) * T + (tile_y0(r) >> 1);
+        tc::mbar_expect_tx(bar, (uint32_t)((BUF + HB) * sizeof(cpx)));
+        tc::tma_load_5d(b0, p.tmap, bar, (TY == 1) ? 4 * (tile_y0(r) & 1) : 0, 0, 0, r4, pair);
+        tc::bulk_g2s(hb, p.h1 + ((long)pair * T * T + r4) * HB, (uint32_t)(HB * sizeof(cpx)), bar);
+    }
+#endif
 
     static DLPD_DEV void flush_best(const Params& p, int pair, unsigned long long bestA, unsigned long long bestB,
                                     unsigned long long* red) {
@@ -1640,6 +1669,8 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0> struct Epilog
         if (threadIdx.x < 32) tc::tmem_alloc(tmem_slot, TC_COLS);
         if (threadIdx.x == 0) {
             for (int i = 0; i < 2 * NWG; ++i) tc::mbar_init(bars + i, 1);
+            tc::mbar_init(bars + 14, 1);
+            tc::mbar_init(bars + 15, 1);
             tc::mbar_fence_init();
         }
         tc::fence_proxy_async();           // the weights were written with ordinary stores, the tensor core reads them through the async proxy
@@ -1766,6 +1797,45 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0> struct Epilog
             ts.bw_addr = tc::smem_u32(Bw);
         }
 #endif
+#if !defined(DLPD_EMU)
+        if constexpr (USE_TMA) {
+            // ---- TMA-fed loop: buffers are filled by the async proxy, "tile landed" is an mbarrier phase ----------------
+            uint64_t* full = ts.bars + 14;
+            unsigned long long bestA = ~0ull, bestB = ~0ull;
+            int cur_pair = -1, slot = 0;
+            uint32_t fullphase = 0;
+            const SubTeam<NC + NX> tmT{(int)threadIdx.x, 1};         // transform team (everybody)
+            const SubTeam<NC> tmS{(int)threadIdx.x, 1};             // scoring threads: one per translation
+            if (threadIdx.x == 0) {
+                tc::tma_prefetch_desc(p.tmap);
+                if (bx < p.n_tiles) issue_tma(p, bx, bufs, hbufs, full);
+            }
+            for (int tile = bx; tile < p.n_tiles; tile += p.grid, slot ^= 1) {
+                tc::fence_proxy_async();                     // my ordinary stores into the other buffer precede its async refill
+                __syncthreads();                             // everyone is done with the other buffer
+                const int pair = tile / TILES, r = tile % TILES;
+                if (pair != cur_pair) {
+                    if (cur_pair >= 0) flush_best(p, cur_pair, bestA, bestB, red);
+                    cur_pair = pair;
+                    bestA = bestB = ~0ull;
+                }
+                if (threadIdx.x == 0 && tile + p.grid < p.n_tiles)
+                    issue_tma(p, tile + p.grid, bufs + (slot ^ 1) * BUF, hbufs + (slot ^ 1) * HB, full + (slot ^ 1));
+                tc::mbar_wait(full + slot, (fullphase >> slot) & 1u);
+                fullphase ^= 1u << slot;
+                cpx* b0 = bufs + slot * BUF;
+                if constexpr (PKT) transform_tile_pk(tmT, b0, tw0, tw0 + N);
+                else transform_tile(tmT, b0, tw0);
+                if (threadIdx.x < NC)
+                    score_voxels_tc(p, tmS, b0, hbufs + slot * HB, ts, pair, 2 * tile_xh(r), tile_y0(r), bestA, bestB);
+            }
+            if (cur_pair >= 0) flush_best(p, cur_pair, bestA, bestB, red);
+            tc::fence_before_sync();
+            __syncthreads();
+            if (threadIdx.x < 32) tc::tmem_dealloc(ts.tmem_base, TC_COLS);
+            return;
+        }
+#endif
         if (bx < p.n_tiles) issue_loads(p, bx, bufs, hbufs);
         cp_async_commit();
         cp_async_wait_pending();
@@ -1776,7 +1846,8 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0> struct Epilog
         const bool producer = true, consumer = true;   // one emulated thread plays both roles, copies complete at once
 #else
         const SubTeam<NC, DLPD_EPI_DUAL != 0> tm{(int)threadIdx.x, 1};
-        const bool producer = threadIdx.x >= NC, consumer = !producer;
+        const SubTeam<NC + NX, DLPD_EPI_DUAL != 0> tmT{(int)threadIdx.x, 1};     // transform team: the scoring threads + NX helpers
+        const bool producer = threadIdx.x >= NC + NX, consumer = !producer;
 #endif
         for (int tile = bx; tile < p.n_tiles; tile += p.grid, slot ^= 1) {
             DLPD_SYNC();                               // this tile has landed; everyone is done with the other buffer
@@ -1797,9 +1868,10 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0> struct Epilog
 #if !defined(DLPD_EMU)
                 if constexpr (TC_OK) {
                     cpx* b0 = bufs + slot * BUF;
-                    if constexpr (PKT) transform_tile_pk(tm, b0, tw0, tw0 + N);
-                    else transform_tile(tm, b0, tw0);
-                    score_voxels_tc(p, tm, b0, hbufs + slot * HB, ts, pair, 2 * tile_xh(r), tile_y0(r), bestA, bestB);
+                    if constexpr (PKT) transform_tile_pk(tmT, b0, tw0, tw0 + N);
+                    else transform_tile(tmT, b0, tw0);
+                    if (threadIdx.x < NC)
+                        score_voxels_tc(p, tm, b0, hbufs + slot * HB, ts, pair, 2 * tile_xh(r), tile_y0(r), bestA, bestB);
                 } else
 #endif
                 score_tile(p, tm, bufs + slot * BUF, hbufs + slot * HB, tw0, ms, pair, 2 * tile_xh(r), tile_y0(r), bestA, bestB);

@@ -41,12 +41,23 @@ def gather_best(local_best: torch.Tensor, n_rot: int, rank: int, world: int, gro
 
 def merge_top_lists(local_top: Sequence[Tuple[int, int, int, int, float]], K: int, group=None) -> List[tuple]:
     """All-gather every rank's top list and reproduce the reference ordering (Docker.py:100-105): ascending score,
-    ties in rotation-file order (the order a single process would have appended them in)."""
+    ties in rotation-file order (the order a single process would have appended them in).
+
+    One fixed-size tensor collective (`all_gather_into_tensor` of [K,5] float64 rows (rot, x, y, z, score), +inf padded) --
+    no pickling, same call on nccl and gloo."""
     if not dist.is_initialized() or dist.get_world_size(group) == 1:
         return list(local_top)[:K]
-    gathered: list = [None] * dist.get_world_size(group)
-    dist.all_gather_object(gathered, list(local_top), group=group)
-    merged = [t for part in gathered for t in part]
+    world = dist.get_world_size(group)
+    dev = torch.device("cuda", torch.cuda.current_device()) if dist.get_backend(group) == "nccl" else torch.device("cpu")
+    buf = torch.full((K, 5), float("inf"), dtype=torch.float64)
+    rows = sorted(local_top, key=lambda t: (t[4], t[0]))[:K]          # a rank can contribute at most K of the global K
+    if rows:
+        buf[:len(rows)] = torch.tensor(rows, dtype=torch.float64)
+    buf = buf.to(dev)
+    out = torch.empty(world * K, 5, dtype=torch.float64, device=dev)
+    dist.all_gather_into_tensor(out, buf, group=group)
+    out = out.cpu()
+    merged = [(int(r[0]), int(r[1]), int(r[2]), int(r[3]), float(r[4])) for r in out.tolist() if r[0] != float("inf")]
     merged.sort(key=lambda t: (t[4], t[0]))
     return merged[:K]
 

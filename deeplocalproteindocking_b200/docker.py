@@ -10,8 +10,8 @@ supplied to accept paths like the reference does.
 """
 from __future__ import annotations
 
-import atexit
 import os
+import weakref
 from dataclasses import dataclass
 from typing import Callable, List, Optional, Tuple
 
@@ -105,8 +105,9 @@ class Docker:
                  rot_batch: int = 16, center: str = "grid", clash_source: str = "project",
                  pdb_loader: Optional[Callable[[str], Atoms]] = None, device=None, generator=None, verbose=False):
         """Reference arguments first (Docker.py:18); then: `rot_batch` rotations per fused call, rotation `center`
-        convention, `clash_source` = 'project' (re-project rotated atoms, Docker.py:221-224) or 'rotate' (rotate the
-        summed ligand density with the feature volumes)."""
+        convention ('grid' = what TorchProteinLibrary's grid_sample-based VolumeRotation does, default; 'box' opt-in),
+        `clash_source` = 'project' (re-project rotated atoms, Docker.py:221-224) or 'rotate' (rotate the summed ligand
+        density with the feature volumes)."""
         self.docking_model = docking_model
         self.log = None
         self.box_size, self.resolution = int(box_size), float(resolution)
@@ -126,7 +127,30 @@ class Docker:
         self.top_list: list = []
         self.best_per_rotation: Optional[torch.Tensor] = None
         self._engine: Optional[DockingSearch] = None
-        atexit.register(self.cleanup)
+        self._engine_key = None
+        # The reference registers `cleanup` with atexit (Docker.py:47), which would keep every Docker -- and the multi-GB
+        # device workspace of its search plan -- alive until interpreter exit.  A finalizer on the state that needs
+        # closing does the same job without pinning the object.
+        self._state = {"log": None, "engine": None}
+        self._finalizer = weakref.finalize(self, Docker._release, self._state)
+
+    @staticmethod
+    def _release(state):
+        if state.get("log") is not None:
+            state["log"].close()
+            state["log"] = None
+        if state.get("engine") is not None:
+            state["engine"].close()
+            state["engine"] = None
+
+    def close(self):
+        """Close the log file and free the search plan's device memory (the object stays usable: a new plan is created on
+        the next dock call)."""
+        self.cleanup()
+        if self._engine is not None:
+            self._engine.close()
+        self._engine = self._engine_key = None
+        self._state["engine"] = None
 
     # ---- log handling: same resume rule as Docker.new_log (Docker.py:63-80) -----------------------------------
     def new_log(self, log_file_name, rewrite=True):
@@ -139,12 +163,14 @@ class Docker:
             if n_lines > 1:
                 return False
         self.log = open(log_file_name, "w")
+        self._state["log"] = self.log
         return True
 
     def cleanup(self):
         if self.log is not None:
             self.log.close()
             self.log = None
+        self._state["log"] = None
 
     # ---- set-up (Docker.py:190-209) ----------------------------------------------------------------------
     def _atoms(self, protein) -> Atoms:
@@ -178,6 +204,7 @@ class Docker:
             self._engine = DockingSearch(self.box_size, (key[1], key[2]), hidden, max_rot=self.rot_batch,
                                          center=self.center, device=self.device)
             self._engine_key = key
+            self._state["engine"] = self._engine
         return self._engine
 
     # ---- the search ----------------------------------------------------------------------------------------
@@ -196,37 +223,53 @@ class Docker:
             lig_vols, lig_density = self._volumes(Atoms(lig.coords + self.box_center, lig.types))
             eng = self._engine_for(rec_vols)
             eng.set_receptor(rec_vols, rec_forbidden)
-            eng.set_ligand(lig_vols, lig_density if self.clash_source == "rotate" else None)
+            project = self.clash_source == "project"
+            eng.set_ligand(lig_vols, None if project else lig_density)
+            if project:          # per-rotation clash volumes re-projected inside the library (Docker.py:221-224)
+                eng.set_ligand_atoms(lig.coords, self.resolution)
             eng.set_filter(self.docking_model.filter)
             tau = float(self.docking_model.threshold_clash)
             rot_idx = torch.arange(len(self.rot)) if rotation_subset is None else torch.as_tensor(rotation_subset)
-            lig_dev = lig.coords.to(self.device)
             best_all = torch.empty(rot_idx.numel(), 4, device=self.device)
             want_topk = self.max_conf > 1
             N = 2 * self.box_size
-            self.exact_batches = self.candidate_batches = 0              # how the top-K list was maintained (diagnostics)
+            # how the top-K list was maintained (diagnostics): batches replayed exactly on a score volume, batches served by the
+            # epilogue's candidate list at the current K-th score, batches whose threshold had to be bootstrapped by probing,
+            # candidate-buffer overflows (each costs one exact replay) and threshold probes (one fused search each)
+            self.exact_batches = self.candidate_batches = self.bootstrap_batches = self.overflow_batches = self.probe_searches = 0
+            cap = max(4 * self.max_conf, 1 << 14)
             for i0 in range(0, rot_idx.numel(), self.rot_batch):
                 sel = rot_idx[i0:i0 + self.rot_batch]
                 Rb = self.rot.R[sel].to(self.device)                     # float64, like r_batch_cpu (Docker.py:214)
-                clash_rot = None
-                if self.clash_source == "project":
-                    clash_rot = project_clash_rotated(lig_dev, Rb, self.box_size, self.resolution)
                 best = None
                 # Top-K maintenance (Docker.py:86-105).  Once the list is full and its K-th score is negative, only
                 # translations scoring <= that value can enter it: the fused epilogue lists exactly those and the score
                 # volume is never written.  Until then (and if a batch overflows the candidate buffer) the batch is
                 # scored into a volume and the reference's extraction loop is replayed on it.
                 kth = self.top_list[-1][4] if (want_topk and len(self.top_list) == self.max_conf) else None
+                Rq = Rb if project else Rb.to(torch.float32)
                 if want_topk and kth is not None and kth < 0.0:
-                    best, cand, total = eng.search_candidates(Rb.to(torch.float32), kth, tau, clash_rot,
-                                                              capacity=max(4 * self.max_conf, 1 << 14))
+                    best, cand, total = eng.search_candidates(Rq, kth, tau, None, capacity=cap, use_atoms=project)
                     if total <= cand.shape[0]:
                         self._merge_candidates(cand.cpu(), sel, N)
                         self.candidate_batches += 1
                     else:
                         best = None
+                        self.overflow_batches += 1
+                elif want_topk:
+                    # list not full yet (first batch): no threshold is known.  Bisect one on the device instead of writing and
+                    # sorting rot_batch x (2L)^3 score volumes: a threshold theta < 0 with K <= #{V <= theta} <= capacity makes
+                    # the candidate list a superset of the batch's K best translations (Docker.py:100-105 keeps K).
+                    found = self._bootstrap_threshold(eng, Rq, tau, project, cap)
+                    if found is not None:
+                        best, cand = found
+                        self._merge_candidates(cand.cpu(), sel, N)
+                        self.bootstrap_batches += 1
                 if best is None:
-                    best, scores = eng.search(Rb.to(torch.float32), tau, clash_rot, return_scores=want_topk)
+                    if project:
+                        best, scores = eng.search_atoms(Rb, tau, return_scores=want_topk)
+                    else:
+                        best, scores = eng.search(Rb.to(torch.float32), tau, None, return_scores=want_topk)
                     if want_topk:
                         self.exact_batches += 1
                         for j, r in enumerate(sel.tolist()):
@@ -240,6 +283,30 @@ class Docker:
                 self.top_list = items[:self.max_conf]
         if write:
             self.write_conformations()
+
+    def _bootstrap_threshold(self, eng, Rq, tau, project, cap, max_probes: int = 14):
+        """Find theta in (min score of the batch, 0) whose candidate list has between K - len(list) ... cap entries; every probe
+        is one fused search (no score volume).  None if the batch has fewer negative scores than needed (the caller then
+        replays the reference's extraction loop on a score volume, zeros and duplicates included)."""
+        need = self.max_conf
+        best = (eng.search_atoms(Rq, tau) if project else eng.search(Rq, tau))[0]
+        self.probe_searches += 1
+        lo = float(best[:, 0].min())                     # count(lo) >= 1
+        if not lo < 0.0:
+            return None
+        hi, theta = 0.0, 0.5 * lo
+        for _ in range(max_probes):
+            best, cand, total = eng.search_candidates(Rq, theta, tau, None, capacity=cap, use_atoms=project)
+            self.probe_searches += 1
+            if need <= total <= cand.shape[0]:
+                return best, cand
+            if total < need:
+                lo, theta = theta, 0.5 * (theta + hi)    # too few: move towards 0
+                if theta > -1e-30:
+                    return None                          # fewer than K negative scores in the whole batch
+            else:
+                hi, theta = theta, 0.5 * (theta + lo)    # too many for the buffer: move towards the minimum
+        return None
 
     def _merge_candidates(self, cand: torch.Tensor, sel: torch.Tensor, N: int):
         """Merge (score, position in `sel`, linear index) candidates into the global list: same order as appending each

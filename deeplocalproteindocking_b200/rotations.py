@@ -8,11 +8,15 @@ Host-side mirror of the reference's `Rotations` class
 Differences, all documented in DESIGN.md:
   * the reference builds the file name with `'oim%d.eul'` so only 20/15/12/10 load
     (`Rotations.py:39`); here 8 and 6 load too and any explicit `.eul` path works;
-  * the six published sets ship in factorised form (`data/soi_axes.json`, see
+  * the six published sets ship in factorised form (`deeplocalproteindocking_b200/data/soi_axes.json`, see
     `tools/pack_soi.py`) and are rebuilt to the exact decimal values of the tables;
-  * `angle_inc=4` (`oim04.eul`, a missing blob in the reference snapshot) is a
-    deterministic surrogate: 2578 Fibonacci-lattice axes x 90 in-plane angles
-    = 232 020 rotations, same 3-column format.
+  * `angle_inc=4`: `oim04.eul` is a missing blob in the reference snapshot, so -- like
+    the reference, which raises "Can't find rotation angles" when the file is absent --
+    `Rotations(4)` raises.  `Rotations(4, allow_surrogate=True)` (or
+    `angle_inc="fibonacci4"`) opts into a deterministic SURROGATE of the same size:
+    2578 Fibonacci-lattice axes x 90 in-plane angles = 232 020 rotations, same
+    3-column format.  It is NOT the published 4-degree SOI set and is labelled as a
+    surrogate wherever it is used (bench.py configs 3 and 5).
 """
 from __future__ import annotations
 
@@ -24,7 +28,7 @@ from functools import lru_cache
 import numpy as np
 import torch
 
-_DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), os.pardir, "data")
+_DATA_DIR = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")      # package data: travels with an installed package
 SOI_SIZES = {20: 1854, 15: 4392, 12: 8580, 10: 14868, 8: 29025, 6: 68760, 4: 232020}
 _SURROGATE_AXES = {4: 2578}
 
@@ -47,11 +51,11 @@ def _fibonacci_axes(m: int) -> np.ndarray:
     return np.stack([theta, psi], axis=1)
 
 
-def soi_euler_angles(angle_inc: int) -> np.ndarray:
+def soi_euler_angles(angle_inc: int, allow_surrogate: bool = False) -> np.ndarray:
     """`[N,3]` float64 (phi, theta, psi) radians, in the file order of `oim<inc>.eul`.
 
     Values are the 6-decimal numbers of the text tables (phi fastest, from -pi in
-    steps of `angle_inc` degrees)."""
+    steps of `angle_inc` degrees).  Sets that are not shipped raise unless `allow_surrogate`."""
     angle_inc = int(angle_inc)
     if 360 % angle_inc:
         raise Exception("Can't find rotation angles:", angle_inc)
@@ -60,7 +64,7 @@ def soi_euler_angles(angle_inc: int) -> np.ndarray:
     axes = _soi_axes().get(str(angle_inc))
     if axes is not None:
         tp = np.array([[float(t), float(p)] for t, p in axes], dtype=np.float64)
-    elif angle_inc in _SURROGATE_AXES:
+    elif angle_inc in _SURROGATE_AXES and allow_surrogate:
         tp = _fibonacci_axes(_SURROGATE_AXES[angle_inc])
         tp = np.array([[float("%f" % t), float("%f" % p)] for t, p in tp])
     else:
@@ -117,10 +121,15 @@ def euler_to_matrix(angles) -> torch.Tensor:
 class Rotations(object):
     """Drop-in for `src.Utils.Rotations` (`Rotations.py:8-66`): `.R` is `[N,3,3]` float64 on CPU.
 
-    `angle_inc` may be one of 20/15/12/10/8/6 (shipped sets), 4 (surrogate) or a path to
-    an `.eul` file.  `verbose` keeps the reference's two print lines."""
+    `angle_inc` may be one of 20/15/12/10/8/6 (shipped sets) or a path to an `.eul` file; 4 raises like the
+    reference does for a missing table unless `allow_surrogate=True` / `angle_inc="fibonacci4"` asks for the labelled
+    surrogate.  `verbose` keeps the reference's two print lines."""
 
-    def __init__(self, angle_inc=12, verbose=False):
+    def __init__(self, angle_inc=12, verbose=False, allow_surrogate=False):
+        self.surrogate = False
+        if angle_inc == "fibonacci4":
+            angle_inc, allow_surrogate = 4, True
+        self.allow_surrogate = bool(allow_surrogate)
         self.loadSOI(angle_inc)
         if verbose:
             print("Angle increment:", angle_inc)
@@ -135,7 +144,8 @@ class Rotations(object):
             inc = int(angle_inc)
             if inc != angle_inc or inc not in SOI_SIZES:
                 raise Exception("Can't find rotation angles:", angle_inc)
-            self.angles = soi_euler_angles(inc)
+            self.angles = soi_euler_angles(inc, self.allow_surrogate)
+            self.surrogate = inc in _SURROGATE_AXES
             assert self.angles.shape[0] == SOI_SIZES[inc]
         self.R = euler_to_matrix(self.angles)
 

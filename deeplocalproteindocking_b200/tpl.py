@@ -8,8 +8,11 @@ unmodified on the sm_100a operators:
                                        TypedCoords2Volume                 -> plain PyTorch (north_star: outside the loop)
     TorchProteinLibrary.FullAtomModel  CoordsTransform.{CoordsRotate, CoordsTranslate}, CoordsRotate, CoordsTranslate,
                                        getBBox, getRandomRotation          -> float64 CPU tensors like TorchProteinLibrary's
-                                       PDB2CoordsUnordered, Coords2TypedCoords -> NOT provided (PDB parsing and the 11-type
-                                       atom typing table are outside the search path; they raise with that message)
+                                       PDB2CoordsUnordered, Coords2TypedCoords -> SYNTHETIC stand-ins: a "file name" is the
+                                       name of a registered synthetic protein (`register_synthetic`) or a spec
+                                       "synthetic:<n_atoms>:<radius>:<seed>"; they return tensors of the same shapes and
+                                       dtypes as TorchProteinLibrary's (PDB parsing and the 11-type typing table are outside
+                                       the search path: a real path raises with that message)
     _Volume                            Volume2Xplor (debug writer, VolumeViz.py:31) -> X-PLOR text map
 
 Conventions follow the call sites: coords [B, 3*Nmax] float64 on the CPU, num_atoms [B] int, R [B,3,3], T [B,3];
@@ -75,24 +78,79 @@ def getRandomRotation(batch_size: int) -> torch.Tensor:
         torch.stack([2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)], 1)], 1)
 
 
-class _NotProvided(nn.Module):
-    what = "this TorchProteinLibrary operator"
-
-    def __init__(self, *args, **kwargs):
-        super().__init__()
-
-    def forward(self, *args, **kwargs):
-        raise NotImplementedError(
-            "%s is outside the docking search path and is not provided by deeplocalproteindocking_b200; use "
-            "TorchProteinLibrary's own, or pass atoms directly (deeplocalproteindocking_b200.Docker(pdb_loader=...))" % self.what)
+# ---- synthetic stand-ins for the PDB reader and the atom typer (Docker.py:37-38, 51-52) ----------------------------
+NUM_ATOM_TYPES = 11
+_SYNTHETIC = {}
 
 
-class PDB2CoordsUnordered(_NotProvided):
-    what = "PDB2CoordsUnordered (PDB parsing)"
+def register_synthetic(name: str, coords: torch.Tensor, types: torch.Tensor) -> None:
+    """Make `name` loadable by `PDB2CoordsUnordered`: coords [Nat,3] Angstrom, types [Nat] in 0..10."""
+    _SYNTHETIC[name] = (torch.as_tensor(coords, dtype=torch.float64).reshape(-1, 3).clone(),
+                        torch.as_tensor(types, dtype=torch.int64).reshape(-1).clone())
 
 
-class Coords2TypedCoords(_NotProvided):
-    what = "Coords2TypedCoords (the 11-type atom typing table)"
+def _synthetic_protein(name: str):
+    if name in _SYNTHETIC:
+        return _SYNTHETIC[name]
+    if isinstance(name, str) and name.startswith("synthetic:"):
+        from .synthetic import random_protein
+        try:
+            _, n, radius, seed = name.split(":")
+            atoms = random_protein(int(n), float(radius), int(seed))
+        except ValueError:
+            raise Exception("bad synthetic protein spec (synthetic:<n_atoms>:<radius>:<seed>)", name)
+        return atoms.coords, atoms.types
+    raise NotImplementedError(
+        "PDB2CoordsUnordered: %r is not a registered synthetic protein -- PDB parsing is outside the docking search path and "
+        "is not provided by deeplocalproteindocking_b200 (use TorchProteinLibrary's reader, tpl.register_synthetic, or pass "
+        "atoms directly to deeplocalproteindocking_b200.Docker)" % (name,))
+
+
+class PDB2CoordsUnordered(nn.Module):
+    """Stand-in with TorchProteinLibrary's return signature (Docker.py:51):
+    `(coords [B,3 Nmax] float64, chains [B,Nmax] uint8, resnames [B,Nmax,4] uint8, resnums [B,Nmax] int32,
+    atomnames [B,Nmax,4] uint8, num_atoms [B] int32)`, all on the CPU, padded with zeros.  The synthetic atom TYPE travels
+    in `atomnames[..., 0]` (there are no real residue / atom names to type from)."""
+
+    def forward(self, filenames):
+        prots = [_synthetic_protein(f) for f in filenames]
+        B, nmax = len(prots), max(p[0].shape[0] for p in prots)
+        coords = torch.zeros(B, 3 * nmax, dtype=torch.float64)
+        chains = torch.zeros(B, nmax, dtype=torch.uint8)
+        resnames = torch.zeros(B, nmax, 4, dtype=torch.uint8)
+        resnums = torch.zeros(B, nmax, dtype=torch.int32)
+        atomnames = torch.zeros(B, nmax, 4, dtype=torch.uint8)
+        num_atoms = torch.zeros(B, dtype=torch.int32)
+        for b, (c, t) in enumerate(prots):
+            n = c.shape[0]
+            coords[b, :3 * n] = c.reshape(-1)
+            chains[b, :n] = ord("A")
+            resnums[b, :n] = torch.arange(n, dtype=torch.int32) // 8 + 1
+            atomnames[b, :n, 0] = t.to(torch.uint8)
+            num_atoms[b] = n
+        return coords, chains, resnames, resnums, atomnames, num_atoms
+
+
+class Coords2TypedCoords(nn.Module):
+    """Stand-in with TorchProteinLibrary's return signature (Docker.py:52): atoms stably sorted by type,
+    `(coords [B,3 Nmax] float64, num_atoms_of_type [B,11] int32, offsets [B,11] int32)`."""
+
+    def forward(self, coords, resnames, atomnames, num_atoms):
+        B, nmax = coords.shape[0], coords.shape[1] // 3
+        out = torch.zeros_like(coords)
+        nat = torch.zeros(B, NUM_ATOM_TYPES, dtype=torch.int32)
+        off = torch.zeros(B, NUM_ATOM_TYPES, dtype=torch.int32)
+        for b in range(B):
+            n = int(num_atoms[b])
+            t = atomnames[b, :n, 0].to(torch.int64)
+            if n and int(t.max()) >= NUM_ATOM_TYPES:
+                raise Exception("atom type out of range", int(t.max()))
+            order = torch.argsort(t, stable=True)
+            out[b, :3 * n] = coords[b].reshape(nmax, 3)[:n][order].reshape(-1)
+            counts = torch.bincount(t, minlength=NUM_ATOM_TYPES)[:NUM_ATOM_TYPES]
+            nat[b] = counts.to(torch.int32)
+            off[b] = (torch.cumsum(counts, 0) - counts).to(torch.int32)
+        return out, nat, off
 
 
 def Volume2Xplor(volume: torch.Tensor, filename: str, resolution: float) -> None:

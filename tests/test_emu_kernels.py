@@ -323,3 +323,78 @@ def test_emu_search_80_one_rotation_matches_oracle():
                      lig_clash.double(), Rs, filt.to(torch.float64), 30.0, K=0)
     assert torch.equal(best[:, 1:].double(), want[:, 1:])
     assert torch.allclose(best[:, 0].double(), want[:, 0], rtol=1e-4, atol=1e-6)
+
+
+# ---- round 2: in-library clash re-projection from atoms, typed projector, per-plan options ---------------------------
+def test_emu_search_atoms_equals_explicit_clash_volumes_and_oracle():
+    """dlpd_search_atoms (float64 matrices in; fp32 cast + re-projection of the rotated atoms chunk by chunk inside the
+    library, Docker.py:214-224) == dlpd_search fed with dlpd_project_clash volumes == the oracle; host-buffer entry too."""
+    L, C0, C1, H, res = 8, 4, 6, 5, 1.25
+    rec, lig, rf, _ = _case(L, C0, C1, seed=31)
+    g = torch.Generator().manual_seed(32)
+    atoms = (torch.rand(40, 3, generator=g, dtype=torch.float64) - 0.5) * 6.0
+    filt = O.FilterWeights.random(C0 + C1, H, seed=33)
+    Rs = R20[[2, 222, 1222]]
+    tau = 1.0
+    plan = emu.EmuPlan(L, C0, C1, H, max_rot=2)
+    try:
+        plan.set_receptor(rec[0][0], rec[1][0], rf[0, 0])
+        plan.set_ligand(lig[0][0], lig[1][0], None)
+        plan.set_filter(filt.W1, filt.b1, filt.W2, filt.b2)
+        with pytest.raises(Exception, match="dlpd_set_ligand_atoms"):
+            plan.search_atoms(Rs, tau)
+        plan.set_ligand_atoms(atoms, res)
+        best, scores = plan.search_atoms(Rs, tau, want_scores=True)
+        clash = emu.project_clash(atoms, Rs, L, res)
+        best2, _ = plan.search(Rs.float(), tau, clash_rot=clash)
+        best3 = plan.search_host_atoms(Rs, tau)
+    finally:
+        plan.close()
+    assert torch.equal(best, best2) and torch.equal(best, best3)
+    spectra = O.ReceptorSpectra([r.double() for r in rec], rf.double())
+    for i in range(3):
+        c = O.ligand_clash_volume(atoms, Rs[i], L, res).double()
+        V = O.score_rotation(spectra, [l.double() for l in lig], c, Rs[i], filt.to(torch.float64), tau, ligand_forbidden_is_rotated=True)
+        s, x, y, z = O.best_pose(V)
+        assert [int(v) for v in best[i, 1:]] == [x, y, z]
+        assert abs(float(best[i, 0]) - s) <= 1e-4 * max(abs(s), 1e-3 * float(V.abs().max()))
+
+
+def test_emu_project_typed_matches_torch_path():
+    from deeplocalproteindocking_b200 import TypedCoords2Volume
+    from deeplocalproteindocking_b200.docker import Atoms, typed_layout
+    L, res = 10, 1.25
+    g = torch.Generator().manual_seed(5)
+    coords = (torch.rand(60, 3, generator=g, dtype=torch.float64) - 0.2) * 14.0
+    types = torch.randint(0, 11, (60,), generator=g)
+    c, nat, off = typed_layout(Atoms(coords.float(), types), "cpu")
+    want = TypedCoords2Volume(L, res)(c, nat, off)
+    got = emu.project_typed(c, nat, off, L, res)
+    assert (got - want).abs().max() <= 2e-6 * max(1.0, float(want.abs().max()))
+
+
+def test_emu_options_belong_to_the_plan():
+    """dlpd_set_option only seeds new plans; dlpd_plan_set_option changes one plan; a plane-mode switch after set_receptor is an
+    error (the spectra are laid out for the other kernel), not a silent corruption."""
+    L, C0, C1, H = 16, 4, 6, 5
+    rec, lig, rf, lf = _case(L, C0, C1, seed=41)
+    filt = O.FilterWeights.random(C0 + C1, H, seed=42)
+    Rs = R20[[7, 700]]
+    a = emu.EmuPlan(L, C0, C1, H)
+    emu.set_option(emu.OPT_PLANE_MODE, emu.PLANE_CLUSTER)        # default for plans created from now on
+    b = emu.EmuPlan(L, C0, C1, H)
+    emu.set_option(emu.OPT_PLANE_MODE, emu.PLANE_AUTO)
+    try:
+        out = []
+        for p in (a, b):
+            p.set_receptor(rec[0][0], rec[1][0], rf[0, 0]); p.set_ligand(lig[0][0], lig[1][0], lf)
+            p.set_filter(filt.W1, filt.b1, filt.W2, filt.b2)
+            out.append(p.search(Rs, 3.0)[0])
+        assert torch.equal(out[0][:, 1:], out[1][:, 1:]) and torch.allclose(out[0][:, 0], out[1][:, 0], rtol=2e-5, atol=1e-6)
+        a.set_option(emu.OPT_PLANE_MODE, emu.PLANE_CLUSTER)
+        with pytest.raises(Exception, match="plane mode"):
+            a.search(Rs, 3.0)
+        a.set_option(emu.OPT_PLANE_MODE, emu.PLANE_SINGLE)
+        assert torch.equal(a.search(Rs, 3.0)[0], out[0])
+    finally:
+        a.close(); b.close()

@@ -53,15 +53,16 @@ def test_docksE3_matches_oracle_loop(clash_source, max_conf, tmp_path):
 
 
 def test_dockSE3_topk_candidates_path_matches_oracle_loop(tmp_path):
-    """max_conf = 300 over 12 rotations in batches of 4: the first batch fills the list through score volumes, the later
-    ones through the epilogue's candidate lists (no score volume) -- same top list as the reference's extraction loop."""
+    """max_conf = 300 over 12 rotations in batches of 4: the first batch fills the list through a bisected threshold (or, if
+    the batch has too few negative scores, through score volumes), the later ones through the epilogue's candidate lists at
+    the current K-th score (no score volume) -- same top list as the reference's extraction loop."""
     L, res, K = 20, 1.25, 300
     model = _model(1)
     rec, lig = synthetic.config_pair(L, seed=5)
     docker = Docker(model, angle_inc=20, box_size=L, resolution=res, max_conf=K, rot_batch=4, clash_source="rotate", device=DEV)
     subset = torch.arange(0, 1854, 160)
     docker.dockSE3(rec, lig, batch_size=2, rotation_subset=subset)
-    assert docker.candidate_batches >= 1 and docker.exact_batches >= 1
+    assert docker.candidate_batches >= 1 and docker.exact_batches + docker.bootstrap_batches >= 1
     with torch.no_grad():
         rc, lc = rec.centred(), lig.centred()
         rv, rf = docker._volumes(Atoms(rc.coords + docker.box_center, rc.types))

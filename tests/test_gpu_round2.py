@@ -1,0 +1,320 @@
+"""GPU parity tests added in round 2: the benchmark's own inputs, pair switching, adversarial volumes, 128^3 with more
+rotations, the in-library clash re-projection, the CUDA typed projector, per-plan options and the reference's dockSE3 call
+sequence on the TorchProteinLibrary stand-ins.  Tolerances as in test_gpu_parity.py (BASELINE.json north_star): indices exact
+unless the fp64 oracle calls the two translations a tie; scores |s - s_ref| <= 1e-4 max(|s_ref|, 1e-3 max|V|)."""
+import os
+import sys
+
+import pytest
+import torch
+
+from oracle import docking_oracle as O
+from deeplocalproteindocking_b200 import (DockingSearch, Docker, GlobalDockingModel, SimpleFilter, E3MultiResRepr4x4,
+                                          TypedCoords2Volume, rotations, synthetic, tpl, _lib)
+from deeplocalproteindocking_b200.volume import project_clash_rotated
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda:0"
+R20 = rotations.Rotations(20).R
+R10 = rotations.Rotations(10).R
+
+
+def _d(t):
+    return t.detach().double().cpu()
+
+
+def _filter_weights(filt):
+    return O.FilterWeights(_d(filt.fc[0].weight), _d(filt.fc[0].bias), _d(filt.fc[2].weight), _d(filt.fc[2].bias))
+
+
+def _check_pose(best_row, V, tol=1e-4):
+    """best_row = (score, x, y, z) of the CUDA path against the fp64 score volume V of the oracle."""
+    s, x, y, z = O.best_pose(V)
+    scale = max(abs(s), 1e-3 * float(V.abs().max()))
+    got = [int(v) for v in best_row[1:]]
+    if got != [x, y, z]:
+        alt = float(V[got[0], got[1], got[2]])
+        assert abs(alt - s) <= tol * scale, ("index mismatch that is not a tie", best_row, (s, x, y, z), alt)
+    assert abs(float(best_row[0]) - s) <= tol * scale, (best_row, s)
+
+
+def test_bench_inputs_80_reprojected_clash_32_rotations():
+    """The benchmark's own problem (bench.build_problem: synthetic atoms -> Gaussian densities -> random-init E3MultiResRepr4x4
+    -> 16@80^3 + 32@40^3, xavier SimpleFilter, tau = 300) with the per-rotation RE-PROJECTED clash volumes of
+    Docker.py:221-224: 32 seeded oim10 rotations (16 packed pairs + chunking over max_rot = 12) vs the fp64 oracle, through
+    dlpd_search_atoms; the explicit-clash entry point and the host-buffer entry point must give the same bits."""
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if root not in sys.path:
+        sys.path.insert(0, root)
+    import bench
+    L = 80
+    rec_vols, rec_clash, lig_vols, lig_coords, filt = bench.build_problem(torch.device(DEV))
+    g = torch.Generator().manual_seed(2024)
+    idx = torch.sort(torch.randperm(R10.shape[0], generator=g)[:32]).values
+    Rs = R10[idx]
+    eng = DockingSearch(L, (16, 32), 24, max_rot=12, device=DEV)
+    eng.set_receptor(rec_vols, rec_clash); eng.set_ligand(lig_vols, None); eng.set_filter(filt)
+    eng.set_ligand_atoms(lig_coords, 1.25)
+    best, _ = eng.search_atoms(Rs, bench.TAU)
+    clash = project_clash_rotated(lig_coords.to(DEV), Rs.to(DEV), L, 1.25)
+    best2, _ = eng.search(Rs.float(), bench.TAU, ligand_forbidden_rotated=clash)
+    best3 = eng.search_host_atoms(Rs, bench.TAU)
+    eng.close()
+    best = best.cpu()
+    assert torch.equal(best, best2.cpu()) and torch.equal(best, best3)
+    spectra = O.ReceptorSpectra([_d(v)[None] for v in rec_vols], _d(rec_clash)[None, None])
+    f64, ligs = _filter_weights(filt), [_d(v)[None] for v in lig_vols]
+    n_masked = 0
+    for i in range(Rs.shape[0]):
+        c = O.ligand_clash_volume(lig_coords.cpu(), Rs[i], L, 1.25).double()
+        V = O.score_rotation(spectra, ligs, c, Rs[i], f64, bench.TAU, ligand_forbidden_is_rotated=True)
+        n_masked += int((V == 0).sum())
+        _check_pose(best[i], V)
+    assert n_masked > 0                                   # the clash mask is active on this problem
+
+
+def test_pair_switch_on_one_plan_matches_fresh_plans():
+    """BASELINE config 4: many pairs through ONE plan (set_receptor / set_ligand per pair).  Two pairs alternating A, B, A, B:
+    every visit must give exactly what a fresh plan gives for that pair, and pair B matches the fp64 oracle."""
+    L, C0, C1 = 80, 16, 32
+    filt = O.FilterWeights.random(C0 + C1, seed=77)
+    pairs = []
+    for k in range(2):
+        rec, rc = synthetic.learned_volumes(L, (C0, C1), seed=100 + 2 * k)
+        lig, lc = synthetic.learned_volumes(L, (C0, C1), seed=101 + 2 * k)
+        pairs.append((rec, rc, lig, lc))
+    Rs = [R20[[11, 500, 1200]], R20[[12, 900, 1800]]]
+    fresh = []
+    for k in range(2):
+        e = DockingSearch(L, (C0, C1), max_rot=4, device=DEV)
+        e.set_receptor(pairs[k][0], pairs[k][1]); e.set_ligand(pairs[k][2], pairs[k][3]); e.set_filter((filt.W1, filt.b1, filt.W2, filt.b2))
+        fresh.append(e.search(Rs[k], 30.0)[0].cpu())
+        e.close()
+    eng = DockingSearch(L, (C0, C1), max_rot=4, device=DEV)
+    eng.set_filter((filt.W1, filt.b1, filt.W2, filt.b2))
+    for visit in range(4):
+        k = visit % 2
+        eng.set_receptor(pairs[k][0], pairs[k][1]); eng.set_ligand(pairs[k][2], pairs[k][3])
+        got = eng.search(Rs[k], 30.0)[0].cpu()
+        assert torch.equal(got, fresh[k]), (visit, got, fresh[k])
+    eng.close()
+    rec, rc, lig, lc = pairs[1]
+    spectra = O.ReceptorSpectra([_d(v)[None] for v in rec], _d(rc)[None, None])
+    f64 = filt.to(torch.float64)
+    for i in range(3):
+        V = O.score_rotation(spectra, [_d(v)[None] for v in lig], _d(lc), Rs[1][i], f64, 30.0)
+        _check_pose(fresh[1][i], V)
+
+
+def _adversarial(kind, L, C0, C1, g):
+    L1 = L // 2
+    z0, z1 = torch.zeros(C0, L, L, L), torch.zeros(C1, L1, L1, L1)
+    if kind == "delta":                    # one spike per channel: the correlation is a shifted copy of the ligand
+        for c in range(C0):
+            z0[c, (3 * c + 5) % L, (7 * c + 2) % L, (c + 9) % L] = 1.0 + 0.1 * c
+        for c in range(C1):
+            z1[c, (3 * c + 1) % L1, (5 * c + 2) % L1, (c + 3) % L1] = -1.0 + 0.05 * c
+    elif kind == "constant":
+        z0 += 0.25
+        z1 -= 0.5
+    elif kind == "corner":                 # all the mass in the corner voxels (the wrap-around seam of the circular index)
+        z0[:, 0, 0, 0], z0[:, L - 1, L - 1, L - 1] = 1.0, -2.0
+        z1[:, 0, 0, 0], z1[:, L1 - 1, L1 - 1, L1 - 1] = 0.5, 1.5
+    elif kind == "positive":               # all-positive volumes: the filter's first layer cancels large sums (ill-conditioned)
+        z0 = torch.rand(C0, L, L, L, generator=g)
+        z1 = torch.rand(C1, L1, L1, L1, generator=g)
+    return [z0, z1]
+
+
+# tolerance that holds per case, relative to max(|s_ref|, 1e-3 max|V|).  All-positive volumes: every correlation value is a
+# sum of ~L^3 positive terms and the first filter layer cancels them, so fp32 rounding of the transforms (not of the filter) is
+# amplified -- the fp32 torch.fft oracle itself misses 1e-4 against fp64 there.
+@pytest.mark.parametrize("kind,tol", [("delta", 1e-4), ("constant", 1e-4), ("corner", 1e-4), ("positive", 2e-3)])
+@pytest.mark.parametrize("filter_kind", ["fp32", "tcgen05"])
+def test_adversarial_receptor_volumes(kind, tol, filter_kind):
+    """SURVEY.md section 4's adversarial inputs as the RECEPTOR (delta spikes, constant volume, corner voxels, all-positive
+    noise) against a random zero-mean ligand at L = 20, 16 + 32 channels, both forms of the first filter layer."""
+    L, C0, C1, H = 20, 16, 32, 24
+    g = torch.Generator().manual_seed(7)
+    rec = _adversarial(kind, L, C0, C1, g)
+    lig = [torch.randn(C0, L, L, L, generator=g), torch.randn(C1, L // 2, L // 2, L // 2, generator=g)]
+    rf, lf = torch.rand(L, L, L, generator=g), torch.rand(L, L, L, generator=g)
+    filt = O.FilterWeights.random(C0 + C1, H, seed=5)
+    Rs = R20[[3, 333, 999, 1500]]
+    tau = float(torch.quantile(O.correlate(rf[None, None], lf[None, None]).flatten(), 0.6))
+    _lib.set_option("filter_kind", filter_kind)
+    try:
+        eng = DockingSearch(L, (C0, C1), H, max_rot=4, device=DEV)
+    finally:
+        _lib.set_option("filter_kind", "auto")
+    eng.set_receptor(rec, rf); eng.set_ligand(lig, lf); eng.set_filter((filt.W1, filt.b1, filt.W2, filt.b2))
+    best, scores = eng.search(Rs, tau, return_scores=True)
+    eng.close()
+    best, scores = best.cpu(), scores.cpu()
+    spectra = O.ReceptorSpectra([_d(r)[None] for r in rec], _d(rf)[None, None])
+    f64 = filt.to(torch.float64)
+    for i in range(Rs.shape[0]):
+        V = O.score_rotation(spectra, [_d(l)[None] for l in lig], _d(lf), Rs[i], f64, tau)
+        _check_pose(best[i], V, tol)
+        lrot = O.rotate_volume(_d(lf)[None, None], Rs[i][None])
+        clash = O.correlate(_d(rf)[None, None], lrot)[0, 0]
+        safe = (clash - tau).abs() > 1e-4 * clash.abs().max()
+        assert (scores[i].double() - V).abs()[safe].max() <= tol * float(V.abs().max())
+
+
+def test_search_128_eight_rotations_and_a_score_volume():
+    """BASELINE config 5 shape (128^3, 16@128^3 + 32@64^3 + clash; cluster plane kernel, 2x1 epilogue tile): 8 rotations in
+    two chunks (max_rot = 6: three packed pairs, then an odd tail pair) vs the fp64 oracle, with the full masked score volume
+    of one rotation."""
+    L, C0, C1 = 128, 16, 32
+    rec, rec_clash = synthetic.learned_volumes(L, (C0, C1), seed=61)
+    lig, lig_clash = synthetic.learned_volumes(L, (C0, C1), seed=62)
+    filt = O.FilterWeights.random(C0 + C1, seed=63)
+    Rs = R20[[9, 123, 456, 789, 1011, 1234, 1516, 1819]]
+    tau = 30.0
+    eng = DockingSearch(L, (C0, C1), max_rot=6, device=DEV)
+    eng.set_receptor(rec, rec_clash); eng.set_ligand(lig, lig_clash); eng.set_filter((filt.W1, filt.b1, filt.W2, filt.b2))
+    best, _ = eng.search(Rs, tau)
+    best1, vol = eng.search(Rs[5:6], tau, return_scores=True)
+    eng.close()
+    best, vol = best.cpu(), vol.cpu()[0]
+    # alone, rotation 5 travels as the real part of its complex volume; in the batch as the imaginary part of pair (4, 5)
+    assert torch.equal(best1.cpu()[0, 1:], best[5, 1:]) and abs(float(best1[0, 0]) - float(best[5, 0])) <= 2e-5 * abs(float(best[5, 0]))
+    spectra = O.ReceptorSpectra([_d(r)[None] for r in rec], _d(rec_clash)[None, None])
+    f64 = filt.to(torch.float64)
+    ligs = [_d(l)[None] for l in lig]
+    for i in range(Rs.shape[0]):
+        V = O.score_rotation(spectra, ligs, _d(lig_clash), Rs[i], f64, tau)
+        _check_pose(best[i], V)
+        if i == 5:
+            lrot = O.rotate_volume(_d(lig_clash)[None, None], Rs[i][None])
+            clash = O.correlate(_d(rec_clash)[None, None], lrot)[0, 0]
+            safe = (clash - tau).abs() > 1e-4 * clash.abs().max()
+            assert (vol.double() - V).abs()[safe].max() <= 1e-4 * float(V.abs().max())
+
+
+def test_typed_projector_cuda_matches_torch_path():
+    """dlpd_project_typed (CUDA) vs the plain-PyTorch TypedCoords2Volume on the same typed layout: two structures of different
+    size (padding slots), atoms partly outside the box, an empty type."""
+    from deeplocalproteindocking_b200.docker import Atoms, typed_layout
+    L, res = 20, 1.25
+    g = torch.Generator().manual_seed(3)
+    structs = []
+    for n in (120, 77):
+        coords = (torch.rand(n, 3, generator=g, dtype=torch.float64) - 0.25) * 30.0
+        types = torch.randint(0, 10, (n,), generator=g)                      # type 10 stays empty
+        structs.append(typed_layout(Atoms(coords.float(), types), "cpu"))
+    nmax = max(s[0].shape[1] for s in structs)
+    coords = torch.zeros(2, nmax)
+    for b, s in enumerate(structs):
+        coords[b, :s[0].shape[1]] = s[0][0]
+    nat = torch.cat([s[1] for s in structs]); off = torch.cat([s[2] for s in structs])
+    proj = TypedCoords2Volume(L, res)
+    want = proj(coords, nat, off)                                            # CPU tensors: PyTorch path
+    got = proj(coords.to(DEV), nat.to(DEV), off.to(DEV)).cpu()               # CUDA tensors: the kernel
+    assert got.shape == want.shape == (2, 11, L, L, L)
+    assert (got - want).abs().max() <= 2e-6 * max(1.0, float(want.abs().max()))
+    assert float(got[:, 10].abs().max()) == 0.0 and float(got.sum()) > 0.0
+
+
+def test_plan_options_are_per_plan_and_layout_hazard_is_an_error():
+    """Options live in the plan: changing one plan does not touch another, and switching the plane kernel after set_receptor
+    (the receptor spectra are laid out for the other kernel) is DLPD_ESTATE instead of silently wrong scores."""
+    L, C0, C1, H = 20, 16, 32, 24
+    g = torch.Generator().manual_seed(21)
+    rec = [torch.randn(C0, L, L, L, generator=g), torch.randn(C1, L // 2, L // 2, L // 2, generator=g)]
+    lig = [torch.randn(C0, L, L, L, generator=g), torch.randn(C1, L // 2, L // 2, L // 2, generator=g)]
+    rf, lf = torch.rand(L, L, L, generator=g), torch.rand(L, L, L, generator=g)
+    filt = O.FilterWeights.random(C0 + C1, H, seed=2)
+    Rs = R20[[5, 50, 500]]
+    a = DockingSearch(L, (C0, C1), H, max_rot=4, device=DEV)
+    b = DockingSearch(L, (C0, C1), H, max_rot=4, device=DEV)
+    for e in (a, b):
+        e.set_receptor(rec, rf); e.set_ligand(lig, lf); e.set_filter((filt.W1, filt.b1, filt.W2, filt.b2))
+    ref = a.search(Rs, 5.0)[0].cpu()
+    a.set_option("plane_mode", "cluster")
+    with pytest.raises(_lib.DlpdError, match="plane mode"):
+        a.search(Rs, 5.0)
+    assert torch.equal(b.search(Rs, 5.0)[0].cpu(), ref)                      # plan b is unaffected
+    a.set_receptor(rec, rf); a.set_ligand(lig, lf)                          # spectra re-laid out for the cluster kernel
+    got = a.search(Rs, 5.0)[0].cpu()
+    assert torch.equal(got[:, 1:], ref[:, 1:]) and torch.allclose(got[:, 0], ref[:, 0], rtol=2e-5, atol=1e-6)
+    a.set_option("filter_kind", "fp32")
+    got2 = a.search(Rs, 5.0)[0].cpu()
+    assert torch.equal(got2[:, 1:], ref[:, 1:]) and torch.allclose(got2[:, 0], ref[:, 0], rtol=2e-5, atol=1e-6)
+    if not _lib.has_experimental():
+        with pytest.raises(_lib.DlpdError, match="EXPERIMENTAL"):
+            a.set_option("epilogue_kind", "fused")
+    a.close(); b.close()
+
+
+def test_reference_dockse3_call_sequence_on_the_stand_ins():
+    """The reference's dockSE3 loop (Docker.py:190-236), restated call for call against the module names `tpl.install()`
+    registers -- TorchProteinLibrary.FullAtomModel / .Volume operators, GlobalDockingModel.forward for the score volume --
+    must give the poses of the fused `Docker.dockSE3`.  (The reference file itself hard-codes device='cuda' and is absent on
+    the GPU box; its CPU half runs unmodified in tests/test_host_logic.py.)"""
+    import importlib
+    saved = {k: sys.modules.get(k) for k in list(sys.modules) if k == "_Volume" or k.startswith("TorchProteinLibrary")}
+    tpl.install()
+    try:
+        FA = importlib.import_module("TorchProteinLibrary.FullAtomModel")
+        VOL = importlib.import_module("TorchProteinLibrary.Volume")
+        L, res, bs = 20, 1.25, 2
+        torch.manual_seed(5)
+        rep = E3MultiResRepr4x4(multiplier=8).to(DEV).eval()
+        filt = SimpleFilter(rep.get_num_outputs()).to(DEV)
+        model = GlobalDockingModel(rep, filt, threshold_clash=4.0).to(DEV).eval()
+        tpl.register_synthetic("rec", *_atoms(300, 8.0, 1))
+        tpl.register_synthetic("lig", *_atoms(150, 6.0, 2))
+        rot_idx = torch.tensor([4, 44, 444, 1444])
+        # ---- the reference's sequence ------------------------------------------------------------------------
+        rotate, translate = FA.CoordsTransform.CoordsRotate(), FA.CoordsTransform.CoordsTranslate()
+        project, convolve, vol_rotate = VOL.TypedCoords2Volume(L, res), VOL.VolumeConvolution(), VOL.VolumeRotation()
+        box_center = torch.full((1, 3), L * res / 2.0, dtype=torch.float64)
+
+        def load_batch(names):                                            # Docker.py:49-61, bbox_center=False
+            coords, chains, resnames, resnums, atomnames, num_atoms = FA.PDB2CoordsUnordered()(names)
+            coords, nat, off = FA.Coords2TypedCoords()(coords, resnames, atomnames, num_atoms)
+            a, b = FA.getBBox(coords, num_atoms)
+            return FA.CoordsTranslate()(coords, -(a + b) * 0.5, num_atoms), nat, off, num_atoms
+
+        with torch.no_grad(), torch.backends.cudnn.flags(enabled=True, allow_tf32=False):
+            rcoords, rnat, roff, rn = load_batch(["rec"] * bs)
+            lcoords, lnat, loff, ln = load_batch(["lig"] * bs)
+            bc = box_center.squeeze().repeat(bs, 1)
+            receptor = project(translate(rcoords, bc, rn).to(dtype=torch.float, device=DEV), rnat.to(DEV), roff.to(DEV))
+            receptor_volumes = model.representation(receptor)
+            receptor_forbidden = receptor.sum(dim=1).unsqueeze(dim=1).contiguous()
+            ligand = project(translate(lcoords, bc, ln).to(dtype=torch.float, device=DEV), lnat.to(DEV), loff.to(DEV))
+            ligand_volumes = model.representation(ligand)
+            ref_best = []
+            for i in range(0, rot_idx.numel(), bs):
+                r_cpu = R20[rot_idx[i:i + bs]]
+                r_gpu = r_cpu.to(dtype=torch.float, device=DEV)
+                lig_rot = [vol_rotate(v, r_gpu) for v in ligand_volumes]
+                lrt = translate(rotate(lcoords, r_cpu, ln), bc, ln)
+                lf = project(lrt.to(dtype=torch.float, device=DEV), lnat.to(DEV), loff.to(DEV)).sum(dim=1).unsqueeze(dim=1).contiguous()
+                norm = convolve(receptor_forbidden, lf).squeeze()
+                V = torch.lt(norm, model.threshold_clash).to(dtype=torch.float) * model(receptor_volumes, lig_rot).squeeze()
+                for j in range(bs):
+                    ref_best.append(O.best_pose(V[j].double().cpu()))
+        # ---- the fused driver --------------------------------------------------------------------------------
+        dk = Docker(model, angle_inc=20, box_size=L, resolution=res, max_conf=1, rot_batch=4, device=DEV)
+        from deeplocalproteindocking_b200.docker import Atoms
+        dk.dockSE3(Atoms(*_atoms(300, 8.0, 1)), Atoms(*_atoms(150, 6.0, 2)), rotation_subset=rot_idx, write=False)
+        got = dk.best_per_rotation
+        dk.close()
+        for j, (s, x, y, z) in enumerate(ref_best):
+            assert [int(v) for v in got[j, 1:]] == [x, y, z], (j, got[j], (s, x, y, z))
+            assert abs(float(got[j, 0]) - s) <= 1e-4 * max(abs(s), 1e-6)
+    finally:
+        for k in [k for k in sys.modules if k == "_Volume" or k.startswith("TorchProteinLibrary")]:
+            del sys.modules[k]
+        for k, m in saved.items():
+            if m is not None:
+                sys.modules[k] = m
+
+
+def _atoms(n, radius, seed):
+    a = synthetic.random_protein(n, radius, seed)
+    return a.coords, a.types

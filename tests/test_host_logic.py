@@ -160,9 +160,17 @@ def test_tpl_module_surface_is_import_compatible(tmp_path):
         xyz0 = coords[0, :12].reshape(4, 3)
         assert torch.equal(a[0], xyz0.min(0).values) and torch.equal(b[0], xyz0.max(0).values)
         with pytest.raises(NotImplementedError):
-            PDB2CoordsUnordered()(["x.pdb"])
-        with pytest.raises(NotImplementedError):
-            Coords2TypedCoords()(coords, None, None, nat)
+            PDB2CoordsUnordered()(["x.pdb"])                               # real PDB parsing is outside the search path: loud
+        # synthetic proteins by name: same return signature as TorchProteinLibrary's reader / typer (Docker.py:51-52)
+        from deeplocalproteindocking_b200 import tpl as T_
+        T_.register_synthetic("toy", [[0.0, 0.0, 0.0], [1.0, 2.0, 3.0], [4.0, 5.0, 6.0]], [7, 0, 7])
+        c, chains, resnames, resnums, atomnames, na = PDB2CoordsUnordered()(["toy", "synthetic:5:3.0:9"])
+        assert c.dtype == torch.float64 and tuple(c.shape) == (2, 15) and na.tolist() == [3, 5] and na.dtype == torch.int32
+        assert tuple(resnames.shape) == (2, 5, 4) and tuple(atomnames.shape) == (2, 5, 4) and tuple(chains.shape) == (2, 5)
+        tc, nat_t, off_t = Coords2TypedCoords()(c, resnames, atomnames, na)
+        assert nat_t.dtype == torch.int32 and tuple(nat_t.shape) == (2, 11) and nat_t.sum(1).tolist() == [3, 5]
+        assert nat_t[0].tolist() == [1, 0, 0, 0, 0, 0, 0, 2, 0, 0, 0] and off_t[0].tolist() == [0, 1, 1, 1, 1, 1, 1, 1, 3, 3, 3]
+        assert tc[0, :9].tolist() == [1.0, 2.0, 3.0, 0.0, 0.0, 0.0, 4.0, 5.0, 6.0]          # stable sort by type
         out = tmp_path / "v.xplor"
         _Volume.Volume2Xplor(torch.arange(27, dtype=torch.float32).reshape(3, 3, 3), str(out), 1.25)
         text = out.read_text().splitlines()
@@ -200,6 +208,22 @@ def test_reference_docker_module_imports_against_the_stand_ins(tmp_path):
         assert mod.CoordsTransform.CoordsRotate.__module__ == "deeplocalproteindocking_b200.tpl"
         models = importlib.import_module("src.Models.DockingModels")
         assert models.VolumeConvolution.__module__ == "deeplocalproteindocking_b200.volume"
+        # the CPU half of the reference's dockSE3 set-up, UNMODIFIED, on the synthetic stand-ins (Docker.py:18-61,190-201):
+        # constructor, load_batch (reader -> typer -> bbox centring), randomised receptor rotation, box-centre translation
+        from deeplocalproteindocking_b200 import synthetic
+        torch.manual_seed(0)
+        dk = mod.Docker(docking_model=None, angle_inc=20, box_size=20, resolution=1.25, max_conf=3, randomize_rot=True)
+        assert dk.rot.R.shape == (1854, 3, 3)
+        lig = synthetic.random_protein(40, 6.0, seed=5)
+        tpl.register_synthetic("lig", lig.coords, lig.types)
+        coords, nat, off, T, natoms = dk.load_batch(["lig", "lig"], bbox_center=False)
+        order = torch.argsort(lig.types, stable=True)
+        assert torch.allclose(coords[0].reshape(-1, 3), lig.centred().coords[order], atol=1e-12)
+        assert nat[0].tolist() == torch.bincount(lig.types, minlength=11).tolist() and natoms.tolist() == [40, 40]
+        moved = dk.translate(dk.rotate(coords, dk.randR.repeat(2, 1, 1), natoms), dk.box_center.squeeze().repeat(2, 1), natoms)
+        want = lig.centred().coords[order] @ dk.randR[0].t() + 12.5
+        assert torch.allclose(moved[1].reshape(-1, 3), want, atol=1e-12)
+        dk.cleanup()
     finally:
         for k in [k for k in sys.modules if k not in saved]:
             del sys.modules[k]

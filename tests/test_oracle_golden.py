@@ -36,10 +36,19 @@ def test_rotation_sets_sizes_and_orthonormality():
         assert (torch.linalg.det(R) - 1).abs().max() < 1e-14
 
 
-def test_surrogate_oim04_is_deterministic_and_well_formed(tmp_path):
-    a = rot.soi_euler_angles(4)
+def test_surrogate_oim04_is_opt_in_deterministic_and_well_formed(tmp_path):
+    """oim04.eul is a missing blob: like the reference (Rotations.py:41,55) the default raises; the Fibonacci surrogate of the
+    same size must be asked for by name."""
+    import pytest
+    with pytest.raises(Exception, match="Can't find rotation angles"):
+        rot.Rotations(4)
+    with pytest.raises(Exception, match="Can't find rotation angles"):
+        rot.soi_euler_angles(4)
+    r4 = rot.Rotations("fibonacci4")
+    assert r4.surrogate and len(r4) == 232020 and not rot.Rotations(20).surrogate
+    a = rot.soi_euler_angles(4, allow_surrogate=True)
     assert a.shape == (232020, 3)
-    assert np.array_equal(a, rot.soi_euler_angles(4))
+    assert np.array_equal(a, rot.soi_euler_angles(4, allow_surrogate=True))
     assert np.all(a[:90, 1] == a[0, 1]) and np.all(a[:90, 2] == a[0, 2])
     assert abs(a[1, 0] - a[0, 0] - math.radians(4)) < 2e-6
     p = tmp_path / "oim04.eul"

@@ -16,7 +16,7 @@ import os
 import sys
 
 REF = "/root/reference/data"
-OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), os.pardir, "data", "soi_axes.json")
+OUT = os.path.join(os.path.dirname(os.path.abspath(__file__)), os.pardir, "deeplocalproteindocking_b200", "data", "soi_axes.json")
 
 
 def main():
