@@ -289,6 +289,9 @@ static std::mutex g_mutex;               // guards g_defaults and the standalone
 #ifndef DLPD_EPILOGUE_DEFAULT_DUO
 #define DLPD_EPILOGUE_DEFAULT_DUO 0
 #endif
+#ifndef DLPD_EPILOGUE_DEFAULT_TC_DUO
+#define DLPD_EPILOGUE_DEFAULT_TC_DUO 0
+#endif
 #ifndef DLPD_EPILOGUE_DEFAULT_FUSED
 #define DLPD_EPILOGUE_DEFAULT_FUSED 0
 #endif
@@ -727,16 +730,16 @@ static int make_s2_tensor_map(const cpx* s2, int C, int N, int T, int P, int pay
 }
 #endif
 
-template <int L, int C0, int C1, int H, int TY, int FK = 0>
+template <int L, int C0, int C1, int H, int TY, int FK = 0, bool DUO = false>
 static int launch_epilogue_t(dlpd_plan* p, int n, int P, float tau, float* out_scores, const CandArgs& ca, dlpd_stream_t st) {
-    typedef Epilogue<L, C0, C1, H, TY, FK> K;
+    typedef Epilogue<L, C0, C1, H, TY, FK, DUO> K;
     if constexpr (K::SMEM <= SMEM_MAX) {
         typename K::Params e;
         e.s2_0 = p->s2_0; e.h1 = p->h1; e.best = p->best; e.score_out = out_scores;
         e.tw0 = p->tw0; e.n_rot = n; e.tau = tau;
         e.cand = ca.cand; e.cand_count = ca.count; e.cand_cap = ca.cap; e.cand_key = ca.key; e.rot_base = ca.rot_base;
         e.n_tiles = P * K::TILES;
-        e.grid = e.n_tiles < p->sm_count ? e.n_tiles : p->sm_count;
+        e.grid = e.n_tiles < K::MINB * p->sm_count ? e.n_tiles : K::MINB * p->sm_count;
         fill_filter(p, e.filt);
         e.mlp = nullptr;
 #if !defined(DLPD_EMU)
@@ -748,7 +751,8 @@ static int launch_epilogue_t(dlpd_plan* p, int n, int P, float tau, float* out_s
             e.mlp = (const MlpDev<C0, H>*)p->mlp;
         }
 #endif
-        return launch<K>(dim3(e.grid), e, st);
+        if constexpr (K::MINB > 1) return launch_mb<K>(dim3(e.grid), e, st);
+        else return launch<K>(dim3(e.grid), e, st);
     } else {
         return fail(DLPD_EINVAL, "epilogue tile does not fit shared memory");
     }
@@ -831,6 +835,18 @@ static int launch_epilogue(dlpd_plan* p, int n, int P, float tau, float* out_sco
     // warpgroups fit the 512 TMEM columns) unless the plan asks for the FP32 chain
     const int fk = filter_kind_of(p);
     if (fk == DLPD_FILTER_TCGEN05) {
+#if DLPD_EXPERIMENTAL
+        // two half-tile CTAs per SM (transform of one overlaps the TMEM / MMA phase of the other): parity-green, measured on
+        // B200 and rejected -- 4.38 ms vs 3.30 ms per 32 rotations (profiles/r02/bench_tc_duo_rejected.log)
+        const bool want_duo = p->opt.epi_kind == DLPD_EPILOGUE_TC_DUO || (p->opt.epi_kind == DLPD_EPILOGUE_AUTO && DLPD_EPILOGUE_DEFAULT_TC_DUO && !p->opt.epi_tile);
+        if (want_duo) {
+            typedef Epilogue<L, C0, C1, H, 1, 2, true> KD;
+            if constexpr (KD::DUO && 2 * (KD::SMEM + 1024) <= 228 * 1024)
+                return launch_epilogue_t<L, C0, C1, H, 1, 2, true>(p, n, P, tau, out_scores, ca, st);
+            if (p->opt.epi_kind == DLPD_EPILOGUE_TC_DUO)
+                return fail(DLPD_EINVAL, "the two-CTA tcgen05 epilogue is not available for this configuration");
+        }
+#endif
         if (ty == 2) {
             if constexpr (Epilogue<L, C0, C1, H, 2, 2>::TC_OK && Epilogue<L, C0, C1, H, 2, 2>::SMEM <= SMEM_MAX)
                 return launch_epilogue_t<L, C0, C1, H, 2, 2>(p, n, P, tau, out_scores, ca, st);
@@ -1082,7 +1098,7 @@ static int apply_option(Options& o, int key, int value) {
             o.plane_mode = value;
             return 0;
         case DLPD_OPT_EPILOGUE_KIND:
-            if (value < DLPD_EPILOGUE_AUTO || value > DLPD_EPILOGUE_FUSED) return fail(DLPD_EINVAL, "bad epilogue kind");
+            if (value < DLPD_EPILOGUE_AUTO || value > DLPD_EPILOGUE_TC_DUO) return fail(DLPD_EINVAL, "bad epilogue kind");
 #if !DLPD_EXPERIMENTAL
             if (value > DLPD_EPILOGUE_CLASSIC)
                 return fail(DLPD_EINVAL, "this epilogue variant is only compiled with -DDLPD_EXPERIMENTAL=1 (see dlpd_build_flags)");

@@ -1328,7 +1328,11 @@ template <int C0, int C1, int H> struct EpiParams {
 // FK_: how the level-0 half of the filter's first layer (C0 -> H, DockingModels.py:29) is evaluated
 //   0 = packed FP32 FFMA2 chain;  1 = mma.sync fp16 split (DLPD_EXPERIMENTAL only);
 //   2 = tcgen05.mma kind::tf32 (3 x TF32 split) with the A operand and the accumulators in TMEM (dlpd_tc.h)
-template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0> struct Epilogue {
+// DUO_ (tcgen05 + 2x1 tiles only): TWO persistent CTAs per SM, each on its own stream of half-tiles.  The transform passes of
+//   one CTA (FP32 pipe, shared memory) then overlap the TMEM staging / MMA waits of the other -- the overlap the round-1
+//   EpilogueDuo could not get while the filter itself was FP32-bound.  The level-1 hidden part is read straight from global
+//   memory (L2) instead of being staged, so that two CTAs fit the SM's shared memory.
+template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0, bool DUO_ = false> struct Epilogue {
     typedef EpiParams<C0, C1, H> Params;
     static constexpr int L = L_, N = 2 * L_, N1 = L_, T = L_;      // T = N/2 tile rows along x
     // tile = 2 x TY (x,y) columns: 2x2 normally; 2x1 when two 2x2 buffers do not fit shared memory (N = 256) -- the
@@ -1343,17 +1347,21 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0> struct Epilog
     static constexpr int TC_COLS = (NWG * TC_COLS_WG <= 32) ? 32 : (NWG * TC_COLS_WG <= 64) ? 64 : (NWG * TC_COLS_WG <= 128) ? 128
                                  : (NWG * TC_COLS_WG <= 256) ? 256 : 512;
     static constexpr bool TC_OK = (FK_ == 2) && (C0 % 8 == 0) && (H % 8 == 0) && (H <= 256) && (NWG * TC_COLS_WG <= 512) && (NWG <= 7);
+    static constexpr bool DUO = DUO_ && TC_OK && (TY_ == 1) && (NWG * TC_COLS_WG <= 256);
+    static constexpr int MINB = DUO ? 2 : 1;                       // resident CTAs per SM the register budget is cut for
     // warp specialisation: the last NPROD threads only issue the cp.async copies of the NEXT tile (each copy touches
     // its own cache line, so issuing them is slow -- but it now overlaps the transform of the current tile instead of
     // stalling every warp); the first NC threads transform and score
     // USE_TMA (tcgen05 kernels): no producer threads at all -- thread 0 issues one tensor-map box load and one bulk copy per
     // tile, completion is counted on an mbarrier; NX extra threads only help with the transform passes
-    static constexpr bool USE_TMA = TC_OK && (DLPD_EPI_TMA != 0);
-    static constexpr int NPROD = USE_TMA ? 0 : ((N >= 128) ? DLPD_EPI_NPROD : 32);
-    static constexpr int NX = (TC_OK && N >= 128) ? DLPD_EPI_TC_EXTRA : 0;
-    static constexpr int NC = TC_OK ? 128 * NWG : ((N >= 128) ? DLPD_EPI_NT : 128) - NPROD;
+    static constexpr bool USE_TMA = TC_OK && !DUO && (DLPD_EPI_TMA != 0);
+    static constexpr int NPROD = USE_TMA ? 0 : (DUO ? 32 : ((N >= 128) ? DLPD_EPI_NPROD : 32));
+    static constexpr int NX = DUO ? ((N >= 128) ? 32 : 0) : ((TC_OK && N >= 128) ? DLPD_EPI_TC_EXTRA : 0);
+    // tcgen05: the scoring threads are the whole warps that hold a translation (the last warpgroup may be partial)
+    static constexpr int NC = TC_OK ? (NVOX + 31) / 32 * 32 : ((N >= 128) ? DLPD_EPI_NT : 128) - NPROD;
     static constexpr int NT = NC + NX + NPROD;
     static constexpr int BUF = N * NL0, HB = N1 * H;
+    static constexpr int HBS = DUO ? 0 : HB;                       // staged level-1 hidden column (none in DUO: read from global)
 #if DLPD_EXPERIMENTAL
     static constexpr int MLP_BYTES = TC_ ? ((int)sizeof(MlpDev<C0, H>) + 15) / 16 * 16 : 0;      // shared-memory copy of the MMA fragments
 #else
@@ -1364,7 +1372,7 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0> struct Epilog
     static constexpr int TC_BW = 2 * C0 * HP;                      // floats
     static constexpr int TC_BYTES = TC_OK ? (TC_BW * 4 + 16 * 8 + 16) : 0;       // bars[0 .. 2 NWG) MMA, bars[14], bars[15] tile landed
     static constexpr bool PKT = DLPD_EPI_PACKED_TW && (N / (2 * LinePlan<N>::R0) > 1);      // packed twiddles of the inverse head pass
-    static constexpr int SMEM = (2 * BUF + 2 * HB + N + (PKT ? N : 0)) * (int)sizeof(cpx) + 64 * 8 + MLP_BYTES + TC_BYTES;
+    static constexpr int SMEM = (2 * BUF + 2 * HBS + N + (PKT ? N : 0)) * (int)sizeof(cpx) + 64 * 8 + MLP_BYTES + TC_BYTES;
     static constexpr int QPT = NPROD / TY;         // (c, kz) rows covered per sweep of the producer threads
     static constexpr int TILES = T * TPR;          // tiles per pair
     static_assert(HB % 2 == 0 && NPROD % 32 == 0 && NC % 32 == 0 && (TY_ == 1 || TY_ == 2), "team shapes");
@@ -1389,8 +1397,10 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0> struct Epilog
                 if (kz >= N) { kz -= N; ++c; }
             }
         }
-        const cpx* hs = p.h1 + ((long)pair * T * T + r4) * HB;          // level-1 column (x/2, y/2): N1*H contiguous
-        DLPD_FOR_TASKS_SUB(t, HB / 2, NPROD, NC + NX) cp_async16(hb + 2 * t, hs + 2 * t);
+        if constexpr (HBS > 0) {
+            const cpx* hs = p.h1 + ((long)pair * T * T + r4) * HB;      // level-1 column (x/2, y/2): N1*H contiguous
+            DLPD_FOR_TASKS_SUB(t, HB / 2, NPROD, NC + NX) cp_async16(hb + 2 * t, hs + 2 * t);
+        }
     }
 
 #if !defined(DLPD_EMU)
@@ -1686,6 +1696,7 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0> struct Epilog
         const int tv = valid ? t : 0;                         // padding rows of the last warpgroup recompute translation 0 and drop it
         const int xy = tv % XY, z = tv / XY;
         const int g = t >> 7, q = (t >> 5) & 3;
+        const int gthreads = (NC - 128 * g) < 128 ? (NC - 128 * g) : 128;          // scoring threads of my warpgroup
         const uint32_t lane_addr = ts.tmem_base + ((uint32_t)(q * 32) << 16);
         const uint32_t colA = (uint32_t)(g * TC_COLS_WG), colD0 = colA + 2 * C0, colD1 = colD0 + HP;
         constexpr uint32_t IDESC = tc::idesc_tf32(128, HP);
@@ -1719,7 +1730,7 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0> struct Epilog
             }
             tc::wait_st();
             tc::fence_before_sync();
-            named_barrier_sync(2 + g, 128);
+            named_barrier_sync(2 + g, gthreads);
             if (q == 0 && tc::elect_one()) {
                 tc::fence_after_sync();
                 const uint32_t d = ts.tmem_base + (rot ? colD1 : colD0), a = ts.tmem_base + colA;
@@ -1757,7 +1768,7 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0> struct Epilog
         float2 sc = dup2(p.filt.b2);
         DLPD_UNROLL
         for (int j = 0; j < H; ++j) {
-            const float2 hh = fadd2_(make_float2(acc[0][j], acc[1][j]), hz[j]);
+            const float2 hh = fadd2_(make_float2(acc[0][j], acc[1][j]), DUO ? __ldg(hz + j) : hz[j]);
             sc = ffma2_(dup2(p.filt.W2[j]), make_float2(fmaxf(hh.x, 0.0f), fmaxf(hh.y, 0.0f)), sc);
         }
         if (valid) {
@@ -1771,7 +1782,7 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0> struct Epilog
     static DLPD_DEV void body(const Params& p, int bx, int, int, char* smem) {
         cpx* bufs = reinterpret_cast<cpx*>(smem);      // [2][kz][NL0]
         cpx* hbufs = bufs + 2 * BUF;                   // [2][z'][H]  (rotA, rotB): b1 + level-1 part of the hidden layer
-        cpx* tw0 = hbufs + 2 * HB;
+        cpx* tw0 = hbufs + 2 * HBS;
         unsigned long long* red = reinterpret_cast<unsigned long long*>(tw0 + N + (PKT ? N : 0));
         MlpDev<C0, H>* ms = reinterpret_cast<MlpDev<C0, H>*>(red + 64);
         DLPD_FOR_TASKS(t, N, NT) tw0[t] = p.tw0[t];
@@ -1859,7 +1870,7 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0> struct Epilog
             }
             if (producer) {
 #if !defined(DLPD_ABLATE_EPI_LOAD)
-                if (tile + p.grid < p.n_tiles) issue_loads(p, tile + p.grid, bufs + (slot ^ 1) * BUF, hbufs + (slot ^ 1) * HB);
+                if (tile + p.grid < p.n_tiles) issue_loads(p, tile + p.grid, bufs + (slot ^ 1) * BUF, hbufs + (slot ^ 1) * HBS);
 #endif
                 cp_async_commit();
                 cp_async_wait_pending();
@@ -1870,11 +1881,14 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0> struct Epilog
                     cpx* b0 = bufs + slot * BUF;
                     if constexpr (PKT) transform_tile_pk(tmT, b0, tw0, tw0 + N);
                     else transform_tile(tmT, b0, tw0);
-                    if (threadIdx.x < NC)
-                        score_voxels_tc(p, tm, b0, hbufs + slot * HB, ts, pair, 2 * tile_xh(r), tile_y0(r), bestA, bestB);
+                    if (threadIdx.x < NC) {
+                        const cpx* hcol = DUO ? p.h1 + ((long)pair * T * T + tile_xh(r) * T + (tile_y0(r) >> 1)) * HB
+                                              : hbufs + slot * HBS;
+                        score_voxels_tc(p, tm, b0, hcol, ts, pair, 2 * tile_xh(r), tile_y0(r), bestA, bestB);
+                    }
                 } else
 #endif
-                score_tile(p, tm, bufs + slot * BUF, hbufs + slot * HB, tw0, ms, pair, 2 * tile_xh(r), tile_y0(r), bestA, bestB);
+                score_tile(p, tm, bufs + slot * BUF, hbufs + slot * HBS, tw0, ms, pair, 2 * tile_xh(r), tile_y0(r), bestA, bestB);
             }
         }
         if (cur_pair >= 0) flush_best(p, cur_pair, bestA, bestB, red);

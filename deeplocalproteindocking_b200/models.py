@@ -101,3 +101,22 @@ class GlobalDockingModel(nn.Module):
             levels.append(corr)
         V = torch.cat(levels, dim=1).permute(0, 2, 3, 4, 1).reshape(B * N * N * N, -1)
         return self.filter(V).reshape(B, N, N, N)
+
+
+def select_model(group: str = "E3", model: str = "E3MultiResRepr4x4", filter: str = "SimpleFilter", threshold_clash=300):
+    """The model table of `local_train.select_model` / `local_test.py` (local_train.py:20-47): equivariance group + model name
+    -> `GlobalDockingModel(representation, SimpleFilter, threshold_clash)` with the reference's multiplier of 8."""
+    from .se3_scalar import SE3MultiResReprScalar
+    if group == "E3":
+        if model != "E3MultiResRepr4x4":
+            raise Exception("Unknown model name", model)
+        representation = E3MultiResRepr4x4(multiplier=8)
+    elif group == "SE3":
+        if model != "SE3MultiResReprScalar":
+            raise Exception("Unknown model name", model)
+        representation = SE3MultiResReprScalar(multiplier=8)
+    else:
+        raise Exception("Unknown equivariance group", group)
+    if filter != "SimpleFilter":
+        raise Exception("Unknown filter name", filter)
+    return GlobalDockingModel(representation, SimpleFilter(representation.get_num_outputs()), threshold_clash=threshold_clash)

@@ -27,7 +27,7 @@ def _worker(rank, world, port, n_rot, q):
     full = D.gather_best(local, n_rot, rank, world)
     top = D.merge_top_lists([(int(i), 1, 2, 3, float(-(i % 7))) for i in idx.tolist()], K=5)
     if rank == 0:
-        q.put((full, top))
+        q.put((full.tolist(), top))
     dist.destroy_process_group()
 
 
@@ -45,7 +45,7 @@ def test_two_rank_gather_equals_single_process():
         assert p.exitcode == 0
     i = torch.arange(n_rot).float()
     want = torch.stack([-(i % 7), i, i * 2, i * 3], dim=1)
-    assert torch.equal(full, want)
+    assert full == want.tolist()
     single = sorted([(int(k), 1, 2, 3, float(-(k % 7))) for k in range(n_rot)], key=lambda t: t[4])[:5]
     assert top == single
 

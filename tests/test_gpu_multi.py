@@ -41,7 +41,7 @@ def _run(rank, world, port, q, angle_inc):
     docker.rot.R = docker.rot.R[:101]                       # a short, odd-sized rotation set
     best, top = D.dock_sharded(docker, rec, lig)
     if rank == 0:
-        q.put((best, top))
+        q.put((best.tolist(), top))          # plain lists: a tensor in the queue is shared through an fd the child may close first
     if world > 1:
         dist.destroy_process_group()
 
@@ -61,5 +61,5 @@ def test_two_gpu_sharded_dock_equals_single_gpu():
             p.join(timeout=120)
             assert p.exitcode == 0
     (b1, t1), (b2, t2) = out
-    assert torch.equal(b1, b2)
+    assert b1 == b2
     assert t1 == t2

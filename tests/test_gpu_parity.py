@@ -487,3 +487,41 @@ def test_filter_kind_2x1_tile_matches_oracle(filter_kind):
         test_search_full_size_80_matches_oracle()
     finally:
         _lib.set_option("epilogue_tile", 0)
+
+
+# ---- two tcgen05 half-tile epilogue CTAs per SM ---------------------------------------------------------------------
+@pytest.fixture
+def tc_duo_epilogue():
+    _need_experimental()
+    _lib.set_option("epilogue_kind", "tc_duo")
+    yield
+    _lib.set_option("epilogue_kind", "auto")
+
+
+@pytest.mark.parametrize("L,C0,C1,H,n", [(8, 16, 32, 24, 3), (16, 16, 32, 24, 2), (20, 16, 32, 24, 5)])
+def test_tc_duo_epilogue_small_matches_oracle(L, C0, C1, H, n, tc_duo_epilogue):
+    test_search_small_matches_oracle(L, C0, C1, H, n)
+
+
+def test_tc_duo_epilogue_80_matches_oracle(tc_duo_epilogue):
+    test_search_full_size_80_matches_oracle()
+
+
+def test_tc_duo_epilogue_80_many_rotations_same_poses():
+    """33 rotations (odd tail) at L = 80: the two-CTA epilogue and the default one give the same poses, scores to rounding."""
+    _need_experimental()
+    L, C0, C1 = 80, 16, 32
+    rec, rec_clash = synthetic.learned_volumes(L, (C0, C1), seed=31)
+    lig, lig_clash = synthetic.learned_volumes(L, (C0, C1), seed=32)
+    filt = O.FilterWeights.random(C0 + C1, seed=33)
+    Rs = R20[torch.arange(33) * 53 + 2]
+    out = []
+    for kind in ("auto", "tc_duo"):
+        _lib.set_option("epilogue_kind", kind)
+        eng = DockingSearch(L, (C0, C1), max_rot=16, device=DEV)
+        eng.set_receptor(rec, rec_clash); eng.set_ligand(lig, lig_clash); eng.set_filter((filt.W1, filt.b1, filt.W2, filt.b2))
+        out.append(eng.search(Rs, 30.0)[0].cpu())
+        eng.close()
+    _lib.set_option("epilogue_kind", "auto")
+    assert torch.equal(out[0][:, 1:], out[1][:, 1:])
+    assert torch.allclose(out[0][:, 0], out[1][:, 0], rtol=1e-5, atol=1e-6)

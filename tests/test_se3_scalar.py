@@ -53,3 +53,22 @@ def test_basis_is_radial_and_normalised():
     assert torch.allclose(b.reshape(3, -1).norm(dim=1), torch.ones(3), atol=1e-6)
     assert torch.allclose(b, b.transpose(3, 4)) and torch.allclose(b, b.flip(5))
     assert int(b[0].argmax()) == 62                  # innermost shell peaks at the centre voxel
+
+
+def test_select_model_builds_both_families_and_checkpoints_round_trip(tmp_path):
+    """`select_model` mirrors local_train.py:20-47; `GlobalDockingModel.save` / `.load` (DockingModels.py:55-61) round-trip the
+    SE(3) representation, basis buffers included."""
+    import pytest
+    from deeplocalproteindocking_b200 import select_model
+    m = select_model("SE3", "SE3MultiResReprScalar")
+    assert m.representation.get_num_outputs() == [16, 32] and m.filter.fc[0].in_features == 48
+    assert select_model("E3", "E3MultiResRepr4x4").representation.get_num_outputs() == [16, 32]
+    with pytest.raises(Exception, match="Unknown"):
+        select_model("SO3", "x")
+    m.save(str(tmp_path), epoch=3)
+    m2 = select_model("SE3", "SE3MultiResReprScalar")
+    m2.load(str(tmp_path), epoch=3)
+    x = torch.randn(1, 11, 8, 8, 8)
+    with torch.no_grad():
+        a, b = m.representation(x), m2.representation(x)
+    assert torch.equal(a[0], b[0]) and torch.equal(a[1], b[1])
