@@ -156,7 +156,14 @@ DLPD_LINEPLAN(40, 5, 4, 1)
 DLPD_LINEPLAN(64, 8, 4, 1)
 DLPD_LINEPLAN(80, 5, 8, 1)
 DLPD_LINEPLAN(128, 8, 8, 1)
+#ifndef DLPD_LINE160_ALT
+#define DLPD_LINE160_ALT 0      // 1: z lines of the 80^3 box as (2,4) x (5,4) = 8 x 20 instead of (2,5) x (4,4) = 10 x 16
+#endif
+#if DLPD_LINE160_ALT
+DLPD_LINEPLAN(160, 4, 5, 4)
+#else
 DLPD_LINEPLAN(160, 5, 4, 4)
+#endif
 DLPD_LINEPLAN(256, 8, 4, 4)
 // alternative factorisation for the plane kernel's x / y passes (private to it: the receptor spectrum is produced by the same
 // code): 160 = (2,4) x (5,4) gives 20 / 8 tasks per line, i.e. whole rounds for teams of 128 threads on 32 lines
@@ -164,6 +171,10 @@ template <int N> struct PlanePlan : LinePlan<N> {};
 #if DLPD_PLANE_ALT_PLAN
 template <> struct PlanePlan<160> {
     static constexpr int R0 = 4, TA = 5, TB = 4, TAIL = 20;
+};
+#elif DLPD_LINE160_ALT
+template <> struct PlanePlan<160> {          // the plane keeps 10 x 16 whatever the z lines use (its order is private to it)
+    static constexpr int R0 = 5, TA = 4, TB = 4, TAIL = 16;
 };
 #endif
 

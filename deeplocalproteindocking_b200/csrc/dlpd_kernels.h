@@ -89,6 +89,14 @@
                                      // REJECTED: a tile is 2720 rows of 32 contiguous bytes and the TMA unit processes such short
                                      // rows far below HBM speed -- epilogue 7.90 ms vs 3.48 ms per 32 rotations (profiles/r02e)
 #endif
+#ifndef DLPD_EPI_BULK_H1
+#define DLPD_EPI_BULK_H1 1           // tcgen05 epilogue: the level-1 hidden column of a tile (N1 * H complex, 15 KB at 80^3, contiguous
+                                     // in HBM) arrives by ONE cp.async.bulk + mbarrier instead of 960 16-byte cp.async of the producers
+#endif
+#if defined(DLPD_ABLATE_EPI_LOAD)
+#undef DLPD_EPI_BULK_H1
+#define DLPD_EPI_BULK_H1 0           // the load ablation issues nothing, so nobody may wait for a bulk copy either
+#endif
 #ifndef DLPD_EPI_TC_EXTRA
 #define DLPD_EPI_TC_EXTRA 64         // tcgen05 epilogue: this many extra threads join the inverse-z transform passes (they do not score)
 #endif
@@ -1362,6 +1370,7 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0, bool DUO_ = f
     static constexpr int NT = NC + NX + NPROD;
     static constexpr int BUF = N * NL0, HB = N1 * H;
     static constexpr int HBS = DUO ? 0 : HB;                       // staged level-1 hidden column (none in DUO: read from global)
+    static constexpr bool BULK_H1 = TC_OK && !USE_TMA && (HBS > 0) && (DLPD_EPI_BULK_H1 != 0) && ((HB * (int)sizeof(cpx)) % 16 == 0);
 #if DLPD_EXPERIMENTAL
     static constexpr int MLP_BYTES = TC_ ? ((int)sizeof(MlpDev<C0, H>) + 15) / 16 * 16 : 0;      // shared-memory copy of the MMA fragments
 #else
@@ -1397,13 +1406,20 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0, bool DUO_ = f
                 if (kz >= N) { kz -= N; ++c; }
             }
         }
-        if constexpr (HBS > 0) {
+        if constexpr (HBS > 0 && !BULK_H1) {
             const cpx* hs = p.h1 + ((long)pair * T * T + r4) * HB;      // level-1 column (x/2, y/2): N1*H contiguous
             DLPD_FOR_TASKS_SUB(t, HB / 2, NPROD, NC + NX) cp_async16(hb + 2 * t, hs + 2 * t);
         }
     }
 
 #if !defined(DLPD_EMU)
+    // level-1 hidden column of a tile by one bulk copy (TMA engine, contiguous 15 KB): issued by ONE thread, completes on `bar`
+    static DLPD_DEV void issue_h1_bulk(const Params& p, int tile, cpx* hb, uint64_t* bar) {
+        const int pair = tile / TILES, r = tile % TILES;
+        const int r4 = tile_xh(r) * T + (tile_y0(r) >> 1);
+        tc::mbar_expect_tx(bar, (uint32_t)(HB * sizeof(cpx)));
+        tc::bulk_g2s(hb, p.h1 + ((long)pair * T * T + r4) * HB, (uint32_t)(HB * sizeof(cpx)), bar);
+    }
     // the same loads as ONE tensor-map box (all channels and kz' of the tile -> [kz'][c][8 floats]) and ONE bulk copy (the
     // level-1 column), issued by a single thread; both complete on `bar`
     static DLPD_DEV void issue_tma(const Params& p, int tile, cpx* b0, cpx* hb, uint64_t* bar) {
@@ -1707,6 +1723,14 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0, bool DUO_ = f
         DLPD_UNROLL
         for (int c = 0; c < C0; ++c) x[c] = v0[c * XY];
         uint64_t* bar = ts.bars + 2 * g;
+#if defined(DLPD_ABLATE_EPI_MLP)
+        if (valid) {                                          // timing experiment: no staging, no MMA, no read-back
+            const unsigned int lin0 = (unsigned int)(((x0 + (xy & 1)) * N + (y0 + (xy >> 1))) * N + z);
+            finish_voxel(p, fadd2_(x[0], hz[0]), v0[C0 * XY], lin0, rotA, rotB, hasB, bestA, bestB);
+        }
+        (void)bar; (void)lane_addr; (void)colA; (void)colD0; (void)colD1; (void)gthreads;
+        return;
+#endif
         DLPD_UNROLL
         for (int rot = 0; rot < 2; ++rot) {
             uint32_t hi[C0], lo[C0];
@@ -1850,6 +1874,12 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0, bool DUO_ = f
         if (bx < p.n_tiles) issue_loads(p, bx, bufs, hbufs);
         cp_async_commit();
         cp_async_wait_pending();
+#if !defined(DLPD_EMU)
+        uint32_t h1phase = 0;
+        if constexpr (BULK_H1) {
+            if (threadIdx.x == NC + NX && bx < p.n_tiles) issue_h1_bulk(p, bx, hbufs, ts.bars + 14);
+        }
+#endif
         unsigned long long bestA = ~0ull, bestB = ~0ull;
         int cur_pair = -1, slot = 0;
 #if defined(DLPD_EMU)
@@ -1870,7 +1900,14 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0, bool DUO_ = f
             }
             if (producer) {
 #if !defined(DLPD_ABLATE_EPI_LOAD)
-                if (tile + p.grid < p.n_tiles) issue_loads(p, tile + p.grid, bufs + (slot ^ 1) * BUF, hbufs + (slot ^ 1) * HBS);
+                if (tile + p.grid < p.n_tiles) {
+                    issue_loads(p, tile + p.grid, bufs + (slot ^ 1) * BUF, hbufs + (slot ^ 1) * HBS);
+#if !defined(DLPD_EMU)
+                    if constexpr (BULK_H1) {
+                        if (threadIdx.x == NC + NX) issue_h1_bulk(p, tile + p.grid, hbufs + (slot ^ 1) * HBS, ts.bars + 14 + (slot ^ 1));
+                    }
+#endif
+                }
 #endif
                 cp_async_commit();
                 cp_async_wait_pending();
@@ -1882,6 +1919,10 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0, bool DUO_ = f
                     if constexpr (PKT) transform_tile_pk(tmT, b0, tw0, tw0 + N);
                     else transform_tile(tmT, b0, tw0);
                     if (threadIdx.x < NC) {
+                        if constexpr (BULK_H1) {                 // the tile's level-1 column has landed (mbarrier phase of this slot)
+                            tc::mbar_wait(ts.bars + 14 + slot, (h1phase >> slot) & 1u);
+                            h1phase ^= 1u << slot;
+                        }
                         const cpx* hcol = DUO ? p.h1 + ((long)pair * T * T + tile_xh(r) * T + (tile_y0(r) >> 1)) * HB
                                               : hbufs + slot * HBS;
                         score_voxels_tc(p, tm, b0, hcol, ts, pair, 2 * tile_xh(r), tile_y0(r), bestA, bestB);
