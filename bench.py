@@ -414,7 +414,10 @@ def main():
     full_set = (args.rot_batch == 0 and args.config == 2) or (args.full_set and not multi_pair)
     shard = D.shard_indices(n_rot_total, rank, world) if not multi_pair else torch.arange(n_rot_total)
     if full_set:
-        nb = -(-D.padded_shard_size(n_rot_total, world) // args.steps)     # ceil: the K steps cover the shard exactly once
+        # the K steps cover the shard exactly once; a step is a whole number of the library's internal chunks (max_rot
+        # rotations) so that only the last step of a rank ends in a partial chunk
+        nb = -(-D.padded_shard_size(n_rot_total, world) // args.steps)
+        nb = -(-nb // args.max_rot) * args.max_rot
     else:
         nb = args.rot_batch or 64
     n_steps_total = args.warmup + args.steps
@@ -505,6 +508,8 @@ def main():
     # ---------------- device-resident leg (value, roofline) -------------------------------------------------
     for s in range(args.warmup):
         device_step(s)
+    if full_set:                                     # the closing collective once outside the region too (NCCL connects lazily)
+        D.gather_best(torch.zeros(shard.numel(), 4, device=device), n_rot_total, rank, world)
     barrier()
     eng.profile(True)
     sampler = ClockSampler(local_rank) if rank == 0 else None

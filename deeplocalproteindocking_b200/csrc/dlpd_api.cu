@@ -229,9 +229,11 @@ template <int L> struct Tile {
 // box sizes the single-level kernels are compiled for
 #define DLPD_OP_SIZES(X) X(4) X(8) X(10) X(16) X(20) X(40) X(64) X(80) X(128)
 // (L, C0, C1, H) the fused search is compiled for
+// (16, 32, 24) is the reference's model (multiplier = 8, local_train.py:23,30); (32, 64, 48) is the representation classes' own
+// default multiplier = 16 (ProteinRepresentationModels.py:24,79); (4, 6, 5) is the golden-fixture size
 #define DLPD_SEARCH_CONFIGS(X) \
     X(8, 4, 6, 5) X(16, 4, 6, 5) X(20, 4, 6, 5) X(8, 16, 32, 24) X(16, 16, 32, 24) X(20, 16, 32, 24) X(80, 16, 32, 24) \
-    X(128, 16, 32, 24)
+    X(128, 16, 32, 24) X(16, 32, 64, 48) X(20, 32, 64, 48) X(80, 32, 64, 48)
 
 static bool op_size_ok(int L) {
     switch (L) {
@@ -285,6 +287,13 @@ static Options g_defaults;
 static std::mutex g_mutex;               // guards g_defaults and the standalone operators' workspaces
 #ifndef DLPD_FILTER_DEFAULT
 #define DLPD_FILTER_DEFAULT DLPD_FILTER_TCGEN05      // what DLPD_FILTER_AUTO means where the tcgen05 kernel exists (else FP32)
+#endif
+#ifndef DLPD_HID_TCGEN05
+#define DLPD_HID_TCGEN05 0            // level-1 part of the first filter layer on the tensor cores too (HiddenL1<..., FK = 2>):
+                                      // parity-green, measured on B200 and REJECTED -- 1.30 ms vs 1.10 ms per 32 rotations.  K = 32
+                                      // needs two staging rounds per rotation through the warpgroup's 32 A columns (two CTAs per SM
+                                      // share the 512 TMEM columns), i.e. four exposed MMA round trips per CTA, and the FP32
+                                      // contraction it replaces is only a third of that kernel (profiles/r02)
 #endif
 #ifndef DLPD_EPILOGUE_DEFAULT_DUO
 #define DLPD_EPILOGUE_DEFAULT_DUO 0
@@ -659,11 +668,18 @@ template <int C0, int C1, int H> static void fill_filter(const dlpd_plan* p, Fil
     f.b2 = p->b2;
 }
 
+static int filter_kind_of(const dlpd_plan* p);
 template <int L, int C0, int C1, int H> static int launch_hidden(dlpd_plan* p, int P, dlpd_stream_t st) {
     typedef HiddenL1<L, C0, C1, H> K;
     typename K::Params e;
     e.s2_1 = p->s2_1; e.h1 = p->h1; e.tw1 = p->tw1;
     fill_filter(p, e.filt);
+#if !defined(DLPD_EMU)
+    typedef HiddenL1<L, C0, C1, H, 2> KT;             // C1 -> H contraction on tcgen05 / TMEM
+    if constexpr (KT::TC_OK && DLPD_HID_TCGEN05) {
+        if (filter_kind_of(p) == DLPD_FILTER_TCGEN05) return launch<KT>(dim3(KT::N1 / KT::YT, KT::N1, P), e, st);
+    }
+#endif
     return launch<K>(dim3(K::N1 / K::YT, K::N1, P), e, st);
 }
 

@@ -1214,7 +1214,10 @@ template <int C0, int C1, int H> struct HidParams {
     FilterW<C0, C1, H> filt;
 };
 
-template <int L_, int C0, int C1, int H> struct HiddenL1 {
+// FK_ = 2: the C1 -> H contraction on tcgen05.mma.kind::tf32 (3 x TF32 split, operand and accumulators in TMEM) like the
+// epilogue's level-0 half: one thread per level-1 voxel (yl, z1) of the CTA, K staged 16 channels at a time into the
+// warpgroup's 32 A columns (hi | lo), accumulating over the C1 / 16 rounds; two CTAs per SM share the 512 TMEM columns.
+template <int L_, int C0, int C1, int H, int FK_ = 0> struct HiddenL1 {
     typedef HidParams<C0, C1, H> Params;
     static constexpr int N1 = L_, YT = DLPD_HID_YT, NL = C1 * YT;
     static constexpr int P1 = NL + 4;                        // row pitch: 16-byte rows, conflict-free (yl, z1) reads
@@ -1222,12 +1225,107 @@ template <int L_, int C0, int C1, int H> struct HiddenL1 {
     static constexpr int VP = (YT * N1 + 31) / 32 * 32;      // (yl, z1) padded to whole warps (warp-uniform hidden group)
     static constexpr int NT = (N1 >= 64) ? DLPD_HID_NT : 128;
     static constexpr bool PKT = DLPD_HID_PACKED_TW && (N1 / (2 * LinePlan<N1>::R0) > 1);
-    static constexpr int SMEM = (N1 * P1 + N1 + (PKT ? N1 : 0)) * (int)sizeof(cpx);
+    // tcgen05 path
+    static constexpr int NVOX = YT * N1, NSC = VP, NWG = (NVOX + 127) / 128, HP = (H + 7) / 8 * 8, KH = 16;
+    static constexpr int TC_COLS_WG = 2 * KH + 2 * HP;
+    static constexpr int TC_COLS = (NWG * TC_COLS_WG <= 32) ? 32 : (NWG * TC_COLS_WG <= 64) ? 64 : (NWG * TC_COLS_WG <= 128) ? 128 : 256;
+    static constexpr bool TC_OK = (FK_ == 2) && (C1 % KH == 0) && (H % 8 == 0) && (NWG * TC_COLS_WG <= 256) && (NSC <= NT) && (NWG <= 6);
+    static constexpr int TC_BW = 2 * C1 * HP;                // floats: [hi | lo][C1 / 4 k-chunks][HP rows][4]
+    static constexpr int TC_BYTES = TC_OK ? (TC_BW * 4 + 8 * 8 + 16) : 0;
+    static constexpr int SMEM = (N1 * P1 + N1 + (PKT ? N1 : 0)) * (int)sizeof(cpx) + TC_BYTES;
     static_assert(N1 % YT == 0, "level-1 y tile");
     struct LoadS2 {          // element e = kz' of line l = c*YT + yl
         const cpx* s;
         DLPD_DEV cpx operator()(int l, int e) const { return __ldg(s + ((long)(l / YT) * N1 + e) * N1 * N1 + (l % YT)); }
     };
+#if !defined(DLPD_EMU)
+    // h1[voxel][j] = b1[j] + sum_c W1[j][C0 + c] corr1[c][voxel] for the thread's voxel, both rotations of the pair
+    static DLPD_DEV void contract_tc(const Params& p, const cpx* b1, cpx* h1, uint32_t tmem_base, uint32_t bw_addr, uint64_t* bars) {
+        const int t = (int)threadIdx.x;
+        const bool valid = t < NVOX;
+        const int tv = valid ? t : 0;
+        const int yl = tv % YT, z1 = tv / YT;
+        const int g = t >> 7, q = (t >> 5) & 3;
+        const int gthreads = (NSC - 128 * g) < 128 ? (NSC - 128 * g) : 128;
+        const uint32_t lane_addr = tmem_base + ((uint32_t)(q * 32) << 16);
+        const uint32_t colA = (uint32_t)(g * TC_COLS_WG), colD0 = colA + 2 * KH, colD1 = colD0 + HP;
+        constexpr uint32_t IDESC = tc::idesc_tf32(128, HP);
+        constexpr uint32_t LBO = HP * 16, SBO = 128, KSTEP = 2 * HP * 16, BLO = C1 * HP * 4;   // bytes
+        const cpx* v0 = b1 + z1 * P1 + yl;
+        uint64_t* bar = bars + g;
+        uint32_t phase = 0;
+        bool first = true;
+        DLPD_UNROLL
+        for (int rot = 0; rot < 2; ++rot) {
+            DLPD_UNROLL
+            for (int kr = 0; kr < C1 / KH; ++kr) {
+                uint32_t hi[KH], lo[KH];
+                DLPD_UNROLL
+                for (int c = 0; c < KH; ++c) {
+                    const cpx xv = v0[(kr * KH + c) * YT];
+                    const float a = rot ? xv.y : xv.x, ah = tc::tf32_hi(a);
+                    hi[c] = __float_as_uint(ah);
+                    lo[c] = __float_as_uint(a - ah);
+                }
+                if (!first) {                                 // the A columns are free once the previous round's MMAs have completed
+                    tc::mbar_wait(bar, phase);
+                    tc::fence_after_sync();
+                    phase ^= 1;
+                }
+                first = false;
+                DLPD_UNROLL
+                for (int h8 = 0; h8 < KH / 8; ++h8) {
+                    uint32_t t0[8], t1[8];
+                    DLPD_UNROLL
+                    for (int i = 0; i < 8; ++i) { t0[i] = hi[8 * h8 + i]; t1[i] = lo[8 * h8 + i]; }
+                    tc::st8(lane_addr + colA + 8 * h8, t0);
+                    tc::st8(lane_addr + colA + KH + 8 * h8, t1);
+                }
+                tc::wait_st();
+                tc::fence_before_sync();
+                named_barrier_sync(2 + g, gthreads);
+                if (q == 0 && tc::elect_one()) {
+                    tc::fence_after_sync();
+                    const uint32_t d = tmem_base + (rot ? colD1 : colD0), a = tmem_base + colA;
+                    DLPD_UNROLL
+                    for (int s = 0; s < KH / 8; ++s) {
+                        const int ks = kr * (KH / 8) + s;                          // 8-channel step within the C1 channels
+                        const uint64_t dhi = tc::smem_desc_kmajor(bw_addr + ks * KSTEP, LBO, SBO);
+                        const uint64_t dlo = tc::smem_desc_kmajor(bw_addr + BLO + ks * KSTEP, LBO, SBO);
+                        tc::mma_tf32_ts(d, a + KH + 8 * s, dhi, IDESC, (kr > 0 || s > 0));      // a_lo w_hi
+                        tc::mma_tf32_ts(d, a + 8 * s, dlo, IDESC, 1);                           // a_hi w_lo
+                        tc::mma_tf32_ts(d, a + 8 * s, dhi, IDESC, 1);                           // a_hi w_hi
+                    }
+                    tc::mma_commit(bar);
+                }
+                __syncwarp();
+            }
+        }
+        tc::mbar_wait(bar, phase);                            // the last round: both accumulators are complete
+        tc::fence_after_sync();
+        float acc[2][HP];
+        DLPD_UNROLL
+        for (int rot = 0; rot < 2; ++rot) {
+            uint32_t r[HP / 8][8];
+            DLPD_UNROLL
+            for (int u = 0; u < HP / 8; ++u) tc::ld8(lane_addr + (rot ? colD1 : colD0) + 8 * u, r[u]);
+            tc::wait_ld();
+            DLPD_UNROLL
+            for (int u = 0; u < HP / 8; ++u) {
+                DLPD_UNROLL
+                for (int i = 0; i < 8; ++i) acc[rot][8 * u + i] = __uint_as_float(r[u][i]);
+            }
+        }
+        if (valid) {
+            cpx* d = h1 + ((long)yl * N1 + z1) * H;
+            DLPD_UNROLL
+            for (int j = 0; j < H; j += 2)
+                store_cpx2(d + j, make_float2(acc[0][j] + p.filt.b1[j], acc[1][j] + p.filt.b1[j]),
+                           make_float2(acc[0][j + 1] + p.filt.b1[j + 1], acc[1][j + 1] + p.filt.b1[j + 1]));
+        }
+    }
+#endif
+
     // grid: x = N1 / YT, y = N1 (x1), z = P
     static DLPD_DEV void body(const Params& p, int bx, int by, int bz, char* smem) {
         cpx* b1 = reinterpret_cast<cpx*>(smem);        // [kz1][P1]   line = c*YT + yl
@@ -1241,6 +1339,28 @@ template <int L_, int C0, int C1, int H> struct HiddenL1 {
             htw1 = pk;
         }
         const CtaTeam<NT, true> tm;
+#if !defined(DLPD_EMU)
+        uint32_t tmem_base = 0;
+        float* Bw = reinterpret_cast<float*>(tw1 + N1 + (PKT ? N1 : 0));
+        uint64_t* bars = reinterpret_cast<uint64_t*>(Bw + TC_BW);
+        uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 8);
+        if constexpr (TC_OK) {
+            DLPD_FOR_TASKS(i, TC_BW, NT) {
+                const int e = i & 3, n = (i >> 2) % HP, kc = (i / (4 * HP)) % (C1 / 4), part = i / (C1 * HP);
+                const int c = 4 * kc + e;
+                const float v = n < H ? p.filt.W1t[(C0 + c) * H + n] : 0.0f;
+                const float hi = tc::tf32_hi(v);
+                Bw[i] = part == 0 ? hi : (v - hi);
+            }
+            if (threadIdx.x < 32) tc::tmem_alloc(tmem_slot, TC_COLS);
+            if (threadIdx.x == 0) {
+                for (int i = 0; i < NWG; ++i) tc::mbar_init(bars + i, 1);
+                tc::mbar_fence_init();
+            }
+            tc::fence_proxy_async();
+            tc::fence_before_sync();           // published by the barrier that follows the tile load below
+        }
+#endif
 #if DLPD_HID_DIRECT
         {
             // the first inverse pass reads its inputs straight from global memory (two tasks = 2 x TAIL loads in flight per
@@ -1286,6 +1406,17 @@ template <int L_, int C0, int C1, int H> struct HiddenL1 {
 #endif
         team_inv_head<N1, NL, P1, LinePlan<N1>, PKT>(tm, b1, htw1, LineMul<1>());
         cpx* h1 = p.h1 + (((long)pair * N1 + x1) * N1 + y0) * N1 * H;
+#if !defined(DLPD_EMU)
+        if constexpr (TC_OK) {
+            tc::fence_after_sync();
+            tmem_base = *tmem_slot;
+            if (threadIdx.x < NSC) contract_tc(p, b1, h1, tmem_base, tc::smem_u32(Bw), bars);
+            tc::fence_before_sync();
+            __syncthreads();
+            if (threadIdx.x < 32) tc::tmem_dealloc(tmem_base, TC_COLS);
+            return;
+        }
+#endif
         DLPD_FOR_TASKS(t, (H / JG) * VP, NT) {
             const int v = t % VP, jg = t / VP;
             if (v < YT * N1) {
@@ -1371,6 +1502,10 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0, bool DUO_ = f
     static constexpr int BUF = N * NL0, HB = N1 * H;
     static constexpr int HBS = DUO ? 0 : HB;                       // staged level-1 hidden column (none in DUO: read from global)
     static constexpr bool BULK_H1 = TC_OK && !USE_TMA && (HBS > 0) && (DLPD_EPI_BULK_H1 != 0) && ((HB * (int)sizeof(cpx)) % 16 == 0);
+    // level-1 column buffers: two (the next tile's column is prefetched) or, where two do not fit next to the tile buffers
+    // (wide models), ONE that the bulk copy refills at the top of every tile while the transform passes run
+    static constexpr int SMEM2 = (2 * BUF + 2 * HBS + N) * (int)sizeof(cpx) + 64 * 8 + 16 * 1024;      // estimate with two
+    static constexpr int NHB = (BULK_H1 && SMEM2 > 227 * 1024) ? 1 : 2;
 #if DLPD_EXPERIMENTAL
     static constexpr int MLP_BYTES = TC_ ? ((int)sizeof(MlpDev<C0, H>) + 15) / 16 * 16 : 0;      // shared-memory copy of the MMA fragments
 #else
@@ -1381,7 +1516,7 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0, bool DUO_ = f
     static constexpr int TC_BW = 2 * C0 * HP;                      // floats
     static constexpr int TC_BYTES = TC_OK ? (TC_BW * 4 + 16 * 8 + 16) : 0;       // bars[0 .. 2 NWG) MMA, bars[14], bars[15] tile landed
     static constexpr bool PKT = DLPD_EPI_PACKED_TW && (N / (2 * LinePlan<N>::R0) > 1);      // packed twiddles of the inverse head pass
-    static constexpr int SMEM = (2 * BUF + 2 * HBS + N + (PKT ? N : 0)) * (int)sizeof(cpx) + 64 * 8 + MLP_BYTES + TC_BYTES;
+    static constexpr int SMEM = (2 * BUF + NHB * HBS + N + (PKT ? N : 0)) * (int)sizeof(cpx) + 64 * 8 + MLP_BYTES + TC_BYTES;
     static constexpr int QPT = NPROD / TY;         // (c, kz) rows covered per sweep of the producer threads
     static constexpr int TILES = T * TPR;          // tiles per pair
     static_assert(HB % 2 == 0 && NPROD % 32 == 0 && NC % 32 == 0 && (TY_ == 1 || TY_ == 2), "team shapes");
@@ -1806,7 +1941,7 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0, bool DUO_ = f
     static DLPD_DEV void body(const Params& p, int bx, int, int, char* smem) {
         cpx* bufs = reinterpret_cast<cpx*>(smem);      // [2][kz][NL0]
         cpx* hbufs = bufs + 2 * BUF;                   // [2][z'][H]  (rotA, rotB): b1 + level-1 part of the hidden layer
-        cpx* tw0 = hbufs + 2 * HBS;
+        cpx* tw0 = hbufs + NHB * HBS;
         unsigned long long* red = reinterpret_cast<unsigned long long*>(tw0 + N + (PKT ? N : 0));
         MlpDev<C0, H>* ms = reinterpret_cast<MlpDev<C0, H>*>(red + 64);
         DLPD_FOR_TASKS(t, N, NT) tw0[t] = p.tw0[t];
@@ -1876,7 +2011,7 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0, bool DUO_ = f
         cp_async_wait_pending();
 #if !defined(DLPD_EMU)
         uint32_t h1phase = 0;
-        if constexpr (BULK_H1) {
+        if constexpr (BULK_H1 && NHB == 2) {
             if (threadIdx.x == NC + NX && bx < p.n_tiles) issue_h1_bulk(p, bx, hbufs, ts.bars + 14);
         }
 #endif
@@ -1900,10 +2035,15 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0, bool DUO_ = f
             }
             if (producer) {
 #if !defined(DLPD_ABLATE_EPI_LOAD)
-                if (tile + p.grid < p.n_tiles) {
-                    issue_loads(p, tile + p.grid, bufs + (slot ^ 1) * BUF, hbufs + (slot ^ 1) * HBS);
 #if !defined(DLPD_EMU)
-                    if constexpr (BULK_H1) {
+                if constexpr (BULK_H1 && NHB == 1) {             // single column buffer: everyone is done with the previous tile's
+                    if (threadIdx.x == NC + NX) issue_h1_bulk(p, tile, hbufs, ts.bars + 14);
+                }
+#endif
+                if (tile + p.grid < p.n_tiles) {
+                    issue_loads(p, tile + p.grid, bufs + (slot ^ 1) * BUF, hbufs + (NHB == 2 ? (slot ^ 1) : 0) * HBS);
+#if !defined(DLPD_EMU)
+                    if constexpr (BULK_H1 && NHB == 2) {
                         if (threadIdx.x == NC + NX) issue_h1_bulk(p, tile + p.grid, hbufs + (slot ^ 1) * HBS, ts.bars + 14 + (slot ^ 1));
                     }
 #endif
@@ -1919,17 +2059,18 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0, bool DUO_ = f
                     if constexpr (PKT) transform_tile_pk(tmT, b0, tw0, tw0 + N);
                     else transform_tile(tmT, b0, tw0);
                     if (threadIdx.x < NC) {
-                        if constexpr (BULK_H1) {                 // the tile's level-1 column has landed (mbarrier phase of this slot)
-                            tc::mbar_wait(ts.bars + 14 + slot, (h1phase >> slot) & 1u);
-                            h1phase ^= 1u << slot;
+                        constexpr int HS = (NHB == 2) ? 1 : 0;    // column buffer of this tile: its slot, or the single one
+                        if constexpr (BULK_H1) {                 // the tile's level-1 column has landed (mbarrier phase of its buffer)
+                            tc::mbar_wait(ts.bars + 14 + HS * slot, (h1phase >> (HS * slot)) & 1u);
+                            h1phase ^= 1u << (HS * slot);
                         }
                         const cpx* hcol = DUO ? p.h1 + ((long)pair * T * T + tile_xh(r) * T + (tile_y0(r) >> 1)) * HB
-                                              : hbufs + slot * HBS;
+                                              : hbufs + HS * slot * HBS;
                         score_voxels_tc(p, tm, b0, hcol, ts, pair, 2 * tile_xh(r), tile_y0(r), bestA, bestB);
                     }
                 } else
 #endif
-                score_tile(p, tm, bufs + slot * BUF, hbufs + slot * HBS, tw0, ms, pair, 2 * tile_xh(r), tile_y0(r), bestA, bestB);
+                score_tile(p, tm, bufs + slot * BUF, hbufs + (NHB == 2 ? slot : 0) * HBS, tw0, ms, pair, 2 * tile_xh(r), tile_y0(r), bestA, bestB);
             }
         }
         if (cur_pair >= 0) flush_best(p, cur_pair, bestA, bestB, red);

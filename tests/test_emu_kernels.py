@@ -398,3 +398,8 @@ def test_emu_options_belong_to_the_plan():
         assert torch.equal(a.search(Rs, 3.0)[0], out[0])
     finally:
         a.close(); b.close()
+
+
+def test_emu_wide_model_16_matches_oracle():
+    """Kernel bodies at the wide model (32 + 64 channels, H = 48) through the emulation."""
+    test_emu_search_matches_oracle(16, 32, 64, 48, 2)

@@ -115,7 +115,7 @@ def _check_against_oracle(best, scores, rec, lig, rf, lf, Rs, filt, tau, clash_r
 
 
 @pytest.mark.parametrize("L,C0,C1,H,n", [(8, 4, 6, 5, 5), (16, 4, 6, 5, 4), (20, 4, 6, 5, 3), (8, 16, 32, 24, 3),
-                                         (16, 16, 32, 24, 2), (20, 16, 32, 24, 5)])
+                                         (16, 16, 32, 24, 2), (20, 16, 32, 24, 5), (16, 32, 64, 48, 2), (20, 32, 64, 48, 3)])
 def test_search_small_matches_oracle(L, C0, C1, H, n):
     rec, lig, rf, lf = _case(L, C0, C1, seed=L * 10 + C0)
     filt = O.FilterWeights.random(C0 + C1, H, seed=3)
@@ -469,7 +469,7 @@ def filter_kind(request):
     _lib.set_option("filter_kind", "auto")
 
 
-@pytest.mark.parametrize("L,C0,C1,H,n", [(8, 16, 32, 24, 3), (16, 16, 32, 24, 2), (20, 16, 32, 24, 5)])
+@pytest.mark.parametrize("L,C0,C1,H,n", [(8, 16, 32, 24, 3), (16, 16, 32, 24, 2), (20, 16, 32, 24, 5), (20, 32, 64, 48, 3)])
 def test_filter_kind_small_matches_oracle(L, C0, C1, H, n, filter_kind):
     """Both shipped forms of the first filter layer at sizes with partly filled warpgroups (64 / 128 / 160 translations per tile)."""
     test_search_small_matches_oracle(L, C0, C1, H, n)
@@ -525,3 +525,19 @@ def test_tc_duo_epilogue_80_many_rotations_same_poses():
     _lib.set_option("epilogue_kind", "auto")
     assert torch.equal(out[0][:, 1:], out[1][:, 1:])
     assert torch.allclose(out[0][:, 0], out[1][:, 0], rtol=1e-5, atol=1e-6)
+
+
+def test_search_80_wide_model_matches_oracle():
+    """The representation classes' own default width (multiplier = 16: 32@80^3 + 64@40^3, H = 48,
+    ProteinRepresentationModels.py:24,79): 2x1 epilogue tile, ONE level-1 column buffer refilled by a bulk copy per tile,
+    160 TMEM columns per warpgroup.  Two rotations (one packed pair) vs the fp64 oracle."""
+    L, C0, C1 = 80, 32, 64
+    rec, rec_clash = synthetic.learned_volumes(L, (C0, C1), seed=71)
+    lig, lig_clash = synthetic.learned_volumes(L, (C0, C1), seed=72)
+    filt = O.FilterWeights.random(C0 + C1, seed=73)
+    Rs = R20[[5, 1500]]
+    eng = DockingSearch(L, (C0, C1), max_rot=2, device=DEV)
+    eng.set_receptor(rec, rec_clash); eng.set_ligand(lig, lig_clash); eng.set_filter((filt.W1, filt.b1, filt.W2, filt.b2))
+    best, _ = eng.search(Rs, 30.0)
+    eng.close()
+    _check_against_oracle(best.cpu(), None, rec, lig, rec_clash, lig_clash, Rs, filt, 30.0)
