@@ -376,7 +376,7 @@ def main():
     ap.add_argument("--ref-rot-per-step", type=int, default=2)
     ap.add_argument("--config", type=int, default=2, choices=sorted(CONFIGS), help="BASELINE.json config (1-based); 2 is the bench line")
     ap.add_argument("--plane-mode", default="auto", choices=["auto", "single", "cluster"], help="plane-stage kernel (tuning)")
-    ap.add_argument("--epilogue-kind", default="auto", choices=["auto", "classic", "pipelined", "duo", "fused", "tc_duo"], help="epilogue kernel (tuning; non-classic kinds need an experimental build)")
+    ap.add_argument("--epilogue-kind", default="auto", choices=["auto", "classic", "pipelined", "duo", "fused", "tc_duo", "pipe_tc"], help="epilogue kernel (tuning; non-classic kinds need an experimental build)")
     ap.add_argument("--filter-kind", default="auto", choices=["auto", "fp32", "tensor", "tcgen05"], help="first filter layer: tcgen05/TMEM (auto), FFMA2 chain, or mma.sync (experimental build)")
     ap.add_argument("--epilogue-tile", type=int, default=0, choices=[0, 1, 2], help="epilogue tile shape (tuning)")
     args = ap.parse_args()

@@ -50,7 +50,7 @@ SIGNATURES = {
 
 CENTER_MODES = {"box": 0, "grid": 1}
 OPTIONS = {"plane_mode": 1, "epilogue_tile": 2, "epilogue_kind": 3, "filter_kind": 4}      # DLPD_OPT_* of include/dlpd.h
-EPILOGUE_KINDS = {"auto": 0, "classic": 1, "pipelined": 2, "duo": 3, "fused": 4, "tc_duo": 5}
+EPILOGUE_KINDS = {"auto": 0, "classic": 1, "pipelined": 2, "duo": 3, "fused": 4, "tc_duo": 5, "pipe_tc": 6}
 PLANE_MODES = {"auto": 0, "single": 1, "cluster": 2}
 FILTER_KINDS = {"auto": 0, "fp32": 1, "tensor": 2, "tcgen05": 3}
 BUILD_EXPERIMENTAL, BUILD_EMULATION = 1, 2

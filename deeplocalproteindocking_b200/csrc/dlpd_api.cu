@@ -791,6 +791,25 @@ static int launch_epilogue_pipe(dlpd_plan* p, int n, int P, float tau, float* ou
         return fail(DLPD_EINVAL, "the pipelined epilogue does not fit shared memory at this box size");
     }
 }
+#if !defined(DLPD_EMU)
+template <int L, int C0, int C1, int H>
+static int launch_epilogue_pipe_tc(dlpd_plan* p, int n, int P, float tau, float* out_scores, const CandArgs& ca, dlpd_stream_t st) {
+    typedef EpiloguePipeTC<L, C0, C1, H> K;
+    if constexpr (K::OK && K::SMEM <= SMEM_MAX) {
+        typename K::Params e;
+        e.s2_0 = p->s2_0; e.h1 = p->h1; e.best = p->best; e.score_out = out_scores;
+        e.tw0 = p->tw0; e.n_rot = n; e.tau = tau;
+        e.cand = ca.cand; e.cand_count = ca.count; e.cand_cap = ca.cap; e.cand_key = ca.key; e.rot_base = ca.rot_base;
+        e.n_tiles = P * L * L;                      // 2x2 groups
+        e.mlp = nullptr;
+        e.grid = e.n_tiles < p->sm_count ? e.n_tiles : p->sm_count;
+        fill_filter(p, e.filt);
+        return launch<K>(dim3(e.grid), e, st);
+    } else {
+        return fail(DLPD_EINVAL, "the pipelined tcgen05 epilogue is not available for this configuration");
+    }
+}
+#endif
 template <int L, int C0, int C1, int H>
 static int launch_epilogue_fused(dlpd_plan* p, int n, int P, float tau, float* out_scores, const CandArgs& ca, dlpd_stream_t st) {
     typedef EpilogueFused<L, C0, C1, H> K;
@@ -840,6 +859,9 @@ static int launch_epilogue(dlpd_plan* p, int n, int P, float tau, float* out_sco
     const bool fused_fits = EpilogueFused<L, C0, C1, H>::SMEM <= SMEM_MAX;
     if (ek == DLPD_EPILOGUE_FUSED || (ek == DLPD_EPILOGUE_AUTO && DLPD_EPILOGUE_DEFAULT_FUSED && fused_fits && !et))
         return launch_epilogue_fused<L, C0, C1, H>(p, n, P, tau, out_scores, ca, st);
+#if !defined(DLPD_EMU)
+    if (ek == DLPD_EPILOGUE_PIPE_TC) return launch_epilogue_pipe_tc<L, C0, C1, H>(p, n, P, tau, out_scores, ca, st);
+#endif
     const bool pipe_fits = EpiloguePipe<L, C0, C1, H>::SMEM <= SMEM_MAX;
     if (ek == DLPD_EPILOGUE_PIPELINED || (ek == DLPD_EPILOGUE_AUTO && DLPD_EPILOGUE_DEFAULT_PIPELINED && pipe_fits && !et))
         return launch_epilogue_pipe<L, C0, C1, H>(p, n, P, tau, out_scores, ca, st);
@@ -1114,7 +1136,7 @@ static int apply_option(Options& o, int key, int value) {
             o.plane_mode = value;
             return 0;
         case DLPD_OPT_EPILOGUE_KIND:
-            if (value < DLPD_EPILOGUE_AUTO || value > DLPD_EPILOGUE_TC_DUO) return fail(DLPD_EINVAL, "bad epilogue kind");
+            if (value < DLPD_EPILOGUE_AUTO || value > DLPD_EPILOGUE_PIPE_TC) return fail(DLPD_EINVAL, "bad epilogue kind");
 #if !DLPD_EXPERIMENTAL
             if (value > DLPD_EPILOGUE_CLASSIC)
                 return fail(DLPD_EINVAL, "this epilogue variant is only compiled with -DDLPD_EXPERIMENTAL=1 (see dlpd_build_flags)");

@@ -183,6 +183,94 @@ template <int L_, int C0, int C1, int H> struct EpiloguePipe {
 };
 
 // ------------------------------------------------------------------------------------------------------
+// EpiloguePipeTC (round 2): the three-stage pipeline of EpiloguePipe with the tcgen05 / TMEM filter in its last stage.  The
+// round-1 pipeline lost because its filter stage was FP32-pipe bound like the transform stage; the tcgen05 scoring is TMEM /
+// latency bound and leaves the FP32 pipe to the transform team.  Role order: scoring team first (its warps must start at a
+// multiple of four: a warp reaches only the TMEM lanes 32 (warp % 4) ..), then the FFT team, then the producers.
+// ------------------------------------------------------------------------------------------------------
+#if !defined(DLPD_EMU)
+template <int L_, int C0, int C1, int H> struct EpiloguePipeTC {
+    typedef Epilogue<L_, C0, C1, H, 1, 2> E;         // half-tile geometry, tcgen05 scoring code
+    typedef EpiloguePipe<L_, C0, C1, H> P0;          // loads, team reductions
+    typedef EpiParams<C0, C1, H> Params;
+    static constexpr int L = L_, N = 2 * L_, N1 = L_, T = L_;
+    static constexpr int NL0 = E::NL0, BUF = N * NL0, HB = N1 * H;
+    static constexpr int NB = 4, NHB = 3;
+    static constexpr int NMLP = E::NC, NFFT = DLPD_PIPE_NFFT, NPROD = DLPD_PIPE_NPROD, PW = NPROD / 2;
+    static constexpr int NT = NMLP + NFFT + NPROD;
+    static constexpr bool OK = E::TC_OK && (N >= 128) && (NMLP == P0::NMLP) && (NFFT == P0::NFFT) && (NPROD == P0::NPROD);
+    static constexpr int SMEM = (NB * BUF + NHB * HB + N) * (int)sizeof(cpx) + 64 * 8 + E::TC_BYTES;
+    static constexpr int BAR_FFT = P0::BAR_FFT, BAR_MLP = P0::BAR_MLP, BAR_FULL = P0::BAR_FULL, BAR_XF = P0::BAR_XF, BAR_FREE = P0::BAR_FREE;
+
+    // grid: x = p.grid persistent CTAs; p.n_tiles = number of 2x2 groups = P * T * T
+    static DLPD_DEV void body(const Params& p, int bx, int, int, char* smem) {
+        cpx* bufs = reinterpret_cast<cpx*>(smem);      // [NB][kz][NL0]
+        cpx* hbufs = bufs + NB * BUF;                  // [NHB][z'][H]
+        cpx* tw0 = hbufs + NHB * HB;
+        unsigned long long* red = reinterpret_cast<unsigned long long*>(tw0 + N);
+        float* Bw = reinterpret_cast<float*>(red + 64);
+        const int my_groups = bx < p.n_tiles ? (p.n_tiles - bx + p.grid - 1) / p.grid : 0;
+        const int n_it = 2 * my_groups;
+        DLPD_FOR_TASKS(t, N, NT) tw0[t] = p.tw0[t];
+        typename E::TcState ts;
+        ts.tmem_base = 0u; ts.phase = 0u;
+        ts.bars = reinterpret_cast<uint64_t*>(Bw + E::TC_BW);
+        ts.team_bar = BAR_MLP; ts.team_threads = NMLP;
+        uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(ts.bars + 16);
+        E::tc_setup(p, Bw, ts.bars, tmem_slot);
+        __syncthreads();
+        tc::fence_after_sync();
+        ts.tmem_base = *tmem_slot;
+        ts.bw_addr = tc::smem_u32(Bw);
+        const int tid = (int)threadIdx.x;
+        if (tid >= NMLP + NFFT) {
+            // ---- producers: group `par` serves the iterations of its parity (buffer index has the same parity)
+            const int par = (tid - NMLP - NFFT) / PW, tp = (tid - NMLP - NFFT) % PW;
+            for (int it = par; it < n_it; it += 2) {
+                const int b = it % NB;
+                if (it >= NB) named_barrier_sync(BAR_FREE + b, PW + NMLP);          // scoring team is done with buffer b
+                P0::issue_loads(p, P0::item(p, bx, it), bufs + b * BUF, hbufs + ((it >> 1) % NHB) * HB, tp);
+                cp_async_commit();
+                cp_async_wait_pending();
+                named_barrier_arrive(BAR_FULL + b, PW + NFFT);
+            }
+        } else if (tid >= NMLP) {
+            // ---- FFT team
+            const SubTeam<NFFT> tm{tid - NMLP, BAR_FFT};
+            for (int it = 0; it < n_it; ++it) {
+                const int b = it % NB;
+                named_barrier_sync(BAR_FULL + b, PW + NFFT);
+                E::transform_tile(tm, bufs + b * BUF, tw0);
+                named_barrier_arrive(BAR_XF + b, NFFT + NMLP);
+            }
+        } else {
+            // ---- scoring team (tcgen05): thread = translation of the half-tile, warpgroup = 128 TMEM lanes
+            const SubTeam<NMLP> tm{tid, BAR_MLP};
+            unsigned long long bestA = ~0ull, bestB = ~0ull;
+            int cur_pair = -1;
+            for (int it = 0; it < n_it; ++it) {
+                const int b = it % NB;
+                const typename P0::Item w = P0::item(p, bx, it);
+                if (w.pair != cur_pair) {
+                    if (cur_pair >= 0) P0::flush_best(p, cur_pair, bestA, bestB, red, tid);
+                    cur_pair = w.pair;
+                    bestA = bestB = ~0ull;
+                }
+                named_barrier_sync(BAR_XF + b, NFFT + NMLP);
+                E::score_voxels_tc(p, tm, bufs + b * BUF, hbufs + ((it >> 1) % NHB) * HB, ts, w.pair, 2 * (w.r4 / T), 2 * (w.r4 % T) + w.half,
+                                   bestA, bestB);
+                if (it + NB < n_it) named_barrier_arrive(BAR_FREE + b, PW + NMLP);
+            }
+            if (cur_pair >= 0) P0::flush_best(p, cur_pair, bestA, bestB, red, tid);
+        }
+        tc::fence_before_sync();
+        __syncthreads();
+        if (threadIdx.x < 32) tc::tmem_dealloc(ts.tmem_base, E::TC_COLS);
+    }
+};
+#endif
+
+// ------------------------------------------------------------------------------------------------------
 // EpilogueFused: the half-tile ring and producer warps of EpiloguePipe, but ONE consumer team whose every thread does, in
 // the same straight-line code, a butterfly task of half-tile it (shared-memory latency bound) AND half of the filter of
 // its voxel of half-tile it - 1 (a pure FFMA2 stream on 2 H accumulators): the instruction scheduler fills the load

@@ -1818,6 +1818,8 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0, bool DUO_ = f
         uint32_t tmem_base, bw_addr;     // TMEM base address, shared-memory address of the weight operand
         uint64_t* bars;                  // [NWG][2]
         uint32_t phase;
+        int team_bar = 0, team_threads = 0;   // > 0: synchronise the staging on this named barrier (whole scoring team) instead of
+                                              // one barrier per warpgroup (callers that have no barrier ids to spare)
     };
     static DLPD_DEV void tc_setup(const Params& p, float* Bw, uint64_t* bars, uint32_t* tmem_slot) {
         DLPD_FOR_TASKS(i, TC_BW, NT) {
@@ -1889,7 +1891,8 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0, bool DUO_ = f
             }
             tc::wait_st();
             tc::fence_before_sync();
-            named_barrier_sync(2 + g, gthreads);
+            if (ts.team_bar > 0) named_barrier_sync(ts.team_bar, ts.team_threads);
+            else named_barrier_sync(2 + g, gthreads);
             if (q == 0 && tc::elect_one()) {
                 tc::fence_after_sync();
                 const uint32_t d = ts.tmem_base + (rot ? colD1 : colD0), a = ts.tmem_base + colA;
@@ -1955,7 +1958,8 @@ template <int L_, int C0, int C1, int H, int TY_ = 2, int FK_ = 0, bool DUO_ = f
         }
 #endif
 #if !defined(DLPD_EMU)
-        TcState ts{0u, 0u, nullptr, 0u};
+        TcState ts;
+        ts.tmem_base = ts.bw_addr = 0u; ts.bars = nullptr; ts.phase = 0u;
         if constexpr (TC_OK) {
             float* Bw = reinterpret_cast<float*>(reinterpret_cast<char*>(red + 64) + MLP_BYTES);
             ts.bars = reinterpret_cast<uint64_t*>(Bw + TC_BW);

@@ -177,6 +177,7 @@ int dlpd_project_typed(const float* coords, const int* num_atoms_of_type, const 
                                        with the filter of its voxel of half-tile i - 1 (N <= 160)                */
 #define DLPD_EPILOGUE_TC_DUO 5      /* experimental builds; tcgen05 filter only: two persistent CTAs per SM on 2x1 half-tiles
                                        (transform passes of one overlap the TMEM staging / MMA waits of the other) */
+#define DLPD_EPILOGUE_PIPE_TC 6     /* experimental builds: load / transform / tcgen05-scoring pipeline on half-tiles   */
 #define DLPD_PLANE_AUTO 0
 #define DLPD_PLANE_SINGLE 1
 #define DLPD_PLANE_CLUSTER 2

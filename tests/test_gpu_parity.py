@@ -541,3 +541,28 @@ def test_search_80_wide_model_matches_oracle():
     best, _ = eng.search(Rs, 30.0)
     eng.close()
     _check_against_oracle(best.cpu(), None, rec, lig, rec_clash, lig_clash, Rs, filt, 30.0)
+
+
+# ---- pipelined epilogue with the tcgen05 scoring stage (experimental builds) -----------------------------------------
+def test_pipe_tc_epilogue_80_matches_oracle_and_default():
+    _need_experimental()
+    _lib.set_option("epilogue_kind", "pipe_tc")
+    try:
+        test_search_full_size_80_matches_oracle()
+    finally:
+        _lib.set_option("epilogue_kind", "auto")
+    L, C0, C1 = 80, 16, 32
+    rec, rec_clash = synthetic.learned_volumes(L, (C0, C1), seed=31)
+    lig, lig_clash = synthetic.learned_volumes(L, (C0, C1), seed=32)
+    filt = O.FilterWeights.random(C0 + C1, seed=33)
+    Rs = R20[torch.arange(33) * 53 + 2]
+    out = []
+    for kind in ("auto", "pipe_tc"):
+        _lib.set_option("epilogue_kind", kind)
+        eng = DockingSearch(L, (C0, C1), max_rot=16, device=DEV)
+        eng.set_receptor(rec, rec_clash); eng.set_ligand(lig, lig_clash); eng.set_filter((filt.W1, filt.b1, filt.W2, filt.b2))
+        out.append(eng.search(Rs, 30.0)[0].cpu())
+        eng.close()
+    _lib.set_option("epilogue_kind", "auto")
+    assert torch.equal(out[0][:, 1:], out[1][:, 1:])
+    assert torch.allclose(out[0][:, 0], out[1][:, 0], rtol=1e-5, atol=1e-6)
