@@ -99,7 +99,7 @@ __global__ void __launch_bounds__(K::NT) dlpd_kernel(const __grid_constant__ typ
     K::body(p, blockIdx.x, blockIdx.y, blockIdx.z, smem);
 }
 template <class K> static int launch(dim3 g, const typename K::Params& p, dlpd_stream_t st) {
-    static bool configured[64] = {};
+    static std::atomic<bool> configured[64];     // zero-initialised; a concurrent first call only repeats the idempotent attribute set
     int dev = 0;
     CU(cudaGetDevice(&dev));
     if (dev < 64 && !configured[dev]) {
@@ -121,7 +121,7 @@ __global__ void __launch_bounds__(K::NT, K::MINB) dlpd_kernel_mb(const __grid_co
 // CARVE: ask for the maximum shared-memory carve-out (kernels that live in shared memory); false for kernels whose
 // global gathers need the L1 cache (FwdZC)
 template <class K, bool CARVE = true> static int launch_mb(dim3 g, const typename K::Params& p, dlpd_stream_t st) {
-    static bool configured[64] = {};
+    static std::atomic<bool> configured[64];     // zero-initialised; a concurrent first call only repeats the idempotent attribute set
     int dev = 0;
     CU(cudaGetDevice(&dev));
     if (dev < 64 && !configured[dev]) {
@@ -166,7 +166,7 @@ __global__ void __launch_bounds__(K::NT, K::MINB) dlpd_cluster_kernel(const __gr
     if (pending) cluster_wait();
 }
 template <class K> static int launch_cluster(unsigned clusters, const typename K::Params& p, dlpd_stream_t st) {
-    static bool configured[64] = {};
+    static std::atomic<bool> configured[64];     // zero-initialised; a concurrent first call only repeats the idempotent attribute set
     int dev = 0;
     CU(cudaGetDevice(&dev));
     if (dev < 64 && !configured[dev]) {
@@ -187,7 +187,7 @@ template <class K> static int launch_cluster(unsigned clusters, const typename K
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    static int resident[64] = {};          // clusters of this kernel the device can hold at once
+    static std::atomic<int> resident[64];     // clusters of this kernel the device can hold at once (0 = not asked yet)
     if (dev < 64 && resident[dev] == 0) {
         int n = 0;
         if (cudaOccupancyMaxActiveClusters(&n, dlpd_cluster_kernel<K>, &cfg) != cudaSuccess || n < 1) { (void)cudaGetLastError(); n = 1 << 30; }

@@ -681,8 +681,13 @@ template <int L_> struct Plane {
                         const Team tm{DLPD_TEAM_TID(TNT), g + 1};
                         cpx* rows = pl + g * (N / G) * NP;
                         PointMul<MulSpec> mul{MulSpec{spec_b + g * (N / G)}};
+#if defined(DLPD_ABLATE_PLANE_YBAR)      // timing experiment (wrong results): the y phase without its two team barriers
+                        team_fwd_head<N, N / G, 1, PP, PKT>(NoSyncTeam<Team>{tm}, rows, htw, LineMul<NP>());
+                        team_mid<N, N / G, 1, PP>(NoSyncTeam<Team>{tm}, rows, tw, LineMul<NP>(), mul);
+#else
                         team_fwd_head<N, N / G, 1, PP, PKT>(tm, rows, htw, LineMul<NP>());                   // along y, rows kx'
                         team_mid<N, N / G, 1, PP>(tm, rows, tw, LineMul<NP>(), mul);                        // y tail . multiply . inverse y tail
+#endif
                         team_inv_head<N, N / G, 1, PP, PKT>(NoSyncTeam<Team>{tm}, rows, htw, LineMul<NP>());  // inverse y; CTA barrier next
                     }
                     DLPD_SYNC();
