@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """parity of the CUDA path on a SEEDED SUBSET of the benchmark's rotation set, on the benchmark's own inputs.
 
-    python tools/parity_sweep.py [--rotations 512] [--seed 512]
+    python tests/sweeps/parity_sweep.py [--rotations 512] [--seed 512]
 
 N rotations drawn without replacement from oim10 (sorted, so the packed pairs mix neighbours of the file order) go through
 `dlpd_search_atoms` on the GPU and through the fp32 oracle (CPU PyTorch `torch.fft`, all host threads) one by one; an index
@@ -15,7 +15,7 @@ import os
 import sys
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402

@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """SURVEY.md 8(f)-2 at the reference's real setting: `Docker(max_conf=2000)` (local_test.py:55) on the benchmark's 80^3 problem.
 
-    python tools/topk_bench.py [--rotations 2048] [--k 2000] [--rot-batch 32] [--parity-rotations 64]
+    python tests/sweeps/topk_bench.py [--rotations 2048] [--k 2000] [--rot-batch 32] [--parity-rotations 64]
 
 Reports rotations/s of the full `dockSE3` (top-K list maintained, pose file written), how the list was maintained (bootstrap /
 candidate / exact batches, candidate-buffer overflows, threshold probes) and -- on the first `--parity-rotations` rotations --
@@ -17,7 +17,7 @@ import sys
 import tempfile
 import time
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 
 import torch  # noqa: E402
