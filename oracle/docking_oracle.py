@@ -42,8 +42,10 @@ def euler_to_matrix(phi: float, theta: float, psi: float) -> torch.Tensor:
 # VolumeRotation  (Docker.py:40,218)   -- PARITY UNPINNED: centre & boundary are our choice
 # --------------------------------------------------------------------------------------
 def rotation_center(L: int, center: str = "grid") -> float:
-    """'box': c = L/2 (voxel i sits at i*res and atoms are centred at box_length/2, Docker.py:34-35);
-    'grid': c = (L-1)/2 (literal torch-1.1 affine_grid/grid_sample, align_corners=True)."""
+    """'grid' (DEFAULT): c = (L-1)/2 -- what `F.affine_grid` + `F.grid_sample` do for either `align_corners` setting
+    (tests/test_oracle_ops.py::test_default_rotation_is_affine_grid_plus_grid_sample), i.e. the construction
+    TorchProteinLibrary's VolumeRotation is built on;
+    'box': c = L/2 (voxel i sits at i*res and atoms are centred at box_length/2, Docker.py:34-35) -- opt-in."""
     if center == "box":
         return L / 2.0
     if center == "grid":
