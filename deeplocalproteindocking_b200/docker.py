@@ -238,25 +238,52 @@ class Docker:
             # candidate-buffer overflows (each costs one exact replay) and threshold probes (one fused search each)
             self.exact_batches = self.candidate_batches = self.bootstrap_batches = self.overflow_batches = self.probe_searches = 0
             cap = max(4 * self.max_conf, 1 << 14)
+            pending = None       # candidate batch in flight: (PendingCandidates, sel, Rb, i0)
+
+            def exact(Rb, sel):
+                """Replay the reference's extraction loop on materialised score volumes (Docker.py:86-105)."""
+                if project:
+                    best, scores = eng.search_atoms(Rb, tau, return_scores=want_topk)
+                else:
+                    best, scores = eng.search(Rb.to(torch.float32), tau, None, return_scores=want_topk)
+                if want_topk:
+                    self.exact_batches += 1
+                    for j, r in enumerate(sel.tolist()):
+                        self.update_top(scores[j], r)
+                return best
+
+            def finish(pend):
+                """Merge a candidate batch that was launched earlier (its list came back through pinned memory meanwhile)."""
+                h, sel_p, Rb_p, i0_p = pend
+                best, cand, total = h.result()
+                if total <= cand.shape[0]:
+                    self._merge_candidates(cand, sel_p, N)
+                    self.candidate_batches += 1
+                else:                                                    # candidate buffer overflowed: redo this batch exactly
+                    self.overflow_batches += 1
+                    best = exact(Rb_p, sel_p)
+                best_all[i0_p:i0_p + sel_p.numel()] = best
+
             for i0 in range(0, rot_idx.numel(), self.rot_batch):
                 sel = rot_idx[i0:i0 + self.rot_batch]
                 Rb = self.rot.R[sel].to(self.device)                     # float64, like r_batch_cpu (Docker.py:214)
-                best = None
                 # Top-K maintenance (Docker.py:86-105).  Once the list is full and its K-th score is negative, only
                 # translations scoring <= that value can enter it: the fused epilogue lists exactly those and the score
-                # volume is never written.  Until then (and if a batch overflows the candidate buffer) the batch is
-                # scored into a volume and the reference's extraction loop is replayed on it.
+                # volume is never written.  The batch is LAUNCHED with the K-th score known at that moment and merged one
+                # iteration later, while the next batch runs (a stale, i.e. larger, threshold only lists a superset).
                 kth = self.top_list[-1][4] if (want_topk and len(self.top_list) == self.max_conf) else None
                 Rq = Rb if project else Rb.to(torch.float32)
                 if want_topk and kth is not None and kth < 0.0:
-                    best, cand, total = eng.search_candidates(Rq, kth, tau, None, capacity=cap, use_atoms=project)
-                    if total <= cand.shape[0]:
-                        self._merge_candidates(cand.cpu(), sel, N)
-                        self.candidate_batches += 1
-                    else:
-                        best = None
-                        self.overflow_batches += 1
-                elif want_topk:
+                    h = eng.search_candidates_async(Rq, kth, tau, None, capacity=cap, use_atoms=project)
+                    if pending is not None:
+                        finish(pending)
+                    pending = (h, sel, Rb, i0)
+                    continue
+                if pending is not None:
+                    finish(pending)
+                    pending = None
+                best = None
+                if want_topk:
                     # list not full yet (first batch): no threshold is known.  Bisect one on the device instead of writing and
                     # sorting rot_batch x (2L)^3 score volumes: a threshold theta < 0 with K <= #{V <= theta} <= capacity makes
                     # the candidate list a superset of the batch's K best translations (Docker.py:100-105 keeps K).
@@ -266,15 +293,10 @@ class Docker:
                         self._merge_candidates(cand.cpu(), sel, N)
                         self.bootstrap_batches += 1
                 if best is None:
-                    if project:
-                        best, scores = eng.search_atoms(Rb, tau, return_scores=want_topk)
-                    else:
-                        best, scores = eng.search(Rb.to(torch.float32), tau, None, return_scores=want_topk)
-                    if want_topk:
-                        self.exact_batches += 1
-                        for j, r in enumerate(sel.tolist()):
-                            self.update_top(scores[j], r)
+                    best = exact(Rb, sel)
                 best_all[i0:i0 + sel.numel()] = best
+            if pending is not None:
+                finish(pending)
             self.best_per_rotation = best_all.cpu()
             if not want_topk:
                 b = self.best_per_rotation

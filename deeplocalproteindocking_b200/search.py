@@ -35,6 +35,27 @@ def _dev_f32(t: torch.Tensor, device, what: str) -> torch.Tensor:
     return t.detach().to(device=device, dtype=torch.float32).contiguous()
 
 
+class PendingCandidates:
+    """Result of `DockingSearch.search_candidates_async`: the candidate list and its count travel to pinned host memory
+    behind an event, so the caller can launch the next batch before it looks at this one."""
+
+    def __init__(self, best, cand, count, capacity, host_cand, host_count, device):
+        self.best, self.capacity = best, int(capacity)
+        self._cand_h, self._count_h = host_cand, host_count
+        self._cand_h.copy_(cand, non_blocking=True)
+        self._count_h.copy_(count, non_blocking=True)
+        self._ev = torch.cuda.Event()
+        self._ev.record(torch.cuda.current_stream(device))
+
+    def result(self) -> Tuple[torch.Tensor, torch.Tensor, int]:
+        """(best [n,4] on the device, candidates [m,3] float64 on the HOST = (score, rotation index, linear index), total)."""
+        self._ev.synchronize()
+        total = int(self._count_h[0])
+        c = self._cand_h[:min(total, self.capacity)]
+        out = torch.stack([c[:, 0].contiguous().view(torch.float32).double(), c[:, 1].double(), c[:, 2].double()], dim=1)
+        return self.best, out, total
+
+
 class DockingSearch:
     """One receptor-ligand pair on one GPU.
 
@@ -189,6 +210,15 @@ class DockingSearch:
         """`search` that also lists every translation with masked score <= `score_max` (the caller's current K-th best,
         Docker.py:100-105).  Returns (best [n,4], candidates [m,3] float64 = (score, rotation index in R, linear index),
         total) -- if total > m == capacity the list is truncated and the caller must redo this batch exactly."""
+        best, out, total = self.search_candidates_async(R, score_max, threshold_clash, ligand_forbidden_rotated, capacity,
+                                                        use_atoms).result()
+        return best, out.to(self.device), total
+
+    def search_candidates_async(self, R: torch.Tensor, score_max: float, threshold_clash: Optional[float] = None,
+                                ligand_forbidden_rotated: Optional[torch.Tensor] = None, capacity: int = 1 << 16,
+                                use_atoms: bool = False) -> PendingCandidates:
+        """The same without waiting: returns a `PendingCandidates` whose `.result()` blocks until THIS batch is done.  Two
+        pinned host buffers are used alternately, so at most two results may be outstanding."""
         tau = self.threshold_clash if threshold_clash is None else float(threshold_clash)
         if use_atoms:        # R float64: clash volumes re-projected inside the library from the atoms of set_ligand_atoms
             Rd = R.detach().to(device=self.device, dtype=torch.float64).contiguous().reshape(-1, 9)
@@ -210,10 +240,11 @@ class DockingSearch:
                 _lib.check(self.lib, self.lib.dlpd_search_candidates(self._h, _ptr(Rd), _ptr(cr), n, tau, float(score_max),
                                                                     _ptr(best), _ptr(cand), int(capacity), _ptr(count),
                                                                     _stream_ptr(self.device)))
-        total = int(count.item())
-        c = cand[:min(total, int(capacity))]
-        out = torch.stack([c[:, 0].contiguous().view(torch.float32).double(), c[:, 1].double(), c[:, 2].double()], dim=1)
-        return best, out, total
+        slots = self._keep.setdefault("cand_host", {})
+        k = self._keep["cand_flip"] = 1 - self._keep.get("cand_flip", 0)
+        if k not in slots or slots[k][0].shape[0] != int(capacity):
+            slots[k] = (torch.empty(int(capacity), 4, dtype=torch.int32).pin_memory(), torch.empty(1, dtype=torch.int32).pin_memory())
+        return PendingCandidates(best, cand, count, capacity, slots[k][0], slots[k][1], self.device)
 
     def search_prerotated(self, lig0_rot: torch.Tensor, lig1_rot: torch.Tensor, ligand_forbidden_rotated: torch.Tensor,
                           threshold_clash: Optional[float] = None, return_scores: bool = False
