@@ -1,12 +1,18 @@
 #!/usr/bin/env python
-"""parity of the CUDA path on a SEEDED SUBSET of the benchmark's rotation set, on the benchmark's own inputs.
+"""parity of the CUDA path on SEEDED SUBSETS of the benchmark configurations' rotation sets, on the
+benchmark's own inputs (bench.py builds them).
 
-    python tests/sweeps/parity_sweep.py [--rotations 512] [--seed 512]
+    python tests/sweeps/parity_sweep.py [--config 2|3|4|5] [--rotations N] [--seed S]
 
-N rotations drawn without replacement from oim10 (sorted, so the packed pairs mix neighbours of the file order) go through
-`dlpd_search_atoms` on the GPU and through the fp32 oracle (CPU PyTorch `torch.fft`, all host threads) one by one; an index
-mismatch is re-examined with the fp64 oracle and only counts if that does not score the two translations within 1e-4 of each
-other.  One JSON line; exit 3 on a real mismatch or a score outside 1e-4 relative."""
+  config 2 / 3  the synthetic-atom pair at 80^3 (calibrated random-init network, re-projected clash volumes), rotations drawn
+                from oim10 / the oim04 surrogate, through `dlpd_search_atoms`
+  config 4      `--pairs` learned-volume pairs at 80^3 switching on ONE plan (set_receptor / set_ligand per pair), rotations
+                drawn from oim06 per pair, rotated clash volume
+  config 5      learned volumes at 128^3, rotations drawn from the oim04 surrogate
+The N rotations (sorted, so packed pairs mix neighbours of the file order) go through the GPU and, one by one, through the fp32
+oracle (CPU PyTorch `torch.fft`, all host threads); an index mismatch is re-examined with the fp64 oracle and only counts if
+that neither scores the two translations within 1e-4 of each other nor puts one of them within 1e-4 of the clash threshold.
+One JSON line; exit 3 on a real mismatch or a score outside 1e-4 relative."""
 from __future__ import annotations
 
 import argparse
@@ -23,44 +29,108 @@ import torch  # noqa: E402
 import bench  # noqa: E402
 
 
-def main():
-    ap = argparse.ArgumentParser()
-    ap.add_argument("--rotations", type=int, default=512)
-    ap.add_argument("--seed", type=int, default=512)
-    args = ap.parse_args()
-    from deeplocalproteindocking_b200 import DockingSearch, rotations
+def sweep(eng, rec_vols, rec_clash, lig_vols, lig_clash, lig_coords, filt_w, tau, Rsub, box, tol=1e-4):
+    """GPU poses vs oracle poses for the rotations Rsub [n,3,3] (float64) of ONE pair already set on `eng`."""
     from oracle import docking_oracle as O
-
-    dev = torch.device("cuda", 0)
-    rec_vols, rec_clash, lig_vols, lig_coords, filt = bench.build_problem(dev)
-    Rall = rotations.Rotations(10).R
-    g = torch.Generator().manual_seed(args.seed)
-    idx = torch.sort(torch.randperm(Rall.shape[0], generator=g)[:args.rotations]).values
-    eng = DockingSearch(80, (16, 32), 24, max_rot=32, device=dev)
-    eng.set_receptor(rec_vols, rec_clash); eng.set_ligand(lig_vols, None); eng.set_filter(filt)
-    eng.set_ligand_atoms(lig_coords, 1.25)
-    best = eng.search_atoms(Rall[idx], bench.TAU)[0].cpu()
-    eng.close()
-    gpu_best = torch.zeros(Rall.shape[0], 4)
-    gpu_best[idx] = best
-
-    torch.set_num_threads(os.cpu_count() or 1)
+    if lig_coords is not None:
+        best = eng.search_atoms(Rsub, tau)[0].cpu()
+    else:
+        best = eng.search(Rsub.float(), tau)[0].cpu()
     cpu = lambda t: t.detach().float().cpu()
-    f = O.FilterWeights(cpu(filt.fc[0].weight), cpu(filt.fc[0].bias), cpu(filt.fc[2].weight), cpu(filt.fc[2].bias))
     spectra = O.ReceptorSpectra([cpu(v)[None] for v in rec_vols], cpu(rec_clash)[None, None])
     ligs = [cpu(v)[None] for v in lig_vols]
-    poses, t0 = [], time.perf_counter()
-    for i in idx.tolist():
-        clash = O.ligand_clash_volume(lig_coords.cpu(), Rall[i], 80, 1.25)
-        V = O.score_rotation(spectra, ligs, clash, Rall[i], f, bench.TAU, ligand_forbidden_is_rotated=True)
-        poses.append((i, O.best_pose(V), float(V.abs().max())))
-    out = bench.parity_block(poses, gpu_best, rec_vols, rec_clash, lig_vols, lig_coords, filt, Rall)
-    out["oracle_seconds"] = time.perf_counter() - t0
-    out["seed"] = args.seed
-    out["distinct_best_translations"] = len({tuple(int(v) for v in best[j, 1:]) for j in range(best.shape[0])})
-    out["against"] = "fp32 oracle (CPU torch.fft), fp64 for ties; %d seeded oim10 rotations, bench.build_problem inputs" % len(poses)
-    print(json.dumps(out), flush=True)
-    if out["index_mismatches"] or out["max_rel_score_err"] > out["tol"]:
+    out = {"rotations": 0, "index_mismatches": 0, "ties_or_mask_flips_within_tol": 0, "max_rel_score_err": 0.0}
+    s64 = None
+    for i in range(Rsub.shape[0]):
+        if lig_coords is not None:
+            clash = O.ligand_clash_volume(lig_coords.cpu(), Rsub[i], box, 1.25)
+            V = O.score_rotation(spectra, ligs, clash, Rsub[i], filt_w, tau, ligand_forbidden_is_rotated=True)
+        else:
+            V = O.score_rotation(spectra, ligs, cpu(lig_clash), Rsub[i], filt_w, tau)
+        s, x, y, z = O.best_pose(V)
+        scale = max(abs(s), 1e-3 * float(V.abs().max()))
+        gi = [int(v) for v in best[i, 1:]]
+        out["rotations"] += 1
+        if gi == [x, y, z]:
+            out["max_rel_score_err"] = max(out["max_rel_score_err"], abs(float(best[i, 0]) - s) / scale)
+            continue
+        d = lambda t: t.detach().double().cpu()
+        if s64 is None:
+            s64 = O.ReceptorSpectra([d(v)[None] for v in rec_vols], d(rec_clash)[None, None])
+            f64 = O.FilterWeights(filt_w.W1.double(), filt_w.b1.double(), filt_w.W2.double(), filt_w.b2.double())
+            ligs64 = [d(v)[None] for v in lig_vols]
+        if lig_coords is not None:
+            c64 = O.ligand_clash_volume(lig_coords.cpu(), Rsub[i], box, 1.25).double()
+            V64 = O.score_rotation(s64, ligs64, c64, Rsub[i], f64, tau, ligand_forbidden_is_rotated=True)
+        else:
+            c64 = O.rotate_volume(d(lig_clash)[None, None], Rsub[i][None].double())[0, 0]
+            V64 = O.score_rotation(s64, ligs64, d(lig_clash), Rsub[i], f64, tau)
+        n = O.correlate(d(rec_clash)[None, None], c64[None, None])[0, 0]
+        a, b = float(V64[x, y, z]), float(V64[gi[0], gi[1], gi[2]])
+        near_tau = min(abs(float(n[x, y, z]) - tau), abs(float(n[gi[0], gi[1], gi[2]]) - tau)) <= tol * float(n.abs().max())
+        if abs(a - b) <= tol * max(abs(a), 1e-3 * float(V64.abs().max())) or near_tau:
+            out["ties_or_mask_flips_within_tol"] += 1
+        else:
+            out["index_mismatches"] += 1
+    return out, best
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--config", type=int, default=2, choices=[2, 3, 4, 5])
+    ap.add_argument("--rotations", type=int, default=512)
+    ap.add_argument("--pairs", type=int, default=4, help="config 4: pairs switching on one plan (rotations are split among them)")
+    ap.add_argument("--seed", type=int, default=512)
+    args = ap.parse_args()
+    from deeplocalproteindocking_b200 import DockingSearch, SimpleFilter, rotations
+    from oracle import docking_oracle as O
+
+    cfg = bench.CONFIGS[args.config]
+    box = cfg["box"]
+    bench.L = box
+    dev = torch.device("cuda", 0)
+    torch.set_num_threads(os.cpu_count() or 1)
+    Rall = rotations.Rotations(cfg["angle_inc"], allow_surrogate=True).R
+    g = torch.Generator().manual_seed(args.seed)
+    total = {"rotations": 0, "index_mismatches": 0, "ties_or_mask_flips_within_tol": 0, "max_rel_score_err": 0.0}
+    distinct = set()
+    t0 = time.perf_counter()
+    eng = DockingSearch(box, (16, 32), 24, max_rot=32, device=dev)
+    if cfg["source"] == "atoms":
+        rec_vols, rec_clash, lig_vols, lig_coords, filt = bench.build_problem(dev)
+        cpu = lambda t: t.detach().float().cpu()
+        fw = O.FilterWeights(cpu(filt.fc[0].weight), cpu(filt.fc[0].bias), cpu(filt.fc[2].weight), cpu(filt.fc[2].bias))
+        idx = torch.sort(torch.randperm(Rall.shape[0], generator=g)[:args.rotations]).values
+        eng.set_receptor(rec_vols, rec_clash); eng.set_ligand(lig_vols, None); eng.set_filter(filt)
+        eng.set_ligand_atoms(lig_coords, 1.25)
+        out, best = sweep(eng, rec_vols, rec_clash, lig_vols, None, lig_coords, fw, bench.TAU, Rall[idx], box)
+        for k in total:
+            total[k] = max(total[k], out[k]) if k == "max_rel_score_err" else total[k] + out[k]
+        distinct |= {tuple(int(v) for v in best[j, 1:]) for j in range(best.shape[0])}
+        what = "bench.build_problem inputs, re-projected clash volumes, dlpd_search_atoms"
+    else:
+        torch.manual_seed(1234 + args.config)
+        filt = SimpleFilter([16, 32])
+        cpu = lambda t: t.detach().float().cpu()
+        fw = O.FilterWeights(cpu(filt.fc[0].weight), cpu(filt.fc[0].bias), cpu(filt.fc[2].weight), cpu(filt.fc[2].bias))
+        eng.set_filter(filt)
+        n_pairs = args.pairs if cfg["pairs"] > 1 else 1
+        per = max(1, args.rotations // n_pairs)
+        for visit in range(n_pairs):
+            rec, rec_clash, lig, lig_clash = bench.build_learned_pair(box, 1000 * args.config + visit, dev)
+            idx = torch.sort(torch.randperm(Rall.shape[0], generator=g)[:per]).values
+            eng.set_receptor(rec, rec_clash); eng.set_ligand(lig, lig_clash)
+            out, best = sweep(eng, rec, rec_clash, lig, lig_clash, None, fw, 30.0, Rall[idx], box)
+            for k in total:
+                total[k] = max(total[k], out[k]) if k == "max_rel_score_err" else total[k] + out[k]
+            distinct |= {(visit,) + tuple(int(v) for v in best[j, 1:]) for j in range(best.shape[0])}
+        what = "bench.build_learned_pair inputs (%d pair%s on one plan), rotated clash volume" % (n_pairs, "s" if n_pairs > 1 else "")
+    eng.close()
+    total.update(tol=1e-4, config=args.config, box=box, rotation_set="oim%02d%s" % (cfg["angle_inc"], " (surrogate)" if cfg["angle_inc"] == 4 else ""),
+                 seed=args.seed, seconds=time.perf_counter() - t0, distinct_best_translations=len(distinct),
+                 against="fp32 oracle (CPU torch.fft), fp64 for ties / mask flips; " + what)
+    print(json.dumps(total), flush=True)
+    if total["index_mismatches"] or total["max_rel_score_err"] > total["tol"]:
         sys.exit(3)
 
 
