@@ -53,6 +53,12 @@
 #ifndef DLPD_PLANE_TEAMS
 #define DLPD_PLANE_TEAMS 5
 #endif
+#ifndef DLPD_PLANE_TEAMS_128
+#define DLPD_PLANE_TEAMS_128 1       // teams of the 128 x 128 plane (Plane<64>: level 1 of the 128^3 box); 1 = whole-CTA passes
+#endif
+#ifndef DLPD_PLANE_NT_128
+#define DLPD_PLANE_NT_128 512        // threads of Plane<64> when it runs in teams
+#endif
 #ifndef DLPD_PLANE_DUAL
 #define DLPD_PLANE_DUAL 1            // two butterfly tasks per iteration in Plane's plain passes (needs registers: 640 threads x 96)
 #endif
@@ -554,13 +560,14 @@ template <int L_> struct Plane {
     typedef PlaneParams Params;
     static constexpr int L = L_, N = 2 * L_, NP = N + 1;     // odd pitch: conflict-free along both axes
     typedef PlanePlan<N> PP;                                 // factorisation of the x / y lines
-    static constexpr int NT = (N >= 128) ? DLPD_PLANE_NT : ((N >= 64) ? DLPD_PLANE_NT_MID : 256);   // 640 = 5 teams x 128: whole head passes per round, <= 102 registers
+    static constexpr int TEAMS = (N == 128) ? DLPD_PLANE_TEAMS_128 : DLPD_PLANE_TEAMS;
+    static constexpr int NT = (N == 128 && TEAMS > 1) ? DLPD_PLANE_NT_128
+                            : ((N >= 128) ? DLPD_PLANE_NT : ((N >= 64) ? DLPD_PLANE_NT_MID : 256));   // 640 = 5 teams x 128: whole head passes per round, <= 102 registers
     static constexpr bool PKT = DLPD_PLANE_PACKED_TW && (N >= 128);       // packed head-pass twiddles (team path)
     static constexpr int SMEM = (N * NP + N + (PKT ? N : 0)) * (int)sizeof(cpx);
     static constexpr int MINB = (SMEM <= 56 * 1024) ? 4 : 1;   // resident CTAs per SM the register budget is cut for
     // teams (see body): only for the big plane, and only when rows, columns and threads split evenly
-    static constexpr int G = (N >= 128 && N % DLPD_PLANE_TEAMS == 0 && L_ % DLPD_PLANE_TEAMS == 0 && NT % (32 * DLPD_PLANE_TEAMS) == 0)
-                                 ? DLPD_PLANE_TEAMS : 1;
+    static constexpr int G = (N >= 128 && N % TEAMS == 0 && L_ % TEAMS == 0 && NT % (32 * TEAMS) == 0) ? TEAMS : 1;
     static constexpr int TNT = NT / G;
     static constexpr int PFT = (G > 1) ? TNT : NT;           // threads that issue the prefetches
     // DLPD_ABLATE_* (never defined in the shipped build): timing experiments that remove one memory stream at a time
