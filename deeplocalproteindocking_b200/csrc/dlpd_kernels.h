@@ -50,11 +50,18 @@
 #ifndef DLPD_HID_NT
 #define DLPD_HID_NT 512
 #endif
+#ifndef DLPD_HID_YT_BIG
+#define DLPD_HID_YT_BIG 2            // HiddenL1 at N1 >= 128 (level 1 of the 128^3 box): 2-line tiles of 70 KB, three CTAs of 256 threads per SM
+#endif                               // instead of one 135 KB CTA of 512: 6.16 -> 5.21 ms (2 lines x 512 threads 5.70, x 384 5.25)
+#ifndef DLPD_HID_NT_BIG
+#define DLPD_HID_NT_BIG 256
+#endif
 #ifndef DLPD_PLANE_TEAMS
 #define DLPD_PLANE_TEAMS 5
 #endif
 #ifndef DLPD_PLANE_TEAMS_128
-#define DLPD_PLANE_TEAMS_128 1       // teams of the 128 x 128 plane (Plane<64>: level 1 of the 128^3 box); 1 = whole-CTA passes
+#define DLPD_PLANE_TEAMS_128 4       // teams of the 128 x 128 plane (Plane<64>: level 1 of the 128^3 box): 5.83 ms with whole-CTA passes of 640
+                                     // threads (1) -> 4.97 with 4 x 128 threads; 2 x 256: 5.13, 4 x 160: 5.19, 8 x 64: 5.73
 #endif
 #ifndef DLPD_PLANE_NT_128
 #define DLPD_PLANE_NT_128 512        // threads of Plane<64> when it runs in teams
@@ -1231,11 +1238,11 @@ template <int C0, int C1, int H> struct HidParams {
 // warpgroup's 32 A columns (hi | lo), accumulating over the C1 / 16 rounds; two CTAs per SM share the 512 TMEM columns.
 template <int L_, int C0, int C1, int H, int FK_ = 0> struct HiddenL1 {
     typedef HidParams<C0, C1, H> Params;
-    static constexpr int N1 = L_, YT = DLPD_HID_YT, NL = C1 * YT;
+    static constexpr int N1 = L_, YT = (L_ >= 128) ? DLPD_HID_YT_BIG : DLPD_HID_YT, NL = C1 * YT;
     static constexpr int P1 = NL + 4;                        // row pitch: 16-byte rows, conflict-free (yl, z1) reads
     static constexpr int JG = (H % 8 == 0) ? 8 : H;          // hidden units per task
     static constexpr int VP = (YT * N1 + 31) / 32 * 32;      // (yl, z1) padded to whole warps (warp-uniform hidden group)
-    static constexpr int NT = (N1 >= 64) ? DLPD_HID_NT : 128;
+    static constexpr int NT = (N1 >= 128) ? DLPD_HID_NT_BIG : ((N1 >= 64) ? DLPD_HID_NT : 128);
     static constexpr bool PKT = DLPD_HID_PACKED_TW && (N1 / (2 * LinePlan<N1>::R0) > 1);
     // tcgen05 path
     static constexpr int NVOX = YT * N1, NSC = VP, NWG = (NVOX + 127) / 128, HP = (H + 7) / 8 * 8, KH = 16;
