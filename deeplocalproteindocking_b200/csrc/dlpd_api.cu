@@ -213,11 +213,12 @@ template <class K> static int launch_cluster(unsigned clusters, const typename K
 template <int L> struct Tile {
     static constexpr int FWD_YT = (L <= 40) ? L : ((L % 40 == 0) ? 40 : 32);      // y lines per FwdZ CTA
     static constexpr int INV_YT = ((2 * L) % 8 == 0) ? 8 : (((2 * L) % 4 == 0) ? 4 : 2);
-    // y lines per FwdZC CTA (4 at L = 128: 68 KB of shared memory, three resident CTAs instead of one)
+    // y lines per FwdZC CTA.  At L = 128: 8 lines = one 132 KB CTA of 1024 threads per SM, 7.88 ms; 4 lines (68 KB, three
+    // resident CTAs of 256 threads) 8.55; 4 x 512 threads 8.60; 4 x 384 8.75; 2 lines 11.6  (profiles/r02/cfg5_variants)
 #ifdef DLPD_CL_YT
     static constexpr int CL_YT = (L % DLPD_CL_YT == 0) ? DLPD_CL_YT : 2;
 #else
-    static constexpr int CL_YT = (L >= 128) ? 4 : ((L % 8 == 0) ? 8 : ((L % 4 == 0) ? 4 : 2));
+    static constexpr int CL_YT = (L % 8 == 0) ? 8 : ((L % 4 == 0) ? 4 : 2);
 #endif
 #ifdef DLPD_CL_CG
     static constexpr int CL_CG = DLPD_CL_CG;

@@ -486,7 +486,8 @@ template <int L_, int CG_, int YT_> struct FwdZC {
     typedef FwdZCParams Params;
     static constexpr int L = L_, N = 2 * L_, CG = CG_, YT = YT_, YTILES = L_ / YT_, CQ = CG_ / 4;
     static constexpr int CS = N * YT + 8;          // per-channel stride: +8 keeps 4 channel groups of a warp on distinct banks
-    static constexpr int NT = (L_ >= 80 && YT_ >= 8) ? 2 * DLPD_FWDZC_NT : DLPD_FWDZC_NT;   // 512 at L = 80: 1.51 vs 1.62 ms; worse at L = 40
+    static constexpr int NT = (L_ >= 128 && YT_ >= 8) ? 4 * DLPD_FWDZC_NT                      // 1024 at L = 128 (one 132 KB CTA per SM): 7.88 ms vs 8.25 at 512
+                            : ((L_ >= 80 && YT_ >= 8) ? 2 * DLPD_FWDZC_NT : DLPD_FWDZC_NT);   // 512 at L = 80: 1.51 vs 1.62 ms; worse at L = 40
     static constexpr bool PKT = DLPD_FWDZ_PACKED_TW && (N / (2 * LinePlan<N>::R0) > 1);
     static constexpr int SMEM = (CG * CS + N + (PKT ? N : 0)) * (int)sizeof(cpx);
     static constexpr int MINB = 1024 / NT;         // resident CTAs the register budget is cut for (64 registers per thread)
