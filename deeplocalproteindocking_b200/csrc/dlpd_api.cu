@@ -153,11 +153,20 @@ __global__ void __launch_bounds__(K::NT, K::MINB) dlpd_cluster_kernel(const __gr
     for (int cid = (int)(blockIdx.x / K::CL); cid < n_items; cid += step) {
         K::phase_a(p, cid, rank, smem, cid + step < n_items ? cid + step : -1, pending);
         if (exch) {
+#if DLPD_PLANEX_LEAD_RELEASE
+            if (threadIdx.x < 32) cluster_arrive(); else cluster_arrive_relaxed();
+            cluster_wait();
+#else
             cl.sync();
+#endif
             K::phase_b(p, cid, rank, slabs, smem);
             // nobody re-fills (or leaves) while its shared memory is still being read: arrive now, wait inside the next
             // item's phase A (after its prefetches) or before leaving
+#if DLPD_PLANEX_RELAXED_ARRIVE
+            cluster_arrive_relaxed();
+#else
             cluster_arrive();
+#endif
             pending = true;
         } else {
             __syncthreads();

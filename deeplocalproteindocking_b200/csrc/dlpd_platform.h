@@ -45,6 +45,7 @@
   static inline void named_barrier_arrive(int, int) {}
   static inline void store_cpx2(float2* dst, float2 a, float2 b) { dst[0] = a; dst[1] = b; }
   static inline void cluster_arrive() {}
+  static inline void cluster_arrive_relaxed() {}
   static inline void cluster_wait() {}
   static inline unsigned int atomic_inc_u32(unsigned int* p) { return (*p)++; }
   static inline void atomic_add_f32(float* p, float v) { *p += v; }
@@ -94,6 +95,9 @@
   // split cluster barrier: arrive (release) when this CTA no longer reads its peers' shared memory, wait (acquire) only
   // right before it overwrites its own
   DLPD_DEV void cluster_arrive() { asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory"); }
+  // arrive without memory ordering: for a barrier that only says "I have finished READING my peers' shared memory" (the values are
+  // already in registers), so that the arrive does not wait for this thread's outstanding global stores
+  DLPD_DEV void cluster_arrive_relaxed() { asm volatile("barrier.cluster.arrive.relaxed.aligned;" ::: "memory"); }
   DLPD_DEV void cluster_wait() { asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory"); }
   DLPD_DEV unsigned int atomic_inc_u32(unsigned int* p) { return atomicAdd(p, 1u); }
   DLPD_DEV void atomic_add_f32(float* p, float v) { atomicAdd(p, v); }
