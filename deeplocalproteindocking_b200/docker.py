@@ -102,7 +102,7 @@ def top_conformations(V: torch.Tensor, K: int) -> List[Tuple[int, int, int, floa
 
 class Docker:
     def __init__(self, docking_model, angle_inc=15.0, box_size=80, resolution=1.25, max_conf=1000, randomize_rot=False,
-                 rot_batch: int = 16, center: str = "grid", clash_source: str = "project",
+                 rot_batch: int = 32, center: str = "grid", clash_source: str = "project",
                  pdb_loader: Optional[Callable[[str], Atoms]] = None, device=None, generator=None, verbose=False):
         """Reference arguments first (Docker.py:18); then: `rot_batch` rotations per fused call, rotation `center`
         convention ('grid' = what TorchProteinLibrary's grid_sample-based VolumeRotation does, default; 'box' opt-in),
@@ -237,7 +237,7 @@ class Docker:
             # epilogue's candidate list at the current K-th score, batches whose threshold had to be bootstrapped by probing,
             # candidate-buffer overflows (each costs one exact replay) and threshold probes (one fused search each)
             self.exact_batches = self.candidate_batches = self.bootstrap_batches = self.overflow_batches = self.probe_searches = 0
-            cap = max(4 * self.max_conf, 1 << 14)
+            cap = max(4 * self.max_conf, 1 << 17)      # 2 MB of candidates: the first batches after the bootstrap run on a loose threshold
             pending = None       # candidate batch in flight: (PendingCandidates, sel, Rb, i0)
 
             def exact(Rb, sel):
@@ -264,9 +264,12 @@ class Docker:
                     best = exact(Rb_p, sel_p)
                 best_all[i0_p:i0_p + sel_p.numel()] = best
 
+            # float64 like r_batch_cpu (Docker.py:214); uploaded ONCE: a pageable host-to-device copy per batch would make the host
+            # wait for the stream at every batch and drain the launch queue
+            R_all = self.rot.R[rot_idx].to(self.device)
             for i0 in range(0, rot_idx.numel(), self.rot_batch):
                 sel = rot_idx[i0:i0 + self.rot_batch]
-                Rb = self.rot.R[sel].to(self.device)                     # float64, like r_batch_cpu (Docker.py:214)
+                Rb = R_all[i0:i0 + self.rot_batch]
                 # Top-K maintenance (Docker.py:86-105).  Once the list is full and its K-th score is negative, only
                 # translations scoring <= that value can enter it: the fused epilogue lists exactly those and the score
                 # volume is never written.  The batch is LAUNCHED with the K-th score known at that moment and merged one
@@ -334,6 +337,10 @@ class Docker:
         """Merge (score, position in `sel`, linear index) candidates into the global list: same order as appending each
         rotation's extraction list and stable-sorting by score (Docker.py:100-105) -- ties keep rotation order, then
         row-major voxel order (Docker.py:91-96)."""
+        if cand.shape[0] > self.max_conf:        # long list (loose threshold): only its K best rows can enter -- cut it with tensor sorts
+            for col in (2, 1, 0):                # stable sorts, least significant key first = order by (score, rotation, voxel)
+                cand = cand[torch.argsort(cand[:, col], stable=True)]
+            cand = cand[:self.max_conf]
         rows = sorted(((float(s), int(j), int(lin)) for s, j, lin in cand.tolist()), key=lambda t: (t[0], t[1], t[2]))
         sel_l = sel.tolist()
         for s, j, lin in rows:

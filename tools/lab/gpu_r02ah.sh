@@ -1,0 +1,10 @@
+#!/bin/bash
+# round 2, visit ah: the same with a 131072-entry candidate buffer and tensor-sorted truncation of long lists: docker tests, top-K run
+# at K = 2000 over 4096 rotations and over the whole oim10 set
+set -u
+OUT=gpurun_out/r02ah; mkdir -p $OUT
+timeout 900 python -m pytest tests/test_gpu_docker.py tests/test_gpu_round2.py -m gpu -q -x -k "dock" > $OUT/pytest_docker.log 2>&1; echo "pytest rc=$?" >> $OUT/pytest_docker.log; tail -3 $OUT/pytest_docker.log
+timeout 1200 python tests/sweeps/topk_bench.py --rotations 4096 --k 2000 --parity-rotations 96 > $OUT/topk_rb32.log 2>&1; echo "topk rc=$?" >> $OUT/topk_rb32.log
+tail -c 1800 $OUT/topk_rb32.log
+timeout 1200 python tests/sweeps/topk_bench.py --rotations 14868 --k 2000 --parity-rotations 0 > $OUT/topk_full.log 2>&1; echo "topk rc=$?" >> $OUT/topk_full.log
+tail -c 1200 $OUT/topk_full.log
