@@ -849,6 +849,9 @@ DLPD_XPLAN(64, 8, 8)
 #ifndef DLPD_PLANEX_KEEP_TW
 #define DLPD_PLANEX_KEEP_TW 1          // persistent clusters copy the twiddle table once instead of once per plane (one CTA barrier less): 37.4 -> 37.05 ms
 #endif
+#ifndef DLPD_PLANEX_SKIP_LAST_SYNC
+#define DLPD_PLANEX_SKIP_LAST_SYNC 0
+#endif
 #ifndef DLPD_PLANEX_LEAD_RELEASE
 #define DLPD_PLANEX_LEAD_RELEASE 0     // barrier before the exchange phase: only warp 0 arrives .release (the CTA barrier that ends phase A
 #endif                                 // has already ordered every thread's shared-memory writes before it), the others .relaxed
@@ -963,7 +966,11 @@ template <int L_, int CL_> struct PlaneX {
         fft_mid<N, M, 1, NT>(pl, tw, LineMul<NP>(), mul);                       // y tail . multiply . inverse y tail
         fft_inv_head<N, M, 1, NT>(pl, tw, LineMul<NP>());                       // inverse y
         if constexpr (XB > 1) fft_pass<PASS_DIT, XB, 1, N, M, XB, N, NP, NT>(pl, tw, LineMul<1>());
+#if DLPD_PLANEX_SKIP_LAST_SYNC      // the cluster barrier that follows phase A is a CTA barrier as well: the pass needs none of its own
+        fft_pass_team<PASS_DIT, XA, 1, N, M, M, N, NP>(NoSyncTeam<CtaTeam<NT> >{CtaTeam<NT>()}, pl, tw, LineMul<1>());
+#else
         fft_pass<PASS_DIT, XA, 1, N, M, M, N, NP, NT>(pl, tw, LineMul<1>());    // A_q = IFFT_M along x, all columns
+#endif
     }
 
     // last inverse-x step across the slabs of the cluster (slabs[r] = CTA r's plane buffer) for the row pairs
