@@ -257,3 +257,29 @@ def test_pose_file_round_trip_and_application(tmp_path):
     out = poses.transform_ligand(centred, nat, got[1])
     R, t, _ = got[1]
     assert torch.allclose(out[0, :3], R[0] @ centred[0, :3] + t[0]) and torch.equal(out[0, 6:], coords[0, 6:])
+
+
+def test_candidate_merge_equals_append_and_stable_sort():
+    """`Docker._merge_candidates` (global top-K from the epilogue's candidate lists) must give what the reference gives: append
+    every rotation's extractions in rotation order, stable-sort by score, keep K (Docker.py:100-105) -- including for lists
+    much longer than K, which are cut with tensor sorts before the Python merge, and with tied scores."""
+    import random
+    import types
+    random.seed(3)
+    N, K = 12, 25
+    holder = types.SimpleNamespace(top_list=[], max_conf=K)
+    reference = []
+    sel = torch.tensor([40, 41, 42, 43, 44, 45, 46, 47])
+    for batch in range(3):
+        m = [400, 7, 60][batch]                                  # one long list (cut by tensor sorts), one short, one medium
+        rows = [(random.choice([-1.0, -2.0, -3.5, -0.25, -7.0 + batch]), random.randrange(8), random.randrange(N ** 3)) for _ in range(m)]
+        rows = list({(j, lin): (s, j, lin) for s, j, lin in rows}.values())     # a (rotation, voxel) pair occurs once
+        random.shuffle(rows)                                     # the device appends in arbitrary order
+        cand = torch.tensor(rows, dtype=torch.float64)
+        dk.Docker._merge_candidates(holder, cand, sel + 8 * batch, N)
+        # reference order: rotations in batch order, each rotation's voxels in row-major order, then ONE stable sort by score
+        for s, j, lin in sorted(rows, key=lambda t: (t[1], t[2])):
+            reference.append((int(sel[j]) + 8 * batch, lin // (N * N), (lin // N) % N, lin % N, s))
+        reference.sort(key=lambda t: t[4])
+        reference = reference[:K]
+        assert holder.top_list == reference
